@@ -1,0 +1,115 @@
+/* libnpcd_b200 -- C ABI of the B200-native PointNeRF render path (drop-in for the renderer call of
+ * lmb-freiburg/neural-point-cloud-diffusion, `npcd/models/pointnerf/pointnerf.py:89-97,126`).
+ *
+ * Conventions:
+ *   - every function returns 0 on success, non-zero on argument (1) or CUDA (2) error; `npcd_last_error()` gives the message.
+ *     The reference's convention is Python asserts/exceptions (e.g. `fields/aggregators/aggregator.py:17`,
+ *     `renderers/renderer.py:163`); the Python shim turns a non-zero code into `RuntimeError`.
+ *   - all buffers are caller-allocated DEVICE pointers (torch tensors' `data_ptr()`), row-major contiguous, fp32 unless noted;
+ *     kernels never allocate; `stream` is a `cudaStream_t` (pass `torch.cuda.current_stream().cuda_stream`); calls are
+ *     asynchronous with respect to the host.
+ *   - no torch types, no global state (apart from a thread-local error string).
+ *
+ * Reference paths below are relative to /root/reference/npcd/models/pointnerf/.
+ */
+#ifndef NPCD_B200_H
+#define NPCD_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NPCD_B200_ABI_VERSION 1
+
+const char* npcd_last_error(void);
+int npcd_abi_version(void);
+
+/* ---- R1 + R2: rays and ray/cube limits ------------------------------------------------------------------------------------
+ * Replaces RaySampler.forward (renderers/ray_sampler.py:10-63), get_ray_limits_box (renderers/math_utils.py:46-97) and
+ * Renderer.get_ray_limits (renderers/renderer.py:36-47), including the train-mode ray subset gather (renderer.py:232-238).
+ *   extr [n_views,4,4] world->cam, intr [n_views,3,3]; ray_subset: NULL, or [n_subset] int64 pixel ids shared by all views.
+ *   cam_centers [n_views,3]; origins [n_views,R,3] (optional, may be NULL: every ray of a view starts at its camera centre);
+ *   dirs [n_views,R,3]; ray_start/ray_end [n_views,R]; limits_scratch: 8 bytes of device scratch.  R = n_subset or res^2.  */
+int npcd_rays_generate(const float* extr, const float* intr, int n_views, int resolution, const long long* ray_subset,
+                       int n_subset, float cube_scale, float* cam_centers, float* origins, float* dirs, float* ray_start,
+                       float* ray_end, void* limits_scratch, void* stream);
+
+/* ---- grid build: replaces torch_knnquery.VoxelGrid.set_pointset (call sites pointnerf.py:67-75,116-124) ---------------------
+ *   kp_pos [n_obj,P,3] -> cell_start [n_obj, cells+1] int32, sorted_pts [n_obj,P,4] (x,y,z,index bits),
+ *   occ_bits [n_obj, words] uint32; `npcd_grid_dims` reports cells / words.                                                   */
+int npcd_grid_dims(int* cells, int* words);
+int npcd_grid_build(const float* kp_pos, int n_obj, int n_points, int* cell_start, float* sorted_pts, unsigned* occ_bits,
+                    void* stream);
+
+/* ---- march + exact radius-kNN: replaces Aggregator.query_keypoints (fields/aggregators/aggregator.py:25-76) and
+ * torch_knnquery.VoxelGrid.query (call site aggregator.py:63), with the depth sampling that feeds them
+ * (renderers/renderer.py:49-77, renderers/volume_renderer.py:63-70).
+ *   pass 1  npcd_march_count: per ray a 128-bit mask of samples having >= 1 point within `radius` and
+ *           ray_count = min(popcount, max_shading_pts).           jitter: NULL or [n_rays,128] U[0,1) (renderer.py:74-76).
+ *   scan    npcd_scan_counts: ray_offset[0..n] (int64) over ray_count[ray_ids[i]] (ray_ids NULL = identity).
+ *   pass 2  npcd_knn_fill: for the kept samples s < min(ray_offset[n_sel], capacity):
+ *           nbr_idx [S,8] int32 (global b*P+p, ascending (distance, index), -1 padded), sample_pos [S,4] = (x,y,z,slot depth),
+ *           sample_ray [S] int32 (optional).                                                                                  */
+int npcd_march_count(const float* cam_centers, const float* dirs, const float* ray_start, const float* ray_end,
+                     const float* jitter, long long n_rays, int rays_per_view, int views_per_obj, int n_points,
+                     const int* cell_start, const float* sorted_pts, const unsigned* occ_bits, float radius, int max_shading_pts,
+                     unsigned* valid_bits, int* ray_count, void* stream);
+int npcd_scan_workspace_bytes(long long n, size_t* bytes);
+int npcd_scan_counts(const int* ray_count, const int* ray_ids, long long n, long long* ray_offset, void* workspace,
+                     size_t workspace_bytes, void* stream);
+/* Generic exact query on explicit positions x [n,3] (object of query i = query_obj ? query_obj[i] : i / queries_per_obj);
+ * used by the TV-loss self-query (npcd/losses/neural_point_cloud_tv_loss.py:41-44) and by Aggregator.query_keypoints. */
+int npcd_knn_points(const float* x, const int* query_obj, long long n, int queries_per_obj, int n_points, const int* cell_start,
+                    const float* sorted_pts, float radius, int* nbr_idx, void* stream);
+int npcd_knn_fill(const float* cam_centers, const float* dirs, const float* ray_start, const float* ray_end, const float* jitter,
+                  const int* ray_ids, long long n_sel, const long long* ray_offset, const unsigned* valid_bits, int rays_per_view,
+                  int views_per_obj, int n_points, const int* cell_start, const float* sorted_pts, float radius,
+                  long long capacity, int* nbr_idx, float* sample_pos, int* sample_ray, void* stream);
+
+/* ---- field: gather + posenc + pair MLP + aggregation + density/colour heads -------------------------------------------------
+ * Replaces aggregators.MLP.get_local_feat / aggregate_local_feat (fields/aggregators/mlp.py:36-125), Aggregator.get_keypoint_data
+ * (aggregator.py:121-144), fields.MLP.get_shape / get_channels (fields/mlp.py:38-72) and the activations of Field.forward
+ * (fields/field.py:126-141).  rgbs [S,4] = (r, g, b, sigma).  n_samples_dev: device int64 (= ray_offset + n_sel).
+ * fp32 SIMT version: weights pre-transposed to [in, 256] ("wt"), first layer zero-padded to a multiple of 16 rows.            */
+typedef struct {
+  int feat_dim;
+  const float* pair_wt[4]; /* local_field.0,2,4,6 */
+  const float* pair_b[4];
+  const float* agg_wt; /* local_field.8, applied after the weighted aggregation (weights sum to 1) */
+  const float* agg_b;
+  const float* shape_wt; /* shape_net.0 */
+  const float* shape_b;
+  const float* shape_out_w; /* shape_net.2 weight [256] */
+  const float* shape_out_b; /* [1] */
+  const float* chan_wt[4];  /* channel_net.0,2,4,6 */
+  const float* chan_b[4];
+  const float* chan_out_w; /* channel_net.8 weight [3,256] */
+  const float* chan_out_b; /* [3] */
+} npcd_mlp_simt_weights;
+
+int npcd_field_simt_fwd(const int* nbr_idx, const float* sample_pos, const float* kp_pos, const float* kp_feat,
+                        const long long* n_samples_dev, long long capacity, const npcd_mlp_simt_weights* weights,
+                        float* agg_workspace /* [capacity,256] */, float* rgbs, float* feat_out /* optional [S,256] */,
+                        int stages /* bit0: pair MLP + aggregation -> agg_workspace, bit1: heads -> rgbs; 3 = both */,
+                        int num_sms, void* stream);
+
+/* ---- compositing: replaces Renderer.get_depths_from_shading_pts (renderers/renderer.py:95-110), VolumeRenderer.get_alpha
+ * (renderers/volume_renderer.py:23-39), Renderer.ray_march (renderers/renderer.py:120-185).
+ *   out_mask [n_sel], out_depth [n_sel] (UNCLAMPED, NaN -> +inf), out_rgb [n_sel,3]; range_scratch (8 bytes) accumulates the
+ *   global slot-depth range (init_range != 0 resets it first, so several view chunks can share one range);
+ *   npcd_clamp_depth then applies renderer.py:154-156 and records out_clamped [n] u8 (optional; needed by the backward).
+ *   Backward: g_* may be NULL; g_rgbs [S,4] = d/d(r,g,b,sigma).                                                                */
+int npcd_composite_fwd(const float* sample_pos, const float* rgbs, const long long* ray_offset, const int* ray_ids,
+                       const float* ray_end, long long n_sel, int white_back, float* out_mask, float* out_depth, float* out_rgb,
+                       void* range_scratch, int init_range, void* stream);
+int npcd_clamp_depth(float* depth, long long n, const void* range_scratch, unsigned char* out_clamped, void* stream);
+int npcd_composite_bwd(const float* sample_pos, const float* rgbs, const long long* ray_offset, long long n_sel, int white_back,
+                       const float* g_rgb, const float* g_mask, const float* g_depth, const float* out_mask,
+                       const float* out_depth, const unsigned char* clamped, float* g_rgbs, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPCD_B200_H */

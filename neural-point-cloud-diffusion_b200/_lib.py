@@ -1,0 +1,109 @@
+"""ctypes binding of the C-ABI library ``libnpcd_b200.so`` (declared in ``include/npcd_b200.h``).
+
+There is NO fallback: if the library cannot be loaded (or built with nvcc) every op raises ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnpcd_b200.so")
+ABI_VERSION = 1
+
+_lock = threading.Lock()
+_lib = None
+
+P = C.c_void_p
+I = C.c_int
+L = C.c_longlong
+F = C.c_float
+
+
+class SimtWeights(C.Structure):
+    """mirror of ``npcd_mlp_simt_weights``"""
+
+    _fields_ = [
+        ("feat_dim", C.c_int),
+        ("pair_wt", P * 4),
+        ("pair_b", P * 4),
+        ("agg_wt", P),
+        ("agg_b", P),
+        ("shape_wt", P),
+        ("shape_b", P),
+        ("shape_out_w", P),
+        ("shape_out_b", P),
+        ("chan_wt", P * 4),
+        ("chan_b", P * 4),
+        ("chan_out_w", P),
+        ("chan_out_b", P),
+    ]
+
+
+# name -> argtypes; every entry point declared in include/npcd_b200.h (tests check the header against this table)
+SIGNATURES = {
+    "npcd_rays_generate": [P, P, I, I, P, I, F, P, P, P, P, P, P, P],
+    "npcd_grid_dims": [P, P],
+    "npcd_grid_build": [P, I, I, P, P, P, P],
+    "npcd_march_count": [P, P, P, P, P, L, I, I, I, P, P, P, F, I, P, P, P],
+    "npcd_scan_workspace_bytes": [L, P],
+    "npcd_scan_counts": [P, P, L, P, P, C.c_size_t, P],
+    "npcd_knn_fill": [P, P, P, P, P, P, L, P, P, I, I, I, P, P, F, L, P, P, P, P],
+    "npcd_knn_points": [P, P, L, I, I, P, P, F, P, P],
+    "npcd_field_simt_fwd": [P, P, P, P, P, L, P, P, P, P, I, I, P],
+    "npcd_composite_fwd": [P, P, P, P, P, L, I, P, P, P, P, I, P],
+    "npcd_clamp_depth": [P, L, P, P, P],
+    "npcd_composite_bwd": [P, P, P, L, I, P, P, P, P, P, P, P, P],
+}
+
+
+def load():
+    """Returns the loaded library; builds it with nvcc if the .so is absent; raises if neither works."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.isfile(LIB_PATH):
+            from . import build as _build
+
+            try:
+                _build.build()
+            except Exception as e:  # noqa: BLE001
+                raise RuntimeError(
+                    f"libnpcd_b200.so is missing and could not be built ({e}); there is no CPU fallback. "
+                    "Run `python -c 'import __graft_entry__ as g; g.build()'`."
+                ) from e
+        try:
+            lib = C.CDLL(LIB_PATH)
+        except OSError as e:
+            raise RuntimeError(f"cannot load {LIB_PATH}: {e}; there is no CPU fallback") from e
+        lib.npcd_last_error.restype = C.c_char_p
+        lib.npcd_last_error.argtypes = []
+        lib.npcd_abi_version.restype = C.c_int
+        lib.npcd_abi_version.argtypes = []
+        if lib.npcd_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"{LIB_PATH}: ABI version {lib.npcd_abi_version()} != {ABI_VERSION}; rebuild")
+        for name, args in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = C.c_int
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def call(name: str, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed (code {rc}): {lib.npcd_last_error().decode(errors='replace')}")
+
+
+def ptr(t):
+    """device pointer of a contiguous tensor (None -> NULL)"""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "C-ABI buffers must be contiguous"
+    return t.data_ptr()

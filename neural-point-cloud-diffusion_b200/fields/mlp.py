@@ -1,0 +1,75 @@
+"""`fields.MLP` mirror (`npcd/models/pointnerf/fields/mlp.py`, `fields/field.py`): owns the aggregator, ``channel_net`` and
+``shape_net`` with the reference's parameter names, and evaluates the whole field (G1..M3) on compact sample lists.
+
+Two evaluation routes over the same parameters:
+  * ``evaluate``        -- no-grad inference: ONE fused CUDA call (gather + posenc + pair MLP + aggregation + heads).
+  * ``evaluate_autograd`` -- training: custom CUDA gather/posenc + composite kernels, dense layers through ``F.linear`` so
+                           autograd produces dgrad/wgrad (round-1 state; see DESIGN.md "training path").
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+import torch.nn.functional as F
+from torch.nn import Module
+
+from .. import ops
+from ..utils import define_mlp
+from . import aggregators
+
+
+class MLP(Module):
+    def __init__(self, in_dim: int, voxel_grid, aggregator: dict, feat_freqs: int, dir_freqs: int, channel_layers: List[int],
+                 shape_layers: List[int], activation: str = "ReLU", layer_norm: bool = False, nerf: bool = True,
+                 use_dir: bool = True, aggregate_shape: bool = False) -> None:
+        super().__init__()
+        if feat_freqs != 0 or use_dir or aggregate_shape or not nerf or activation != "LeakyReLU" \
+                or list(channel_layers) != [256] * 4 or list(shape_layers) != [256]:
+            raise NotImplementedError("kernels are specialised for the reference option tree (pointnerf.py:155-165; "
+                                      "use_view_dir False in configs/npcd_srncars.yaml:8)")
+        self.aggregator = getattr(aggregators, aggregator["network"])(in_dim, voxel_grid, **aggregator["kwargs"])
+        self.hid_dim = self.aggregator.out_dim
+        self.nerf, self.use_dir, self.aggregate_shape = nerf, use_dir, aggregate_shape
+        self.channel_net = define_mlp(channel_layers, self.hid_dim, d_out=3, act=activation, layer_norm=layer_norm)
+        self.shape_net = define_mlp(shape_layers, self.hid_dim, d_out=1, act=activation, layer_norm=layer_norm)
+        self._packed = None
+        self._packed_key = None
+        self.mlp_impl = "simt"  # "simt": fp32 CUDA-core kernels (mlp_simt.cu); "tc": tcgen05 tensor-core kernels (mlp_tc.cu)
+
+    def compute_dtype(self) -> str:
+        return {"simt": "f32", "tc": "f32 (fp16 2-way split, 3-product tcgen05 emulation, fp32 accumulate)"}[self.mlp_impl]
+
+    # ---- weights packed for the kernels, re-packed whenever a parameter changes (optimizer step, load_state_dict) ----
+    def packed_weights(self):
+        params = list(self.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if self._packed is None or key != self._packed_key:
+            self._packed = ops.PackedSimtWeights(self.aggregator.local_field, self.shape_net, self.channel_net, self.aggregator.in_dim)
+            self._packed_key = key
+        return self._packed
+
+    def evaluate(self, nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, want_feat=False):
+        """-> rgbs [capacity,4] = (r,g,b,sigma).  Fused CUDA path, no autograd."""
+        return ops.field_simt_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, self.packed_weights(), want_feat)
+
+    def evaluate_autograd(self, nbr_idx, sample_pos, kp_pos, kp_feat):
+        """Differentiable w.r.t. kp_feat and the MLP parameters (`aggregators/mlp.py:69-88,119-121`, `field.py:126-141`)."""
+        S = nbr_idx.shape[0]
+        valid = nbr_idx >= 0
+        sidx, slot = torch.nonzero(valid, as_tuple=True)
+        g = nbr_idx[sidx, slot].long()
+        pos = kp_pos.detach().reshape(-1, 3)[g]
+        feat = kp_feat.reshape(-1, kp_feat.shape[-1])[g]
+        x_rel = sample_pos[sidx, :3] - pos
+        w = 1.0 / (torch.norm(x_rel, dim=-1) + 1e-5)
+        norm = torch.zeros(S, device=w.device).index_add_(0, sidx, w)
+        w = w / norm[sidx]
+        freq = (2.0 ** torch.arange(self.aggregator.n_freqs, dtype=torch.float32, device=w.device)) * torch.pi
+        spec = x_rel[..., None] * freq
+        enc = torch.cat([spec.sin(), spec.cos()], -1).flatten(-2)
+        local = self.aggregator.local_field(torch.cat([feat, x_rel, enc], -1))
+        agg = torch.zeros(S, local.shape[1], device=w.device).index_add_(0, sidx, w[:, None] * local)
+        sigma = F.softplus(self.shape_net(agg) - 1)
+        rgb = torch.sigmoid(self.channel_net(agg))
+        return torch.cat([rgb, sigma], -1)

@@ -1,0 +1,289 @@
+"""Thin torch-tensor wrappers over the C-ABI entry points (one function per ``npcd_*`` call).
+
+PyTorch is plumbing only: device memory, streams, autograd bookkeeping.  Every function here launches hand-written
+sm_100a kernels from ``libnpcd_b200.so`` on ``torch.cuda.current_stream()``; nothing falls back to torch ops or the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr
+
+K_NEIGHBORS = 8
+DEPTH_RES = 128
+HIDDEN = 256
+
+# number of kernels launched by this process through the C-ABI (bench.py reports it as gpu_launches)
+LAUNCHES = 0
+# bench.py sets this to a list to collect (start_event, end_event, tag) around the field kernels (roofline timing)
+PROFILE = None
+
+
+def _timed(tag, fn):
+    if PROFILE is None:
+        fn()
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    fn()
+    b.record()
+    PROFILE.append((a, b, tag))
+
+
+def _count(n):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("npcd_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+@dataclass
+class Rays:
+    cam: torch.Tensor  # [N,3]
+    dirs: torch.Tensor  # [N,R,3]
+    start: torch.Tensor  # [N,R]
+    end: torch.Tensor  # [N,R]
+    origins: Optional[torch.Tensor] = None  # [N,R,3] (only if requested)
+
+
+def rays_generate(extr, intr, resolution: int, ray_subset=None, cube_scale: float = 1.0, want_origins: bool = False) -> Rays:
+    """extr [N,4,4], intr [N,3,3] fp32 CUDA; ray_subset: optional int64 [n] pixel ids shared by all views."""
+    _need_cuda(extr, intr, ray_subset)
+    extr = extr.contiguous().float()
+    intr = intr.contiguous().float()
+    N = extr.shape[0]
+    dev = extr.device
+    if ray_subset is not None:
+        ray_subset = ray_subset.contiguous().to(torch.int64)
+        R = ray_subset.numel()
+    else:
+        R = resolution * resolution
+    cam = torch.empty((N, 3), device=dev)
+    dirs = torch.empty((N, R, 3), device=dev)
+    start = torch.empty((N, R), device=dev)
+    end = torch.empty((N, R), device=dev)
+    origins = torch.empty((N, R, 3), device=dev) if want_origins else None
+    scratch = torch.empty(2, dtype=torch.int32, device=dev)
+    call("npcd_rays_generate", ptr(extr), ptr(intr), N, resolution, ptr(ray_subset), 0 if ray_subset is None else R,
+         float(cube_scale), ptr(cam), ptr(origins), ptr(dirs), ptr(start), ptr(end), ptr(scratch), _stream())
+    _count(3)
+    return Rays(cam, dirs, start, end, origins)
+
+
+@dataclass
+class Grid:
+    cell_start: torch.Tensor  # [B, cells+1] int32
+    sorted_pts: torch.Tensor  # [B, P, 4]
+    occ_bits: torch.Tensor  # [B, words] int32 (bit pattern)
+    n_obj: int
+    n_points: int
+
+
+_GRID_DIMS = None
+
+
+def grid_dims():
+    global _GRID_DIMS
+    if _GRID_DIMS is None:
+        c, w = C.c_int(), C.c_int()
+        call("npcd_grid_dims", C.byref(c), C.byref(w))
+        _GRID_DIMS = (c.value, w.value)
+    return _GRID_DIMS
+
+
+def grid_build(kp_pos) -> Grid:
+    """kp_pos [B,P,3] fp32 CUDA (detached)."""
+    _need_cuda(kp_pos)
+    kp_pos = kp_pos.detach().contiguous().float()
+    B, P = kp_pos.shape[:2]
+    cells, words = grid_dims()
+    dev = kp_pos.device
+    g = Grid(torch.empty((B, cells + 1), dtype=torch.int32, device=dev), torch.empty((B, P, 4), device=dev),
+             torch.empty((B, words), dtype=torch.int32, device=dev), B, P)
+    call("npcd_grid_build", ptr(kp_pos), B, P, ptr(g.cell_start), ptr(g.sorted_pts), ptr(g.occ_bits), _stream())
+    _count(1)
+    return g
+
+
+def march_count(rays: Rays, grid: Grid, views_per_obj: int, radius: float, max_shading_pts: int, jitter=None):
+    """Returns valid_bits [N*R,4] int32 (bit masks), ray_count [N*R] int32."""
+    N, R = rays.start.shape
+    dev = rays.start.device
+    n_rays = N * R
+    valid_bits = torch.empty((n_rays, 4), dtype=torch.int32, device=dev)
+    ray_count = torch.empty((n_rays,), dtype=torch.int32, device=dev)
+    if jitter is not None:
+        jitter = jitter.contiguous().float()
+        assert jitter.numel() == n_rays * DEPTH_RES
+    call("npcd_march_count", ptr(rays.cam), ptr(rays.dirs), ptr(rays.start), ptr(rays.end), ptr(jitter), n_rays, R, views_per_obj,
+         grid.n_points, ptr(grid.cell_start), ptr(grid.sorted_pts), ptr(grid.occ_bits), float(radius), int(max_shading_pts),
+         ptr(valid_bits), ptr(ray_count), _stream())
+    _count(1)
+    return valid_bits, ray_count
+
+
+_SCAN_WS = {}
+
+
+def scan_counts(ray_count, ray_ids=None):
+    """ray_offset [n+1] int64: exclusive scan of ray_count (gathered through ray_ids if given)."""
+    dev = ray_count.device
+    n = ray_ids.numel() if ray_ids is not None else ray_count.numel()
+    out = torch.empty((n + 1,), dtype=torch.int64, device=dev)
+    nbytes = C.c_size_t()
+    call("npcd_scan_workspace_bytes", n, C.byref(nbytes))
+    key = (dev, nbytes.value)
+    ws = _SCAN_WS.get(key)
+    if ws is None:
+        ws = _SCAN_WS[key] = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    call("npcd_scan_counts", ptr(ray_count), ptr(ray_ids), n, ptr(out), ptr(ws), nbytes.value, _stream())
+    _count(2)
+    return out
+
+
+def knn_fill(rays: Rays, grid: Grid, views_per_obj: int, radius: float, valid_bits, ray_offset, capacity: int, ray_ids=None,
+             jitter=None, want_sample_ray: bool = False):
+    """Returns nbr_idx [capacity,8] int32, sample_pos [capacity,4], sample_ray [capacity] int32 or None."""
+    N, R = rays.start.shape
+    dev = rays.start.device
+    n_sel = ray_offset.numel() - 1
+    nbr = torch.empty((capacity, K_NEIGHBORS), dtype=torch.int32, device=dev)
+    pos = torch.empty((capacity, 4), device=dev)
+    sray = torch.empty((capacity,), dtype=torch.int32, device=dev) if want_sample_ray else None
+    if jitter is not None:
+        jitter = jitter.contiguous().float()
+    call("npcd_knn_fill", ptr(rays.cam), ptr(rays.dirs), ptr(rays.start), ptr(rays.end), ptr(jitter), ptr(ray_ids), n_sel,
+         ptr(ray_offset), ptr(valid_bits), R, views_per_obj, grid.n_points, ptr(grid.cell_start), ptr(grid.sorted_pts),
+         float(radius), capacity, ptr(nbr), ptr(pos), ptr(sray), _stream())
+    _count(1 if capacity and n_sel else 0)
+    return nbr, pos, sray
+
+
+def knn_points(x, grid: Grid, radius: float, queries_per_obj: int = 0, query_obj=None):
+    """Exact radius-kNN of explicit positions x [n,3] -> [n,8] int32 (global index, canonical order, -1 padded)."""
+    _need_cuda(x)
+    x = x.contiguous().float()
+    n = x.shape[0]
+    out = torch.empty((n, K_NEIGHBORS), dtype=torch.int32, device=x.device)
+    call("npcd_knn_points", ptr(x), ptr(query_obj), n, queries_per_obj, grid.n_points, ptr(grid.cell_start), ptr(grid.sorted_pts),
+         float(radius), ptr(out), _stream())
+    _count(1 if n else 0)
+    return out
+
+
+class PackedSimtWeights:
+    """Device copies of the MLP weights in the layout ``npcd_field_simt_fwd`` wants (transposed, first layer padded)."""
+
+    def __init__(self, local_field, shape_net, channel_net, feat_dim: int):
+        lin = lambda seq: [m for m in seq if isinstance(m, torch.nn.Linear)]
+        lf, sn, cn = lin(local_field), lin(shape_net), lin(channel_net)
+        assert len(lf) == 5 and len(sn) == 2 and len(cn) == 5, "unexpected MLP depth"
+        self.keep = []
+
+        def wt(l, pad_to=None):
+            w = l.weight.detach().float().t().contiguous()  # [in, out]
+            if pad_to is not None and w.shape[0] < pad_to:
+                w = torch.cat([w, w.new_zeros(pad_to - w.shape[0], w.shape[1])]).contiguous()
+            self.keep.append(w)
+            return w.data_ptr()
+
+        def vec(t):
+            v = t.detach().float().contiguous()
+            self.keep.append(v)
+            return v.data_ptr()
+
+        k0 = (lf[0].in_features + 15) // 16 * 16
+        s = _lib.SimtWeights()
+        s.feat_dim = feat_dim
+        for i in range(4):
+            s.pair_wt[i] = wt(lf[i], k0 if i == 0 else None)
+            s.pair_b[i] = vec(lf[i].bias)
+            s.chan_wt[i] = wt(cn[i])
+            s.chan_b[i] = vec(cn[i].bias)
+        s.agg_wt, s.agg_b = wt(lf[4]), vec(lf[4].bias)
+        s.shape_wt, s.shape_b = wt(sn[0]), vec(sn[0].bias)
+        s.shape_out_w, s.shape_out_b = vec(sn[1].weight.reshape(-1)), vec(sn[1].bias)
+        s.chan_out_w, s.chan_out_b = vec(cn[4].weight), vec(cn[4].bias)
+        self.struct = s
+
+
+_SM_COUNT = {}
+
+
+def sm_count(dev) -> int:
+    i = dev.index if dev.index is not None else torch.cuda.current_device()
+    if i not in _SM_COUNT:
+        _SM_COUNT[i] = torch.cuda.get_device_properties(i).multi_processor_count
+    return _SM_COUNT[i]
+
+
+def field_simt_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity: int, weights: PackedSimtWeights,
+                   want_feat: bool = False):
+    """rgbs [capacity,4] = (r,g,b,sigma); feat [capacity,256] if requested."""
+    dev = sample_pos.device
+    rgbs = torch.empty((capacity, 4), device=dev)
+    feat = torch.empty((capacity, HIDDEN), device=dev) if want_feat else None
+    if capacity == 0:
+        return rgbs, feat
+    agg = torch.empty((capacity, HIDDEN), device=dev)
+    kp_pos = kp_pos.detach().contiguous().float()
+    kp_feat = kp_feat.detach().contiguous().float()
+    args = (ptr(nbr_idx), ptr(sample_pos), ptr(kp_pos), ptr(kp_feat), ptr(n_samples_dev), capacity, C.byref(weights.struct),
+            ptr(agg), ptr(rgbs), ptr(feat))
+    _timed("pair_mlp", lambda: call("npcd_field_simt_fwd", *args, 1, sm_count(dev), _stream()))
+    _timed("heads", lambda: call("npcd_field_simt_fwd", *args, 2, sm_count(dev), _stream()))
+    _count(2)
+    return rgbs, feat
+
+
+def composite_fwd(sample_pos, rgbs, ray_offset, ray_end, ray_ids=None, white_back: bool = True, range_scratch=None,
+                  init_range: bool = True, out=None):
+    """Returns mask [n], depth_raw [n], rgb [n,3], range_scratch (call clamp_depth afterwards).
+    ``out`` = (mask, depth, rgb) contiguous views to write into (chunked inference)."""
+    dev = ray_offset.device
+    n = ray_offset.numel() - 1
+    if out is None:
+        mask = torch.empty((n,), device=dev)
+        depth = torch.empty((n,), device=dev)
+        rgb = torch.empty((n, 3), device=dev)
+    else:
+        mask, depth, rgb = out
+        assert mask.numel() == n and depth.numel() == n and rgb.numel() == 3 * n
+    if range_scratch is None:
+        range_scratch = torch.empty(2, dtype=torch.int32, device=dev)
+    call("npcd_composite_fwd", ptr(sample_pos), ptr(rgbs), ptr(ray_offset), ptr(ray_ids), ptr(ray_end), n, int(white_back),
+         ptr(mask), ptr(depth), ptr(rgb), ptr(range_scratch), int(init_range), _stream())
+    _count((1 if init_range else 0) + (1 if n else 0))
+    return mask, depth, rgb, range_scratch
+
+
+def clamp_depth(depth, range_scratch, want_clamped: bool = False):
+    n = depth.numel()
+    clamped = torch.empty((n,), dtype=torch.uint8, device=depth.device) if want_clamped else None
+    call("npcd_clamp_depth", ptr(depth), n, ptr(range_scratch), ptr(clamped), _stream())
+    _count(1 if n else 0)
+    return clamped
+
+
+def composite_bwd(sample_pos, rgbs, ray_offset, white_back, g_rgb, g_mask, g_depth, out_mask, out_depth, clamped):
+    S = rgbs.shape[0]
+    n = ray_offset.numel() - 1
+    g = torch.zeros((S, 4), device=rgbs.device)
+    cont = lambda t: None if t is None else t.contiguous().float()
+    call("npcd_composite_bwd", ptr(sample_pos), ptr(rgbs), ptr(ray_offset), n, int(white_back), ptr(cont(g_rgb)), ptr(cont(g_mask)),
+         ptr(cont(g_depth)), ptr(out_mask), ptr(out_depth), ptr(clamped), ptr(g), _stream())
+    _count(1 if n else 0)
+    return g

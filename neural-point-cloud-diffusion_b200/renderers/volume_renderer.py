@@ -1,0 +1,185 @@
+"""``VolumeRenderer`` drop-in (`npcd/models/pointnerf/renderers/{renderer,volume_renderer}.py`).
+
+Same constructor and ``forward`` signature / return dict as the reference (`renderers/renderer.py:202-268`), resolved by name
+from this package's ``renderers`` namespace exactly like `pointnerf.py:28`.  ``forward`` drives the sm_100a kernels through the
+C-ABI:  rays -> grid -> march/count -> scan -> kNN fill -> field (gather+posenc+MLPs) -> composite.
+
+Differences from the reference that are visible to a caller (all documented in DESIGN.md):
+  * one host sync per call (the kept-sample count, to size buffers) instead of >= 4;
+  * ``return_kp_weights`` / ``ray_limits`` / ``disparity_space_sampling`` are never used by any reference caller and raise;
+  * train-mode random tensors can be injected (``rng=`` object with ray_perm / depth_jitter / valid_ray_perm) for parity tests;
+    by default they are drawn with torch on the device like the reference does.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from .. import ops
+from ..utils import AttrDict
+
+
+class _CompositeFn(torch.autograd.Function):
+    """Compositing over compact per-ray sample lists; backward = ``npcd_composite_bwd``."""
+
+    @staticmethod
+    def forward(ctx, rgbs, sample_pos, ray_offset, ray_end, ray_ids, white_back):
+        mask, depth, rgb, rng = ops.composite_fwd(sample_pos, rgbs, ray_offset, ray_end, ray_ids, white_back)
+        clamped = ops.clamp_depth(depth, rng, want_clamped=True)
+        ctx.save_for_backward(rgbs, sample_pos, ray_offset, mask, depth, clamped)
+        ctx.white_back = white_back
+        return mask, depth, rgb
+
+    @staticmethod
+    def backward(ctx, g_mask, g_depth, g_rgb):
+        rgbs, sample_pos, ray_offset, mask, depth, clamped = ctx.saved_tensors
+        g = ops.composite_bwd(sample_pos, rgbs, ray_offset, ctx.white_back, g_rgb, g_mask, g_depth, mask, depth, clamped)
+        return g, None, None, None, None, None
+
+
+class VolumeRenderer(nn.Module):
+    def __init__(self, field, cube_scale: float, depth_resolution: int, ray_limits: Optional[Tuple[float, float]] = None,
+                 ray_subsamples: int = 0, disparity_space_sampling: bool = False, white_back: bool = False):
+        super().__init__()
+        if ray_limits is not None or disparity_space_sampling:
+            raise NotImplementedError("ray_limits / disparity_space_sampling are unused by the reference (pointnerf.py:185,189)")
+        if depth_resolution != ops.DEPTH_RES:
+            raise NotImplementedError(f"kernels are specialised for depth_resolution={ops.DEPTH_RES} (pointnerf.py:184)")
+        self.field = field
+        self.cube_scale = cube_scale
+        self.depth_resolution = depth_resolution
+        self.ray_limits = ray_limits
+        self.ray_subsamples = ray_subsamples
+        self.disparity_space_sampling = disparity_space_sampling
+        self.white_back = white_back
+        self.randomize_depth_samples = False  # toggled by PointNeRF.train() (pointnerf.py:30-33)
+        self.max_samples_per_chunk = 1 << 24  # kept shading samples per fused field launch (bounds the workspace)
+        self.last_stats = {}
+
+    # ---- train-mode valid-ray subsampling (fields/aggregators/aggregator.py:78-119) ----
+    def _subsample_valid_rays(self, ray_count: Tensor, rng):
+        """ray_count [N,R] -> (ray_ids [N*n] int32 ascending per view, n)."""
+        N, R = ray_count.shape
+        valid = ray_count > 0
+        nvalid = valid.sum(-1)
+        n = int(min(int(nvalid.min().item()), self.field.aggregator.ray_subsamples)) if N > 0 else 0
+        if n == 0:
+            return torch.zeros(0, dtype=torch.int32, device=ray_count.device), 0
+        inst, ray = torch.nonzero(valid, as_tuple=True)
+        total = inst.numel()
+        if rng is not None:
+            perm = torch.as_tensor(rng.valid_ray_perm(total), device=inst.device)
+        else:
+            perm = torch.randperm(total, device=inst.device)
+        inst, ray = inst[perm], ray[perm]
+        order = torch.argsort(inst, stable=True)  # shuffle within instances (aggregator.py:95-99)
+        ray = ray[order]
+        start = torch.cumsum(nvalid, 0) - nvalid
+        take = (torch.arange(n, device=inst.device)[None, :] + start[:, None]).reshape(-1)
+        sel = ray[take].view(N, n)
+        sel = torch.sort(sel, dim=1).values  # mask order = ascending ray index (renderer.py:266)
+        ray_ids = (sel + torch.arange(N, device=sel.device)[:, None] * R).reshape(-1).to(torch.int32)
+        return ray_ids.contiguous(), n
+
+    def forward(self, kp_pos: Tensor, kp_feat: Tensor, extr: Tensor, intr: Tensor, resolution: int, sample: bool,
+                return_channels: bool = True, return_kp_weights: bool = False, rng=None, return_aux: bool = False) -> AttrDict:
+        """kp_pos [B,P,3], kp_feat [B,P,F], extr [B,T,4,4] world->cam, intr [B,T,3,3]  ->  AttrDict with
+        mask [B,T,R',1], depth [B,T,R',1], channels [B,T,R',3] (if return_channels), ray_idx [B,T,R',1] int64 (if sample)."""
+        if return_kp_weights:
+            raise NotImplementedError("return_kp_weights is never requested by the reference callers")
+        if not kp_pos.is_cuda:
+            raise RuntimeError("npcd_b200 renders on CUDA only (no CPU fallback)")
+        B, T = extr.shape[:2]
+        N = B * T
+        dev = kp_pos.device
+        agg = self.field.aggregator
+        radius, SR = float(agg.scaled_r), int(agg.max_shading_pts)
+        num_pix = resolution * resolution
+
+        # R1/R2: rays (+ train-mode ray subset shared by all views, renderer.py:232-238)
+        subset = None
+        if self.ray_subsamples and sample:
+            perm = torch.as_tensor(rng.ray_perm(num_pix), device=dev) if rng is not None else torch.randperm(num_pix, device=dev)
+            subset = perm[: self.ray_subsamples].contiguous()
+        rays = ops.rays_generate(extr.reshape(N, 4, 4), intr.reshape(N, 3, 3), resolution, subset, self.cube_scale,
+                                 want_origins=return_aux)
+        R = rays.start.shape[1]
+
+        grid = agg._grid(kp_pos.detach())
+
+        jitter = None
+        if self.randomize_depth_samples:  # renderer.py:74-76
+            if rng is not None:
+                jitter = torch.as_tensor(rng.depth_jitter((N, R, ops.DEPTH_RES, 1)), device=dev).reshape(N, R, ops.DEPTH_RES)
+            else:
+                jitter = torch.rand((N, R, ops.DEPTH_RES), device=dev)
+
+        valid_bits, ray_count = ops.march_count(rays, grid, T, radius, SR, jitter)
+
+        needs_grad = torch.is_grad_enabled() and (kp_feat.requires_grad or any(p.requires_grad for p in self.field.parameters()))
+        out_rays = R
+        ray_ids = None
+        if sample:
+            ray_ids, out_rays = self._subsample_valid_rays(ray_count.view(N, R), rng)
+        n_out = N * out_rays
+        mask = torch.empty((n_out,), device=dev)
+        depth = torch.empty((n_out,), device=dev)
+        rgb = torch.empty((n_out, 3), device=dev)
+        aux = {}
+
+        if needs_grad or sample or return_aux:
+            # single launch group with autograd support
+            ray_offset = ops.scan_counts(ray_count, ray_ids)
+            S = int(ray_offset[-1].item())
+            nbr, pos, _ = ops.knn_fill(rays, grid, T, radius, valid_bits, ray_offset, S, ray_ids, jitter)
+            if needs_grad:
+                rgbs = self.field.evaluate_autograd(nbr, pos, kp_pos, kp_feat) if S > 0 else torch.zeros((0, 4), device=dev)
+                feat = None
+            else:
+                rgbs, feat = self.field.evaluate(nbr, pos, kp_pos, kp_feat, ray_offset[-1:], S, want_feat=return_aux)
+            mask, depth, rgb = _CompositeFn.apply(rgbs, pos, ray_offset, rays.end.reshape(-1), ray_ids, self.white_back)
+            self.last_stats = dict(S=S, Np=None)
+            if return_aux:
+                aux = dict(neighbor_idx=nbr, sample_pos=pos, rgbs=rgbs, feat=feat, ray_offset=ray_offset, ray_count=ray_count,
+                           rays=rays, ray_ids=ray_ids)
+        else:
+            # inference: chunk rays so the per-launch workspace stays bounded; the depth clamp range is shared by all chunks
+            rng_scratch = torch.empty(2, dtype=torch.int32, device=dev)
+            n_rays = N * R
+            rays_per_chunk = max(R, (self.max_samples_per_chunk // max(SR, 1)) // R * R) if R > 0 else 1
+            ray_end = rays.end.reshape(-1)
+            S_total = 0
+            first = True
+            for r0 in range(0, max(n_rays, 1), rays_per_chunk):
+                r1 = min(n_rays, r0 + rays_per_chunk)
+                if r1 <= r0:
+                    break
+                ids = None if (r0 == 0 and r1 == n_rays) else torch.arange(r0, r1, dtype=torch.int32, device=dev)
+                ray_offset = ops.scan_counts(ray_count, ids) if ids is not None else ops.scan_counts(ray_count)
+                S = int(ray_offset[-1].item())
+                S_total += S
+                nbr, pos, _ = ops.knn_fill(rays, grid, T, radius, valid_bits, ray_offset, S, ids, jitter)
+                rgbs, _ = self.field.evaluate(nbr, pos, kp_pos, kp_feat, ray_offset[-1:], S)
+                ops.composite_fwd(pos, rgbs, ray_offset, ray_end, ids, self.white_back, range_scratch=rng_scratch, init_range=first,
+                                  out=(mask[r0:r1], depth[r0:r1], rgb[r0:r1]))
+                first = False
+            if first:  # no rays at all
+                ops.composite_fwd(None, None, torch.zeros(1, dtype=torch.int64, device=dev), ray_end, None, self.white_back,
+                                  range_scratch=rng_scratch, init_range=True, out=(mask, depth, rgb))
+            ops.clamp_depth(depth, rng_scratch)
+            self.last_stats = dict(S=S_total, Np=None)
+
+        out = AttrDict(mask=mask.view(B, T, out_rays, 1), depth=depth.view(B, T, out_rays, 1))
+        if return_channels:
+            out["channels"] = rgb.view(B, T, out_rays, 3)
+        if sample:
+            if ray_ids is not None and out_rays > 0:
+                local = (ray_ids.long() % R).view(B, T, out_rays, 1)
+                out["ray_idx"] = subset[local] if subset is not None else local
+            else:
+                out["ray_idx"] = torch.zeros((B, T, 0, 1), dtype=torch.int64, device=dev)
+        if return_aux:
+            out["aux"] = aux
+        return out

@@ -1,0 +1,64 @@
+"""``torch_knnquery.VoxelGrid``-compatible object backed by the sm_100a grid/query kernels.
+
+ABI inferred from the reference call sites only (the extension's source is not available):
+ctor `pointnerf.py:20,147-153`; ``set_pointset`` `pointnerf.py:67-75,116-124`; ``query`` `fields/aggregators/aggregator.py:63`;
+attribute ``vsize_tup`` `aggregator.py:20`.
+
+Semantics: EXACT radius query (the reference's own ``voxel_grid is None`` branch, `aggregator.py:42-58`): no per-voxel point
+cap, no occupied-voxel cap, candidates = all samples, so the returned slots have no holes.  ``max_points_per_voxel`` /
+``max_occ_voxels_per_example`` / ``kernel_size`` are accepted and ignored (documented deviation: upstream drops points in
+over-full voxels -- "VoxelGrid looses keypoints sometimes", `npcd/losses/neural_point_cloud_tv_loss.py:42`).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class VoxelGrid:
+    def __init__(self, voxel_size, voxel_scale, kernel_size, max_points_per_voxel, max_occ_voxels_per_example, ranges):
+        self.vsize_tup = tuple(voxel_size)
+        self.vscale_tup = tuple(voxel_scale)
+        self.kernel_size = tuple(kernel_size)
+        self.max_points_per_voxel = max_points_per_voxel
+        self.max_occ_voxels_per_example = max_occ_voxels_per_example
+        self.ranges = tuple(ranges)
+        self._grid = None
+        self._points_key = None
+
+    def set_pointset(self, points: torch.Tensor, actual_num_points: torch.Tensor = None) -> None:
+        """points [B,P,3] (detached).  Builds the per-object acceleration grid on the current stream."""
+        self._grid = ops.grid_build(points)
+        self._points_key = (points.data_ptr(), points._version, tuple(points.shape))
+
+    def grid_for(self, points: torch.Tensor) -> "ops.Grid":
+        """Grid for ``points``; reuses the one from ``set_pointset`` when it was built from the same tensor."""
+        key = (points.data_ptr(), points._version, tuple(points.shape))
+        if self._grid is None or key != self._points_key:
+            self.set_pointset(points.detach())
+            self._points_key = key
+        return self._grid
+
+    def query(self, raypos: torch.Tensor, k: int, radius_limit_scale: float, max_shading_pts: int):
+        """raypos [B,Rall,D,3] -> (sample_idx [Rv,SR,K] int32, sample_loc [Rv,SR,3], ray_mask [B,Rall] int8)."""
+        if self._grid is None:
+            raise RuntimeError("VoxelGrid.query called before set_pointset")
+        if k != ops.K_NEIGHBORS:
+            raise NotImplementedError(f"kernels are specialised for k={ops.K_NEIGHBORS}")
+        B, Rall, D = raypos.shape[:3]
+        radius = radius_limit_scale * max(self.vsize_tup)
+        idx = ops.knn_points(raypos.reshape(-1, 3), self._grid, radius, queries_per_obj=Rall * D).view(B, Rall, D, k)
+        valid = (idx >= 0).any(-1)
+        keep = valid & (valid.cumsum(-1) <= max_shading_pts)
+        ray_mask = keep.any(-1)
+        order = torch.argsort((~keep).to(torch.int8), dim=-1, stable=True)[..., :max_shading_pts]  # kept samples first
+        take = torch.gather(keep, -1, order)
+        sidx = torch.gather(idx, 2, order[..., None].expand(-1, -1, -1, k))
+        sloc = torch.gather(raypos, 2, order[..., None].expand(-1, -1, -1, 3))
+        sidx = torch.where(take[..., None], sidx, torch.full_like(sidx, -1))
+        if max_shading_pts > D:
+            pad = max_shading_pts - D
+            sidx = torch.nn.functional.pad(sidx, (0, 0, 0, pad), value=-1)
+            sloc = torch.nn.functional.pad(sloc, (0, 0, 0, pad))
+        return sidx[ray_mask].contiguous(), sloc[ray_mask].contiguous(), ray_mask.to(torch.int8)

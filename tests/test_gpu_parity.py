@@ -1,0 +1,358 @@
+"""GPU parity tests: the CUDA path (through the C-ABI / drop-in modules) against the CPU oracle and the golden vectors
+generated from the unmodified reference.  Run on the B200 box: ``python -m pytest tests -m gpu``.
+
+Bars (BASELINE.json north_star): kNN indices bit-exact (canonical (distance, index) order); RGB / depth / mask within 1e-4
+max-abs in fp32; PSNR within 0.01 dB.
+"""
+import numpy as np
+import pytest
+
+from helpers import EVAL_CASES, canon_sets, load_case, psnr
+from oracle import pointnerf_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+IMG_TOL = 1e-4  # north_star tolerance for RGB/depth/mask (fp32)
+GRAD_TOL = 5e-3  # see tests/test_oracle_vs_golden.py (LeakyReLU kink flips)
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+@pytest.fixture(scope="module")
+def model(torch_cuda, weights):
+    torch = torch_cuda
+    import npcd_b200  # noqa: F401
+    from npcd_b200.pointnerf import PointNeRF
+
+    m = PointNeRF(1, 32, 512, False).eval().cuda()
+    sd = m.state_dict()
+    with torch.no_grad():
+        for k, v in weights.items():
+            sd[k].copy_(torch.from_numpy(v))
+    return m
+
+
+def _t(torch, a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["view32", "b2t3_16", "wide16", "empty16"])
+def test_rays_and_limits_bit_exact(name, syn, torch_cuda):
+    torch = torch_cuda
+    from npcd_b200 import ops
+
+    g, coords, feats, extr, intr, res = load_case(name, syn)
+    B, T = extr.shape[:2]
+    o, d = orc.generate_rays(extr.reshape(-1, 4, 4), intr.reshape(-1, 3, 3), res)
+    s, e = orc.get_ray_limits(o.reshape(B, T, -1, 3), d.reshape(B, T, -1, 3))
+    rays = ops.rays_generate(_t(torch, extr.reshape(-1, 4, 4)), _t(torch, intr.reshape(-1, 3, 3)), res, want_origins=True)
+    np.testing.assert_array_equal(rays.origins.cpu().numpy(), o)
+    np.testing.assert_array_equal(rays.dirs.cpu().numpy(), d)
+    np.testing.assert_array_equal(rays.start.cpu().numpy().reshape(s.shape), s)
+    np.testing.assert_array_equal(rays.end.cpu().numpy().reshape(e.shape), e)
+
+
+def test_rays_subset_bit_exact(syn, torch_cuda):
+    torch = torch_cuda
+    from npcd_b200 import ops
+
+    g, coords, feats, extr, intr, res = load_case("train_b2t2", syn)
+    pick = syn.NumpyRNGStreams(3).ray_perm(res * res)[:112]
+    o, d = orc.generate_rays(extr.reshape(-1, 4, 4), intr.reshape(-1, 3, 3), res)
+    rays = ops.rays_generate(_t(torch, extr.reshape(-1, 4, 4)), _t(torch, intr.reshape(-1, 3, 3)), res, _t(torch, pick), want_origins=True)
+    np.testing.assert_array_equal(rays.dirs.cpu().numpy(), d[:, pick])
+    np.testing.assert_array_equal(rays.origins.cpu().numpy(), o[:, pick])
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_knn_query_bit_exact(name, syn, model, weights, torch_cuda):
+    """march_count + scan + knn_fill vs oracle.query_keypoints_exact: indices, order, positions, per-ray counts identical."""
+    torch = torch_cuda
+    g, coords, feats, extr, intr, res = load_case(name, syn)
+    ref = orc.render(coords, feats, extr, intr, res, weights, return_aux=True)["aux"]
+    with torch.no_grad():
+        out = model.renderer(_t(torch, coords), _t(torch, feats), _t(torch, extr), _t(torch, intr), res, False, return_aux=True)
+    aux = out["aux"]
+    np.testing.assert_array_equal(aux["ray_count"].cpu().numpy().reshape(ref["slot_mask"].shape[:-1]), ref["slot_mask"].sum(-1))
+    nbr = aux["neighbor_idx"].cpu().numpy().astype(np.int64)
+    assert nbr.shape == ref["neighbor_idx"].shape
+    np.testing.assert_array_equal(nbr, ref["neighbor_idx"])  # bit-exact incl. canonical (distance, index) order
+    pos = aux["sample_pos"].cpu().numpy()
+    np.testing.assert_array_equal(pos[:, :3], ref["shading_pts"])
+    # and against the reference's own neighbour sets
+    np.testing.assert_array_equal(canon_sets(nbr), g["neighbor_sets"])
+
+
+def test_knn_points_ties_and_padding(syn, torch_cuda):
+    """Duplicate points (distance ties -> lower index first), fewer than 8 neighbours (-1 padding), queries outside the cube."""
+    torch = torch_cuda
+    from npcd_b200 import ops
+
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(-0.3, 0.3, size=(2, 512, 3)).astype(np.float32)
+    pts[0, 100:110] = pts[0, 0]  # exact duplicates -> ties
+    pts[1, 200:] = pts[1, :312] + np.float32(1e-4)
+    q = np.concatenate([pts[:, :64] + rng.normal(0, 0.03, (2, 64, 3)).astype(np.float32),
+                        rng.uniform(-1.2, 1.2, size=(2, 64, 3)).astype(np.float32)], 1)
+    grid = ops.grid_build(_t(torch, pts))
+    got = ops.knn_points(_t(torch, q.reshape(-1, 3)), grid, 0.08, queries_per_obj=128).cpu().numpy().reshape(2, 128, 8)
+    for b in range(2):
+        idx, cnt = orc.knn_exact(q[b], pts[b])
+        want = np.where(idx >= 0, idx + b * 512, -1)
+        np.testing.assert_array_equal(got[b], want)
+    assert (got == -1).any() and (got >= 0).any()
+
+
+def test_max_shading_cap(syn, model, weights, torch_cuda):
+    """box cloud: some rays hit the 50-sample cap; a smaller cap (max_shading_points=7) must keep the FIRST 7 valid samples."""
+    torch = torch_cuda
+    g, coords, feats, extr, intr, res = load_case("box32", syn)
+    assert int(g["ray_count"].max()) == 50
+    with torch.no_grad():
+        agg = model.field.aggregator
+        prev = agg.max_shading_pts
+        agg.max_shading_pts = 7
+        try:
+            out = model.renderer(_t(torch, coords), _t(torch, feats), _t(torch, extr), _t(torch, intr), res, False, return_aux=True)
+        finally:
+            agg.max_shading_pts = prev
+    B, T = extr.shape[:2]
+    o, d = orc.generate_rays(extr.reshape(-1, 4, 4), intr.reshape(-1, 3, 3), res)
+    o, d = o.reshape(B, T, -1, 3), d.reshape(B, T, -1, 3)
+    s, e = orc.get_ray_limits(o, d)
+    x = orc.sample_positions(o, d, orc.sample_depths(s, e))
+    ref = orc.query_keypoints_exact(x, coords, max_shading_pts=7)
+    np.testing.assert_array_equal(out["aux"]["neighbor_idx"].cpu().numpy(), ref["neighbor_idx"])
+    assert int(out["aux"]["ray_count"].max()) == 7
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["view32", "box32"])
+def test_field_kernels_vs_oracle(name, syn, model, weights, torch_cuda):
+    torch = torch_cuda
+    g, coords, feats, extr, intr, res = load_case(name, syn)
+    ref = orc.render(coords, feats, extr, intr, res, weights, return_aux=True)["aux"]
+    with torch.no_grad():
+        out = model.renderer(_t(torch, coords), _t(torch, feats), _t(torch, extr), _t(torch, intr), res, False, return_aux=True)
+    rgbs = out["aux"]["rgbs"].cpu().numpy()
+    feat = out["aux"]["feat"].cpu().numpy()
+    np.testing.assert_allclose(feat, ref["feat"], atol=2e-5 * max(1.0, np.abs(ref["feat"]).max()), rtol=0)
+    np.testing.assert_allclose(rgbs[:, :3], ref["rgb"], atol=2e-5, rtol=0)
+    np.testing.assert_allclose(rgbs[:, 3], ref["sigma"], atol=2e-5 * max(1.0, ref["sigma"].max()), rtol=0)
+
+
+def test_field_autograd_route_matches_fused(syn, model, torch_cuda):
+    """The training route (custom kernels + F.linear) and the fused inference kernels evaluate the same function."""
+    torch = torch_cuda
+    g, coords, feats, extr, intr, res = load_case("view32", syn)
+    args = (_t(torch, coords), _t(torch, feats), _t(torch, extr), _t(torch, intr), res, False)
+    with torch.no_grad():
+        a = model.renderer(*args)
+    b = model.renderer(*args)  # grad enabled, parameters require grad -> autograd route
+    for k in ("mask", "depth", "channels"):
+        np.testing.assert_allclose(a[k].cpu().numpy(), b[k].detach().cpu().numpy(), atol=2e-5, rtol=0, err_msg=k)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def test_composite_fwd_bwd_vs_torch(syn, torch_cuda):
+    """Random sigma/rgb on ragged per-ray lists (n = 0, 1, 2, 33, 50, 128) against a dense torch restatement + autograd."""
+    torch = torch_cuda
+    from npcd_b200 import ops
+    from npcd_b200.renderers.volume_renderer import _CompositeFn
+
+    rs = np.random.default_rng(5)
+    counts = np.array([0, 1, 2, 33, 50, 128, 0, 7, 64, 3, 0, 31, 32], np.int64)
+    n = len(counts)
+    off = np.concatenate([[0], np.cumsum(counts)])
+    S = int(off[-1])
+    SR = 128
+    t = np.concatenate([np.sort(rs.uniform(0.2, 2.5, c)) for c in counts]).astype(np.float32)
+    sigma = rs.uniform(0, 60, S).astype(np.float32)
+    rgb = rs.uniform(0, 1, (S, 3)).astype(np.float32)
+    ray_end = rs.uniform(2.6, 3.0, n).astype(np.float32)
+    pos = np.zeros((S, 4), np.float32)
+    pos[:, 3] = t
+    rgbs_np = np.concatenate([rgb, sigma[:, None]], 1)
+
+    rgbs = _t(torch, rgbs_np).requires_grad_(True)
+    mask, depth, col = _CompositeFn.apply(rgbs, _t(torch, pos), _t(torch, off), _t(torch, ray_end), None, True)
+    gm, gd, gc = [_t(torch, rs.normal(size=s).astype(np.float32)) for s in ((n,), (n,), (n, 3))]
+    (mask * gm).sum().add((depth * gd).sum()).add((col * gc).sum()).backward()
+
+    # dense torch restatement (renderer.py:95-110,146-176) on CPU in float64 for a tight reference
+    r64 = torch.tensor(rgbs_np, dtype=torch.float64, requires_grad=True)
+    m = torch.zeros(n, SR, dtype=torch.bool)
+    for i, c in enumerate(counts):
+        m[i, :c] = True
+    sig_d = torch.zeros(n, SR, dtype=torch.float64).masked_scatter(m, r64[:, 3])
+    dep = torch.full((n, SR), -np.inf, dtype=torch.float64).masked_scatter(m, torch.tensor(t, dtype=torch.float64))
+    dep = torch.cummax(dep, -1).values
+    dep = torch.where(dep == -np.inf, torch.tensor(ray_end, dtype=torch.float64)[:, None].expand_as(dep), dep)
+    delta = torch.cat([dep[:, 1:] - dep[:, :-1], torch.zeros(n, 1, dtype=torch.float64)], -1)
+    alpha = 1 - torch.exp(-sig_d * delta)
+    w = alpha * torch.cumprod(torch.cat([torch.ones(n, 1, dtype=torch.float64), 1 - alpha + 1e-10], -1), -1)[:, :-1]
+    wt = w.sum(-1)
+    cd = torch.nan_to_num((w * dep).sum(-1) / wt, float("inf")).clamp(dep.min(), dep.max())
+    ray_id = torch.arange(n)[:, None].expand(n, SR)[m]
+    comp = torch.zeros(n, 3, dtype=torch.float64).index_add_(0, ray_id, w[m][:, None] * r64[:, :3]) + 1 - wt[:, None]
+    (wt * gm.cpu().double()).sum().add((cd * gd.cpu().double()).sum()).add((comp * gc.cpu().double()).sum()).backward()
+
+    np.testing.assert_allclose(mask.detach().cpu().numpy(), wt.detach().numpy(), atol=2e-6)
+    np.testing.assert_allclose(col.detach().cpu().numpy(), comp.detach().numpy(), atol=2e-6)
+    np.testing.assert_allclose(depth.detach().cpu().numpy(), cd.detach().numpy(), atol=2e-5)
+    gref = r64.grad.numpy()
+    got = rgbs.grad.cpu().numpy()
+    np.testing.assert_allclose(got, gref, atol=1e-4 * max(1.0, np.abs(gref).max()), rtol=1e-3)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_render_vs_golden_small(name, syn, model, torch_cuda):
+    torch = torch_cuda
+    g, coords, feats, extr, intr, res = load_case(name, syn)
+    with torch.no_grad():
+        out = model.render(_t(torch, coords), _t(torch, feats), _t(torch, extr), _t(torch, intr), resolution=res)
+    assert model.renderer.last_stats["S"] == int(g["S"])
+    for k in ("mask", "depth", "channels"):
+        got = out[k].cpu().numpy()
+        assert got.shape == g[k].shape and got.dtype == np.float32
+        np.testing.assert_allclose(got, g[k], atol=IMG_TOL, rtol=0, err_msg=k)
+    assert "ray_idx" not in out
+
+
+def test_render_vs_golden_full_view(syn, model, weights, torch_cuda):
+    """Config 1: one 128x128 SRN-cars view.  Against the reference's golden image (1e-4 except the <= 8 rays where the
+    reference's own matmul-form cdist flips a boundary neighbour) and bit-exact kNN against the oracle."""
+    torch = torch_cuda
+    g, coords, feats, extr, intr, res = load_case("view128", syn)
+    with torch.no_grad():
+        out = model.renderer(_t(torch, coords), _t(torch, feats), _t(torch, extr), _t(torch, intr), res, False, return_aux=True)
+    ch = out["channels"].cpu().numpy()
+    bad = np.abs(ch - g["channels"]).max(-1) > IMG_TOL
+    assert bad.sum() <= 8, int(bad.sum())
+    ok = ~bad.reshape(-1)
+    for k in ("mask", "depth"):
+        np.testing.assert_allclose(out[k].cpu().numpy().reshape(-1)[ok], g[k].reshape(-1)[ok], atol=IMG_TOL, rtol=0)
+    img = lambda a: np.clip(a.reshape(res, res, 3), 0, 1)
+    white = np.ones((res, res, 3), np.float32)
+    assert abs(psnr(img(ch), white) - psnr(img(g["channels"]), white)) < 0.01  # PSNR within 0.01 dB
+    assert psnr(img(ch), img(g["channels"])) > 70.0
+    ref = orc.render(coords, feats, extr, intr, res, weights, return_aux=True)
+    np.testing.assert_array_equal(out["aux"]["neighbor_idx"].cpu().numpy(), ref["aux"]["neighbor_idx"])
+    np.testing.assert_allclose(ch, ref["channels"], atol=IMG_TOL, rtol=0)
+    np.testing.assert_allclose(out["depth"].cpu().numpy(), ref["depth"], atol=IMG_TOL, rtol=0)
+
+
+def test_train_mode_forward_backward_vs_golden(syn, model, weights, torch_cuda):
+    torch = torch_cuda
+    g, coords, feats, extr, intr, res = load_case("train_b2t2", syn)
+    seed = int(g["seed"])
+    model.train()
+    try:
+        for p in model.parameters():
+            p.grad = None
+        ft = _t(torch, feats).requires_grad_(True)
+        out = model.renderer(_t(torch, coords), ft, _t(torch, extr), _t(torch, intr), res, True, rng=syn.NumpyRNGStreams(seed))
+        np.testing.assert_array_equal(out["ray_idx"].cpu().numpy(), g["ray_idx"])
+        for k in ("mask", "depth", "channels"):
+            np.testing.assert_allclose(out[k].detach().cpu().numpy(), g[k], atol=IMG_TOL, rtol=0, err_msg=k)
+        target = np.random.default_rng(seed).random(tuple(out["channels"].shape), dtype=np.float32)
+        loss = ((out["channels"] - _t(torch, target)) ** 2).mean()
+        assert abs(loss.item() - float(g["loss"])) < 1e-5
+        loss.backward()
+        gf = ft.grad.cpu().numpy()
+        np.testing.assert_allclose(gf, g["grad_feats"], atol=GRAD_TOL * np.abs(g["grad_feats"]).max(), rtol=0)
+        own = dict(model.named_parameters())
+        for k in weights:
+            gr = own[k].grad.cpu().numpy()
+            refg = g["grad__" + k]
+            got = gr if gr.size <= 4096 else gr.reshape(-1)[::61]
+            np.testing.assert_allclose(got.reshape(refg.shape), refg, atol=GRAD_TOL * max(np.abs(refg).max(), 1e-12), rtol=0, err_msg=k)
+    finally:
+        model.eval()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Size-independent properties at BASELINE.json's full sizes (128x128 views, 512 points).
+def test_full_size_properties(syn, model, cameras, torch_cuda):
+    torch = torch_cuda
+    poses, intr = cameras
+    views = [0, 31, 62, 93, 124, 155, 186, 217]
+    coords, feats = syn.make_clouds([0])
+    c, f = _t(torch, coords), _t(torch, feats)
+    e, i = _t(torch, poses[views][None]), _t(torch, intr[views][None])
+    r = model.renderer
+    with torch.no_grad():
+        a = r(c, f, e, i, 128, False)
+        b = r(c, f, e, i, 128, False)
+        # determinism: bit-identical run to run (no atomics on the data path)
+        for k in ("mask", "depth", "channels"):
+            assert torch.equal(a[k], b[k]), k
+        # chunked == unchunked (the clamp range is shared across chunks)
+        prev = r.max_samples_per_chunk
+        r.max_samples_per_chunk = 50 * 16384 * 2
+        try:
+            cch = r(c, f, e, i, 128, False)
+        finally:
+            r.max_samples_per_chunk = prev
+        for k in ("mask", "depth", "channels"):
+            assert torch.equal(a[k], cch[k]), k
+        # batch of views == single views (mask / colour exactly; depth wherever the ray hit, the miss value is a global clamp)
+        one = r(c, f, e[:, 3:4], i[:, 3:4], 128, False)
+        assert torch.equal(one["channels"], a["channels"][:, 3:4])
+        hit = one["mask"] > 0
+        assert torch.equal(one["depth"][hit], a["depth"][:, 3:4][hit])
+        # permuting the point order of the cloud changes nothing but the neighbour labels
+        perm = torch.randperm(512, generator=torch.Generator().manual_seed(0)).cuda()
+        p = r(c[:, perm], f[:, perm], e[:, :2], i[:, :2], 128, False)
+        np.testing.assert_allclose(p["channels"].cpu().numpy(), a["channels"][:, :2].cpu().numpy(), atol=2e-5, rtol=0)
+        # sanity of ranges
+        assert float(a["mask"].min()) >= 0 and float(a["mask"].max()) <= 1 + 1e-5
+        assert torch.isfinite(a["depth"]).all() and torch.isfinite(a["channels"]).all()
+
+
+def test_drop_in_module_interface(syn, model, torch_cuda):
+    """`PointNeRF.forward(obj_idx, intrinsics, extrinsics, sample_rays)` -> (pred, aux) like pointnerf.py:56-105."""
+    torch = torch_cuda
+    poses, intr = syn.load_cameras()
+    coords, feats = syn.make_clouds([0])
+    with torch.no_grad():
+        model.set_all_coords(_t(torch, coords))
+        w = model.feats.get_emb().weight
+        w.zero_()
+        w.view(1, 512, 64)[:, :, :32] = _t(torch, feats)
+        pred, aux = model(torch.zeros(1, dtype=torch.long, device="cuda"), _t(torch, intr[[0, 5]][None]), _t(torch, poses[[0, 5]][None]), False)
+        direct = model.render(_t(torch, coords), _t(torch, feats), _t(torch, poses[[0, 5]][None]), _t(torch, intr[[0, 5]][None]))
+    assert pred.channels.shape == (1, 2, 16384, 3) and pred.mask.shape == (1, 2, 16384, 1) and pred.depth.shape == (1, 2, 16384, 1)
+    assert pred.get("ray_idx") is None
+    assert torch.equal(pred.channels, direct.channels)
+    assert set(aux) == {"coords", "feats", "feats_mean", "feats_log_var", "feats_std"}
+    keys = set(model.state_dict().keys())
+    for pre in ("field.", "renderer.field."):
+        for net, idxs in (("aggregator.local_field", (0, 2, 4, 6, 8)), ("channel_net", (0, 2, 4, 6, 8)), ("shape_net", (0, 2))):
+            for j in idxs:
+                assert f"{pre}{net}.{j}.weight" in keys and f"{pre}{net}.{j}.bias" in keys
+    assert "feats._extra_state" in keys and "coords._extra_state" in keys
+
+
+def test_tv_loss_self_query(syn, model, torch_cuda):
+    """Second caller of the kNN boundary (npcd/losses/neural_point_cloud_tv_loss.py:41-44): each point queries its own cloud."""
+    torch = torch_cuda
+    coords, _ = syn.make_clouds([7, 8])
+    c = _t(torch, coords)
+    nidx, pts, mask = model.field.aggregator.query_keypoints(c.view(2, 1, 512, 1, 3), c)
+    assert mask.shape == (2, 1, 512, 50, 1) and bool(mask[..., 0, :].all())  # every point finds at least itself
+    for b in range(2):
+        idx, cnt = orc.knn_exact(coords[b], coords[b])
+        np.testing.assert_array_equal(nidx[b * 512:(b + 1) * 512].cpu().numpy(), np.where(idx >= 0, idx + b * 512, -1))
+        assert (idx[:, 0] == np.arange(512)).all()  # distance 0 to itself sorts first
