@@ -25,19 +25,22 @@ class VoxelGrid:
         self.max_occ_voxels_per_example = max_occ_voxels_per_example
         self.ranges = tuple(ranges)
         self._grid = None
-        self._points_key = None
+        self._points = None  # the tensor the grid was built from (kept alive so its storage address cannot be recycled)
+        self._points_version = -1
 
     def set_pointset(self, points: torch.Tensor, actual_num_points: torch.Tensor = None) -> None:
         """points [B,P,3] (detached).  Builds the per-object acceleration grid on the current stream."""
         self._grid = ops.grid_build(points)
-        self._points_key = (points.data_ptr(), points._version, tuple(points.shape))
+        self._points = points
+        self._points_version = points._version
 
     def grid_for(self, points: torch.Tensor) -> "ops.Grid":
         """Grid for ``points``; reuses the one from ``set_pointset`` when it was built from the same tensor."""
-        key = (points.data_ptr(), points._version, tuple(points.shape))
-        if self._grid is None or key != self._points_key:
+        p = self._points
+        same = (self._grid is not None and p is not None and p.data_ptr() == points.data_ptr() and p.shape == points.shape
+                and p._version == self._points_version == points._version)
+        if not same:
             self.set_pointset(points.detach())
-            self._points_key = key
         return self._grid
 
     def query(self, raypos: torch.Tensor, k: int, radius_limit_scale: float, max_shading_pts: int):

@@ -202,7 +202,11 @@ def test_composite_fwd_bwd_vs_torch(syn, torch_cuda):
     alpha = 1 - torch.exp(-sig_d * delta)
     w = alpha * torch.cumprod(torch.cat([torch.ones(n, 1, dtype=torch.float64), 1 - alpha + 1e-10], -1), -1)[:, :-1]
     wt = w.sum(-1)
-    cd = torch.nan_to_num((w * dep).sum(-1) / wt, float("inf")).clamp(dep.min(), dep.max())
+    # rays whose total weight is 0 have depth 0/0 -> NaN -> +inf -> clamp (renderer.py:151-156); autograd through the raw 0/0
+    # yields NaN gradients (0 * inf), so the restatement uses the NaN-safe form of the same forward value (zero gradient there).
+    safe = wt > 0
+    cd = torch.where(safe, (w * dep).sum(-1) / torch.where(safe, wt, torch.ones_like(wt)), torch.full_like(wt, float("inf")))
+    cd = cd.clamp(dep.min(), dep.max())
     ray_id = torch.arange(n)[:, None].expand(n, SR)[m]
     comp = torch.zeros(n, 3, dtype=torch.float64).index_add_(0, ray_id, w[m][:, None] * r64[:, :3]) + 1 - wt[:, None]
     (wt * gm.cpu().double()).sum().add((cd * gd.cpu().double()).sum()).add((comp * gc.cpu().double()).sum()).backward()
