@@ -95,6 +95,40 @@ int npcd_field_simt_fwd(const int* nbr_idx, const float* sample_pos, const float
                         int stages /* bit0: pair MLP + aggregation -> agg_workspace, bit1: heads -> rgbs; 3 = both */,
                         int num_sms, void* stream);
 
+/* Tensor-core (tcgen05 / TMEM) version of the same field.  Each Linear layer is packed ONCE by npcd_tc_pack_weights into
+ * pre-swizzled fp16 hi/lo tiles: per 64-column K-block a 32 KB "hi" image then a 32 KB "lo" image of the [256 x 64] weight slice
+ * in the K-major SWIZZLE_128B shared-memory layout, multiplied by `scale` (a power of two; pass inv_scale = 1/scale).
+ * perm (optional, [k_pad] int32): source column of packed column k (-1 = zero); k_pad: multiple of 16, <= 256.
+ * Pair layer 0 uses OUR 112-column input order: [feat 0..31 | x: d, sin f0..9, cos f0..9, 0,0,0 | y: ... | z: ... | 8 zeros].  */
+typedef struct {
+  const void* packed_w; /* 2 * ceil(k_pad / 64) tiles of 32 KB */
+  const float* bias;    /* [256] */
+  float inv_scale;
+  int k_pad;
+} npcd_tc_layer;
+
+typedef struct {
+  int feat_dim;          /* must be 32 */
+  npcd_tc_layer pair[4]; /* local_field.0,2,4,6 */
+  npcd_tc_layer agg;     /* local_field.8 (after aggregation) */
+  npcd_tc_layer shape;   /* shape_net.0 */
+  npcd_tc_layer chan[4]; /* channel_net.0,2,4,6 */
+  const float* shape_out_w; /* shape_net.2 weight [256] */
+  const float* shape_out_b;
+  const float* chan_out_w; /* channel_net.8 weight [3,256] */
+  const float* chan_out_b;
+} npcd_mlp_tc_weights;
+
+int npcd_tc_pack_weights(const float* w /* [256,k_in] */, int k_in, const int* perm, int k_pad, float scale, void* out,
+                         void* stream);
+int npcd_field_tc_fwd(const int* nbr_idx, const float* sample_pos, const float* kp_pos, const float* kp_feat,
+                      const long long* n_samples_dev, long long capacity, const npcd_mlp_tc_weights* weights,
+                      float* agg_workspace, float* rgbs, float* feat_out, int stages, int* error_flag /* device int, optional */,
+                      int num_sms, void* stream);
+/* self-test: out[s,:] = x[s,:] @ W^T + b for one packed 256x256 layer */
+int npcd_tc_linear_probe(const float* x, const long long* n_rows_dev, long long capacity, const npcd_tc_layer* layer, float* out,
+                         int* error_flag, int num_sms, void* stream);
+
 /* ---- compositing: replaces Renderer.get_depths_from_shading_pts (renderers/renderer.py:95-110), VolumeRenderer.get_alpha
  * (renderers/volume_renderer.py:23-39), Renderer.ray_march (renderers/renderer.py:120-185).
  *   out_mask [n_sel], out_depth [n_sel] (UNCLAMPED, NaN -> +inf), out_rgb [n_sel,3]; range_scratch (8 bytes) accumulates the

@@ -41,6 +41,28 @@ class SimtWeights(C.Structure):
     ]
 
 
+class TcLayer(C.Structure):
+    """mirror of ``npcd_tc_layer``"""
+
+    _fields_ = [("packed_w", P), ("bias", P), ("inv_scale", C.c_float), ("k_pad", C.c_int)]
+
+
+class TcWeights(C.Structure):
+    """mirror of ``npcd_mlp_tc_weights``"""
+
+    _fields_ = [
+        ("feat_dim", C.c_int),
+        ("pair", TcLayer * 4),
+        ("agg", TcLayer),
+        ("shape", TcLayer),
+        ("chan", TcLayer * 4),
+        ("shape_out_w", P),
+        ("shape_out_b", P),
+        ("chan_out_w", P),
+        ("chan_out_b", P),
+    ]
+
+
 # name -> argtypes; every entry point declared in include/npcd_b200.h (tests check the header against this table)
 SIGNATURES = {
     "npcd_rays_generate": [P, P, I, I, P, I, F, P, P, P, P, P, P, P],
@@ -52,6 +74,9 @@ SIGNATURES = {
     "npcd_knn_fill": [P, P, P, P, P, P, L, P, P, I, I, I, P, P, F, L, P, P, P, P],
     "npcd_knn_points": [P, P, L, I, I, P, P, F, P, P],
     "npcd_field_simt_fwd": [P, P, P, P, P, L, P, P, P, P, I, I, P],
+    "npcd_tc_pack_weights": [P, I, P, I, F, P, P],
+    "npcd_field_tc_fwd": [P, P, P, P, P, L, P, P, P, P, I, P, I, P],
+    "npcd_tc_linear_probe": [P, P, L, P, P, P, I, P],
     "npcd_composite_fwd": [P, P, P, P, P, L, I, P, P, P, P, I, P],
     "npcd_clamp_depth": [P, L, P, P, P],
     "npcd_composite_bwd": [P, P, P, L, I, P, P, P, P, P, P, P, P],

@@ -392,6 +392,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
         } else if (L.epi == EPI_AGG) {
           // bias + LeakyReLU, scale by the normalised inverse-distance weight of this pair, stage as fp32 in the (now free) A
           // region with a 16-byte XOR swizzle, then sum the 8 slot rows of every sample (fields/aggregators/mlp.py:86-88,119-121)
+          epi_bar_sync();  // wts[] was written by other warps in the prologue
           float wsum = 0.f;
 #pragma unroll
           for (int j = 0; j < 8; ++j) wsum += wts[(row & ~7) + j];
@@ -481,7 +482,10 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
 }
 
 // Pack an fp32 [256, k_in] nn.Linear weight into per-K-block pre-swizzled fp16 hi/lo tiles (the exact shared-memory image the

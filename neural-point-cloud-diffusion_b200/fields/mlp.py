@@ -43,15 +43,17 @@ class MLP(Module):
     # ---- weights packed for the kernels, re-packed whenever a parameter changes (optimizer step, load_state_dict) ----
     def packed_weights(self):
         params = list(self.parameters())
-        key = tuple((p.data_ptr(), p._version) for p in params)
+        key = (self.mlp_impl,) + tuple((p.data_ptr(), p._version) for p in params)
         if self._packed is None or key != self._packed_key:
-            self._packed = ops.PackedSimtWeights(self.aggregator.local_field, self.shape_net, self.channel_net, self.aggregator.in_dim)
+            cls = ops.PackedTcWeights if self.mlp_impl == "tc" else ops.PackedSimtWeights
+            self._packed = cls(self.aggregator.local_field, self.shape_net, self.channel_net, self.aggregator.in_dim)
             self._packed_key = key
         return self._packed
 
     def evaluate(self, nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, want_feat=False):
         """-> rgbs [capacity,4] = (r,g,b,sigma).  Fused CUDA path, no autograd."""
-        return ops.field_simt_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, self.packed_weights(), want_feat)
+        fn = ops.field_tc_fwd if self.mlp_impl == "tc" else ops.field_simt_fwd
+        return fn(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, self.packed_weights(), want_feat)
 
     def evaluate_autograd(self, nbr_idx, sample_pos, kp_pos, kp_feat):
         """Differentiable w.r.t. kp_feat and the MLP parameters (`aggregators/mlp.py:69-88,119-121`, `field.py:126-141`)."""

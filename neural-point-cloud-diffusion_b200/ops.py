@@ -6,6 +6,7 @@ sm_100a kernels from ``libnpcd_b200.so`` on ``torch.cuda.current_stream()``; not
 from __future__ import annotations
 
 import ctypes as C
+import math
 from dataclasses import dataclass
 from typing import Optional
 
@@ -218,6 +219,111 @@ class PackedSimtWeights:
         s.shape_out_w, s.shape_out_b = vec(sn[1].weight.reshape(-1)), vec(sn[1].bias)
         s.chan_out_w, s.chan_out_b = vec(cn[4].weight), vec(cn[4].bias)
         self.struct = s
+
+
+def pair_input_perm(feat_dim: int = 32, n_freqs: int = 10):
+    """Source column (in the reference's [feat | d(3) | per-axis sin*10, cos*10] order, `aggregators/mlp.py:82`,
+    `positional_encoder.py:17-20`) of every column of OUR 112-wide first-layer input (-1 = zero padding)."""
+    assert feat_dim == 32 and n_freqs == 10
+    perm = list(range(32))
+    for c in range(3):
+        perm.append(32 + c)
+        perm += [35 + 20 * c + i for i in range(10)]
+        perm += [35 + 20 * c + 10 + i for i in range(10)]
+        perm += [-1, -1, -1]
+    perm += [-1] * 8
+    assert len(perm) == 112
+    return perm
+
+
+class PackedTcWeights:
+    """MLP weights packed for ``npcd_field_tc_fwd``: pre-swizzled fp16 hi/lo tiles, power-of-two scaled (see include/npcd_b200.h)."""
+
+    def __init__(self, local_field, shape_net, channel_net, feat_dim: int):
+        if feat_dim != 32:
+            raise NotImplementedError("tensor-core field kernel is specialised for feat_dim=32 (use mlp_impl='simt')")
+        lin = lambda seq: [m for m in seq if isinstance(m, torch.nn.Linear)]
+        lf, sn, cn = lin(local_field), lin(shape_net), lin(channel_net)
+        assert len(lf) == 5 and len(sn) == 2 and len(cn) == 5, "unexpected MLP depth"
+        dev = lf[0].weight.device
+        self.keep = []
+        s = _lib.TcWeights()
+        s.feat_dim = feat_dim
+        perm0 = torch.tensor(pair_input_perm(), dtype=torch.int32, device=dev)
+        self.keep.append(perm0)
+
+        def layer(dst, l, k_pad, perm=None):
+            w = l.weight.detach().float().contiguous()
+            b = l.bias.detach().float().contiguous()
+            assert w.shape[0] == HIDDEN
+            maxabs = float(w.abs().max().item())
+            scale = 2.0 ** math.floor(math.log2(4.0 / maxabs)) if maxabs > 0 else 1.0
+            n_kb = (k_pad + 63) // 64
+            out = torch.zeros(n_kb * 2 * 32768, dtype=torch.uint8, device=dev)
+            call("npcd_tc_pack_weights", ptr(w), w.shape[1], ptr(perm), k_pad, float(scale), ptr(out), _stream())
+            _count(1)
+            self.keep += [w, b, out]
+            dst.packed_w, dst.bias, dst.inv_scale, dst.k_pad = out.data_ptr(), b.data_ptr(), 1.0 / scale, k_pad
+
+        def vec(t):
+            v = t.detach().float().contiguous()
+            self.keep.append(v)
+            return v.data_ptr()
+
+        layer(s.pair[0], lf[0], 112, perm0)
+        for i in range(1, 4):
+            layer(s.pair[i], lf[i], 256)
+        layer(s.agg, lf[4], 256)
+        layer(s.shape, sn[0], 256)
+        for i in range(4):
+            layer(s.chan[i], cn[i], 256)
+        s.shape_out_w, s.shape_out_b = vec(sn[1].weight.reshape(-1)), vec(sn[1].bias)
+        s.chan_out_w, s.chan_out_b = vec(cn[4].weight), vec(cn[4].bias)
+        self.struct = s
+        self.error_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+
+
+def field_tc_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity: int, weights: PackedTcWeights,
+                 want_feat: bool = False):
+    """Tensor-core (tcgen05) field: rgbs [capacity,4] = (r,g,b,sigma); feat [capacity,256] if requested."""
+    dev = sample_pos.device
+    rgbs = torch.empty((capacity, 4), device=dev)
+    feat = torch.empty((capacity, HIDDEN), device=dev) if want_feat else None
+    if capacity == 0:
+        return rgbs, feat
+    agg = torch.empty((capacity, HIDDEN), device=dev)
+    kp_pos = kp_pos.detach().contiguous().float()
+    kp_feat = kp_feat.detach().contiguous().float()
+    args = (ptr(nbr_idx), ptr(sample_pos), ptr(kp_pos), ptr(kp_feat), ptr(n_samples_dev), capacity, C.byref(weights.struct),
+            ptr(agg), ptr(rgbs), ptr(feat))
+    _timed("pair_mlp", lambda: call("npcd_field_tc_fwd", *args, 1, ptr(weights.error_flag), sm_count(dev), _stream()))
+    _timed("heads", lambda: call("npcd_field_tc_fwd", *args, 2, ptr(weights.error_flag), sm_count(dev), _stream()))
+    _count(2)
+    return rgbs, feat
+
+
+def tc_linear_probe(x, linear: torch.nn.Linear):
+    """out = x @ W^T + b through the tcgen05 engine (one packed 256x256 layer); self-test of descriptors / swizzle / TMEM."""
+    _need_cuda(x)
+    dev = x.device
+    x = x.contiguous().float()
+    n = x.shape[0]
+    w = linear.weight.detach().float().contiguous()
+    b = linear.bias.detach().float().contiguous()
+    maxabs = float(w.abs().max().item())
+    scale = 2.0 ** math.floor(math.log2(4.0 / maxabs)) if maxabs > 0 else 1.0
+    packed = torch.zeros(4 * 2 * 32768, dtype=torch.uint8, device=dev)
+    call("npcd_tc_pack_weights", ptr(w), 256, None, 256, float(scale), ptr(packed), _stream())
+    lay = _lib.TcLayer(packed.data_ptr(), b.data_ptr(), 1.0 / scale, 256)
+    out = torch.zeros((n, HIDDEN), device=dev)
+    nrows = torch.tensor([n], dtype=torch.int64, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    call("npcd_tc_linear_probe", ptr(x), ptr(nrows), n, C.byref(lay), ptr(out), ptr(err), sm_count(dev), _stream())
+    _count(2)
+    torch.cuda.synchronize()
+    if int(err.item()) != 0:
+        raise RuntimeError("npcd_tc_linear_probe: shared memory not 1024-byte aligned")
+    return out
 
 
 _SM_COUNT = {}
