@@ -35,7 +35,8 @@ class MLP(Module):
         self.shape_net = define_mlp(shape_layers, self.hid_dim, d_out=1, act=activation, layer_norm=layer_norm)
         self._packed = None
         self._packed_key = None
-        self.mlp_impl = "simt"  # "simt": fp32 CUDA-core kernels (mlp_simt.cu); "tc": tcgen05 tensor-core kernels (mlp_tc.cu)
+        # "tc": tcgen05 tensor-core kernels (mlp_tc.cu, default); "simt": fp32 CUDA-core kernels (mlp_simt.cu, any feat_dim)
+        self.mlp_impl = "tc" if in_dim == 32 else "simt"
 
     def compute_dtype(self) -> str:
         return {"simt": "f32", "tc": "f32 (fp16 2-way split, 3-product tcgen05 emulation, fp32 accumulate)"}[self.mlp_impl]

@@ -403,6 +403,24 @@ def tc_model(model):
     model.field.mlp_impl = prev
 
 
+@pytest.fixture()
+def simt_model(model):
+    prev = model.field.mlp_impl
+    model.field.mlp_impl = "simt"
+    yield model
+    model.field.mlp_impl = prev
+
+
+@pytest.mark.parametrize("name", ["view32", "box32"])
+def test_simt_field_vs_oracle(name, syn, simt_model, weights, torch_cuda):
+    test_field_kernels_vs_oracle(name, syn, simt_model, weights, torch_cuda)
+
+
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_simt_render_vs_golden(name, syn, simt_model, torch_cuda):
+    test_render_vs_golden_small(name, syn, simt_model, torch_cuda)
+
+
 @pytest.mark.parametrize("name", ["view32", "box32"])
 def test_tc_field_vs_oracle(name, syn, tc_model, weights, torch_cuda):
     torch = torch_cuda
@@ -440,14 +458,16 @@ def test_tc_matches_simt_full_size(syn, model, cameras, torch_cuda):
     views = [0, 31, 62, 93, 124, 155, 186, 217]
     coords, feats = syn.make_clouds([0])
     args = (_t(torch, coords), _t(torch, feats), _t(torch, poses[views][None]), _t(torch, intr[views][None]), 128, False)
+    prev = model.field.mlp_impl
     with torch.no_grad():
-        a = model.renderer(*args)
-        model.field.mlp_impl = "tc"
         try:
+            model.field.mlp_impl = "simt"
+            a = model.renderer(*args)
+            model.field.mlp_impl = "tc"
             b = model.renderer(*args)
             c = model.renderer(*args)
         finally:
-            model.field.mlp_impl = "simt"
+            model.field.mlp_impl = prev
     for k in ("mask", "depth", "channels"):
         assert torch.equal(b[k], c[k]), k
         np.testing.assert_allclose(a[k].cpu().numpy(), b[k].cpu().numpy(), atol=2e-5, rtol=0, err_msg=k)
