@@ -99,10 +99,11 @@ int npcd_field_simt_fwd(const int* nbr_idx, const float* sample_pos, const float
  * pre-swizzled fp16 hi/lo tiles: per 64-column K-block a 32 KB "hi" image then a 32 KB "lo" image of the [256 x 64] weight slice
  * in the K-major SWIZZLE_128B shared-memory layout, multiplied by `scale` (a power of two; pass inv_scale = 1/scale).
  * perm (optional, [k_pad] int32): source column of packed column k (-1 = zero); k_pad: multiple of 16, <= 256.
- * Pair layer 0 uses OUR 112-column input order: [feat 0..31 | x: d, sin f0..9, cos f0..9, 0,0,0 | y: ... | z: ... | 8 zeros].  */
+ * Pair layer 0 uses OUR 112-column input order: [feat 0..31 | x: d, sin f0..9, cos f0..9, 0,0,0 | y: ... | z: ... | 8 zeros].
+ * Biases and the two narrow output layers are HOST pointers: they travel to the kernel by value (constant bank).           */
 typedef struct {
-  const void* packed_w; /* 2 * ceil(k_pad / 64) tiles of 32 KB */
-  const float* bias;    /* [256] */
+  const void* packed_w; /* DEVICE: 2 * ceil(k_pad / 64) tiles of 32 KB */
+  const float* bias;    /* HOST: [256] */
   float inv_scale;
   int k_pad;
 } npcd_tc_layer;
@@ -113,20 +114,28 @@ typedef struct {
   npcd_tc_layer agg;     /* local_field.8 (after aggregation) */
   npcd_tc_layer shape;   /* shape_net.0 */
   npcd_tc_layer chan[4]; /* channel_net.0,2,4,6 */
-  const float* shape_out_w; /* shape_net.2 weight [256] */
-  const float* shape_out_b;
-  const float* chan_out_w; /* channel_net.8 weight [3,256] */
-  const float* chan_out_b;
+  const float* shape_out_w; /* HOST: shape_net.2 weight [256] */
+  const float* shape_out_b; /* HOST: [1] */
+  const float* chan_out_w;  /* HOST: channel_net.8 weight [3,256] */
+  const float* chan_out_b;  /* HOST: [3] */
 } npcd_mlp_tc_weights;
 
 int npcd_tc_pack_weights(const float* w /* [256,k_in] */, int k_in, const int* perm, int k_pad, float scale, void* out,
                          void* stream);
+/* workspace (device bytes) for `capacity` kept samples (< 2^27 per launch): the pre-split [S,256] aggregate image that links the
+ * pair stage to the heads stage, the dense pair packing (pair offsets, tile starts) and scan scratch.                          */
+int npcd_field_tc_workspace_bytes(long long capacity, size_t* bytes);
 int npcd_field_tc_fwd(const int* nbr_idx, const float* sample_pos, const float* kp_pos, const float* kp_feat,
-                      const long long* n_samples_dev, long long capacity, const npcd_mlp_tc_weights* weights,
-                      float* agg_workspace, float* rgbs, float* feat_out, int stages, int* error_flag /* device int, optional */,
-                      int num_sms, void* stream);
-/* self-test: out[s,:] = x[s,:] @ W^T + b for one packed 256x256 layer */
-int npcd_tc_linear_probe(const float* x, const long long* n_rows_dev, long long capacity, const npcd_tc_layer* layer, float* out,
+                      const long long* n_samples_dev, long long capacity, const npcd_mlp_tc_weights* weights, void* workspace,
+                      size_t workspace_bytes, float* rgbs, float* feat_out,
+                      int stages /* bit0: dense packing + pair MLP + aggregation -> workspace, bit1: heads -> rgbs */,
+                      int* error_flag /* device int, optional */, int num_sms, void* stream);
+/* fp32 rows [n,256] <-> the pre-split operand image the tensor-core kernels exchange: per 128-row tile 4 K-blocks x
+ * (fp16 hi 16 KB, fp16 lo 16 KB) in the SWIZZLE_128B layout; ceil(n / 128) * 128 KB.                                           */
+int npcd_tc_rows_to_image(const float* rows, long long n, void* image, void* stream);
+int npcd_tc_image_to_rows(const void* image, long long n, float* rows, void* stream);
+/* self-test: out[s,:] = x[s,:] @ W^T + b for one packed 256x256 layer; `image` = npcd_tc_rows_to_image(x) */
+int npcd_tc_linear_probe(const void* image, const long long* n_rows_dev, long long capacity, const npcd_tc_layer* layer, float* out,
                          int* error_flag, int num_sms, void* stream);
 
 /* ---- compositing: replaces Renderer.get_depths_from_shading_pts (renderers/renderer.py:95-110), VolumeRenderer.get_alpha

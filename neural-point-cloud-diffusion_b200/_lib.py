@@ -75,7 +75,10 @@ SIGNATURES = {
     "npcd_knn_points": [P, P, L, I, I, P, P, F, P, P],
     "npcd_field_simt_fwd": [P, P, P, P, P, L, P, P, P, P, I, I, P],
     "npcd_tc_pack_weights": [P, I, P, I, F, P, P],
-    "npcd_field_tc_fwd": [P, P, P, P, P, L, P, P, P, P, I, P, I, P],
+    "npcd_field_tc_workspace_bytes": [L, P],
+    "npcd_field_tc_fwd": [P, P, P, P, P, L, P, P, C.c_size_t, P, P, I, P, I, P],
+    "npcd_tc_rows_to_image": [P, L, P, P],
+    "npcd_tc_image_to_rows": [P, L, P, P],
     "npcd_tc_linear_probe": [P, P, L, P, P, P, I, P],
     "npcd_composite_fwd": [P, P, P, P, P, L, I, P, P, P, P, I, P],
     "npcd_clamp_depth": [P, L, P, P, P],

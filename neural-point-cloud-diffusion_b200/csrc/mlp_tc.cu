@@ -1,23 +1,28 @@
-// G1/G2/M1/A1/M2/M3 on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
+// G1/G2/M1/A1/M2/M3 on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only -- kernel generation 2.
 // Same contract as mlp_simt.cu (reference: fields/aggregators/mlp.py:69-88,119-121, fields/mlp.py:38-72, fields/field.py:126-141).
 //
 // Precision: the reference runs TRUE fp32 GEMMs (no TF32, train_pointnerf.py:16-17) and the parity bar is 1e-4 on RGB after ten
 // chained layers, which single-pass TF32/BF16 cannot meet.  Every operand is therefore split into two fp16 halves
 // (x = hi + lo, 22 significant bits) and each layer is accumulated in fp32 TMEM from THREE tcgen05.mma.kind::f16 products
-// (hi*hi + lo*hi + hi*lo; the dropped lo*lo term is 2^-22 relative).  kind::f16 runs at twice the TF32 rate, so this costs
-// 3 bf16-rate passes where 3xTF32 would cost 6.  Weights are pre-scaled by a power of two per layer (exact) so the lo halves
-// stay out of the fp16 subnormal range; the inverse scale is folded into the epilogue FMA.
+// (hi*hi + lo*hi + hi*lo; the dropped lo*lo term is 2^-22 relative).  Weights are pre-scaled by a power of two per layer (exact)
+// so the lo halves stay out of the fp16 subnormal range; the inverse scale is folded into the epilogue FMA.
 //
-// Kernel shape (one persistent CTA per SM, 320 threads, warp-specialised):
-//   warp 0      : producer.  Streams pre-swizzled 32 KB weight tiles (256 out x 64 k, hi or lo) from L2 into a 3-stage ring
-//                 with cp.async.bulk (UBLKCP) completing on mbarriers.
-//   warp 1      : allocates 256 TMEM columns, then one elected lane issues tcgen05.mma (M=128, N=256, K=16, cta_group::1),
-//                 A and B both from shared memory (K-major, SWIZZLE_128B descriptors); tcgen05.commit frees ring slots and
-//                 publishes the accumulator.
-//   warps 2..9  : 256 prologue/epilogue threads, two per tile row (column halves).  tcgen05.ld the fp32 accumulator, apply
-//                 scale+bias+LeakyReLU, split to fp16 hi/lo and write the NEXT layer's A operand straight into the swizzled
-//                 shared-memory image (activations never leave the SM between layers).
-// Tile = 128 rows: 16 samples x 8 neighbour slots (pair MLP) or 128 samples (heads).
+// Kernel shape (one persistent CTA per SM, 352 threads, warp-specialised):
+//   warp 0      : weight producer.  Streams pre-swizzled 32 KB weight tiles (256 out x 64 k, hi or lo) from L2 into a 3-stage
+//                 ring with cp.async.bulk (UBLKCP) completing on mbarriers.
+//   warp 1      : allocates all 512 TMEM columns (two 128x256 fp32 accumulators), then one elected lane issues tcgen05.mma
+//                 (M=128, N=256, K=16, cta_group::1), A and B from shared memory (K-major SWIZZLE_128B descriptors).
+//   warps 2..9  : 256 prologue/epilogue threads, two per tile row.  The epilogue of layer l runs in 32-column chunks: tcgen05.ld,
+//                 scale+bias+LeakyReLU, fp16 hi/lo split, store IN PLACE over the layer's own (already consumed) A operand, and
+//                 publish each 64-column K-block on its own mbarrier -- the MMAs of layer l+1 (into the OTHER accumulator) start
+//                 as soon as K-block 0 is there, so the tensor pipe only idles for one chunk per layer.
+//   warp 10     : heads mode only: bulk-copies the next tile's pre-split A operand (written by the pair kernel) into the
+//                 K-blocks the last layer's MMAs have released.
+// Pair mode packs (sample, neighbour) pairs DENSELY: tile t holds the samples whose first pair offset lies in [121 t, 121 t+121)
+// (<= 120 + 8 = 128 rows, whole samples only), instead of 8 slots per sample (21 % padding at 6.3 neighbours per sample).
+// The next tile's gather + positional encoding is computed by the epilogue threads while the tensor pipe works on layers 1..2
+// and is stored during layer 3 into the K-blocks that layer has already consumed.
+#include <cub/cub.cuh>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -26,19 +31,35 @@
 namespace npcd {
 namespace tc {
 
-constexpr int kThreadsTc = 320;
+constexpr int kThreadsTc = 352;
 constexpr int kEpiThreads = 256;
 constexpr int kTileBytesA = 128 * 128;        // one K-block (64 fp16) of 128 rows
 constexpr int kTileBytesW = 256 * 128;        // one K-block of 256 output rows
 constexpr int kStages = 3;
-constexpr int kSmemA = 4 * 2 * kTileBytesA;   // 4 K-blocks x (hi, lo) = 128 KB (aliased by the fp32 aggregation staging)
+constexpr int kSmemA = 4 * 2 * kTileBytesA;   // 4 K-blocks x (hi, lo) = 128 KB; K-blocks 2..3 double as fp32 aggregation staging
 constexpr int kSmemW = kStages * kTileBytesW; // 96 KB
 constexpr int kSmemMisc = 3072;
 constexpr int kSmemTotal = kSmemA + kSmemW + kSmemMisc;  // 232448 = the 227 KB per-CTA maximum
 constexpr uint32_t kIdesc = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);  // D=f32, A=B=f16, K-major, N=256, M=128
-constexpr int kTmemCols = 256;
+constexpr int kTmemCols = 512;
+constexpr int kPackRows = 121;                // pair offsets per dense tile
+constexpr int kImgTileBytes = 4 * 2 * kTileBytesA;  // one 128-sample tile of the pre-split [S,256] operand image (128 KB)
 
 enum Epi { EPI_ACT = 0, EPI_LINEAR = 1, EPI_AGG = 2, EPI_DOT1 = 3, EPI_DOT3 = 4, EPI_DUMP = 5 };
+enum Mode { MODE_PAIR = 0, MODE_HEADS = 1, MODE_PROBE = 2 };
+
+// misc shared-memory layout (byte offsets)
+constexpr int kOffBars = 0;       // 24 mbarriers
+constexpr int kOffTmem = 192;
+constexpr int kOffInfo = 208;     // int[2][4]: s_begin, n_samp, n_rows
+constexpr int kOffWts = 256;      // float[2][128] raw inverse-distance weights           (pair)
+constexpr int kOffRowSamp = 1280; // u8[2][128] row -> sample-in-tile                      (pair)
+constexpr int kOffSampRow = 1536; // u8[2][128] sample-in-tile -> first row                (pair)
+constexpr int kOffSampCnt = 1792; // u8[2][128] sample-in-tile -> rows                     (pair)
+constexpr int kOffPart = 256;     // float[128][4] cross-half partial dot products         (heads; aliases the pair arrays)
+
+// barrier indices
+constexpr int kBarWFull = 0, kBarWEmpty = 3, kBarARdy = 6, kBarA0Rdy = 10, kBarAFree = 14, kBarAccRdy = 18, kBarAccFree = 20;
 
 // ---------------------------------------------------------------------------------------------------------------- PTX ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -92,7 +113,8 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+// asynchronous TMEM -> register load of 32 consecutive fp32 columns of this thread's lane; complete after tmem_wait(v)
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -103,7 +125,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// tcgen05.wait::ld with the destination registers as in/out operands, so no use of them can be scheduled above the wait
+__device__ __forceinline__ void tmem_wait(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                 "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                 "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
 }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(1)<<16 | SBO(1024B>>4)<<32 |
@@ -113,68 +144,123 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 }
 
 // byte offset of the 16-byte chunk holding columns [8*c16, 8*c16+8) of `row` inside a K-block tile
-__device__ __forceinline__ uint32_t swz(int row, int c16) { return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((c16 ^ (row & 7)) << 4)); }
+__host__ __device__ __forceinline__ uint32_t swz(int row, int c16) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((c16 ^ (row & 7)) << 4));
+}
 
 __device__ __forceinline__ float lrelu(float x) { return fmaxf(x, 0.01f * x); }
 
-// split 8 fp32 values into fp16 hi / lo and store them as one 16-byte chunk each (columns col..col+7 of `row`)
-__device__ __forceinline__ void store_split8(uint8_t* sA, int row, int col, const float (&y)[8]) {
-  uint32_t hi[4], lo[4];
+// sin and cos of |a| < ~1e4 to ~1e-7 absolute: two-term Cody-Waite reduction by pi/2 (exact first step under FMA), Taylor
+// polynomials to r^9 / r^8 on |r| <= pi/4 (truncation 2e-9 / 2e-8), quadrant from the low bits of the rounding magic number.
+// The positional-encoding arguments are |x_rel * 2^i pi| <= 129 (utils/positional_encoder.py:17-20); this replaces sincosf,
+// whose (never taken) Payne-Hanek slow path would be inlined thirty times.
+__device__ __forceinline__ void sincos_small(float a, float& sn, float& cs) {
+  const float t = fmaf(a, 0.636619747f, 12582912.0f);
+  const int quad = __float_as_int(t);
+  const float q = t - 12582912.0f;
+  float r = fmaf(q, -1.57079637f, a);
+  r = fmaf(q, 4.37113883e-8f, r);
+  const float r2 = r * r;
+  float s = fmaf(r2, 2.75573192e-6f, -1.98412698e-4f);
+  s = fmaf(s, r2, 8.33333333e-3f);
+  s = fmaf(s, r2, -1.66666667e-1f);
+  s = fmaf(s * r2, r, r);
+  float c = fmaf(r2, 2.48015873e-5f, -1.38888889e-3f);
+  c = fmaf(c, r2, 4.16666667e-2f);
+  c = fmaf(c, r2, -0.5f);
+  c = fmaf(c, r2, 1.0f);
+  const float u = (quad & 1) ? c : s, w = (quad & 1) ? s : c;
+  sn = (quad & 2) ? -u : u;
+  cs = ((quad + 1) & 2) ? -w : w;
+}
+
+// fp16 hi / lo halves of 8 fp32 values as two 16-byte vectors
+__device__ __forceinline__ void split8(const float (&y)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const __half2 h = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
-    const float2 f = __half22float2(h);
-    const __half2 l = __floats2half2_rn(y[2 * j] - f.x, y[2 * j + 1] - f.y);
-    hi[j] = *reinterpret_cast<const uint32_t*>(&h);
-    lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+    const __half2 hh = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
+    const float2 f = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(y[2 * j] - f.x, y[2 * j + 1] - f.y);
+    h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[j] = *reinterpret_cast<const uint32_t*>(&ll);
   }
-  uint8_t* p = sA + (col >> 6) * (2 * kTileBytesA) + swz(row, (col & 63) >> 3);
-  *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  *reinterpret_cast<uint4*>(p + kTileBytesA) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 struct Layer {
-  const uint8_t* w;   // packed tiles: for each K-block: hi tile (32 KB) then lo tile (32 KB)
-  const float* bias;  // [256]
-  float inv_scale;    // weights were multiplied by 1/inv_scale (a power of two) when packed
-  int ksteps;         // K / 16 (a multiple of 1; K-blocks = ceil(ksteps / 4))
+  const uint8_t* w;  // packed tiles: for each K-block: hi tile (32 KB) then lo tile (32 KB)
+  float inv_scale;   // weights were multiplied by 1/inv_scale (a power of two) when packed
+  int ksteps;        // K / 16
   int epi;
 };
 
+// Passed by value (constant bank): biases and the two narrow output layers are read with warp-uniform constant loads.
 struct Params {
   Layer layers[6];
+  float bias[6][256];
+  float shape_out_w[256];
+  float chan_out_w[3][256];
+  float shape_out_b;
+  float chan_out_b[3];
   int n_layers;
-  int mode;  // 0 = pair MLP, 1 = heads, 2 = probe (one linear layer, dump fp32)
   // pair
   const int* nbr_idx;
   const float4* sample_pos;
   const float* kp_pos;
   const float* kp_feat;
-  float* agg;  // [S,256] (pair: out, heads/probe: in)
+  const int* pair_off;    // [S+1] exclusive scan of the neighbour counts
+  const int* tile_start;  // [n_tiles+1] first sample of every dense tile
+  const int* n_tiles_dev;
+  uint8_t* img;           // pre-split [S,256] operand image: pair mode writes it, heads / probe mode read it
   // heads
-  const float* shape_out_w;
-  const float* shape_out_b;
-  const float* chan_out_w;
-  const float* chan_out_b;
   float4* rgbs;
-  float* feat_out;  // optional [S,256] (heads: local_field output; probe: layer output)
+  float* feat_out;  // optional [S,256] fp32 (heads: local_field output; probe: layer output)
   const long long* n_samples_dev;
   long long capacity;
   int* error_flag;
 };
 
+// One chunk (32 accumulator columns starting at c0) of an ACT / LINEAR epilogue: y = [lrelu](acc * inv + b) -> fp16 hi/lo ->
+// K-block (c0 >> 6) of the A operand, 16-byte chunks (c0 & 63) / 8 .. +3.
+// slope = 0.01 (LeakyReLU) or 1 (linear layer: max(y, y) = y).
+__device__ __forceinline__ void epi_chunk_store(const Params& P, int l, float inv, float slope, const uint32_t (&v)[32], int c0,
+                                                uint8_t* sA, uint32_t rowbase, int x7, float* feat_row) {
+  uint8_t* kb_base = sA + (c0 >> 6) * (2 * kTileBytesA) + rowbase;
+  const int c16_0 = (c0 & 63) >> 3;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float4 b0 = *reinterpret_cast<const float4*>(&P.bias[l][c0 + g * 8]);
+    const float4 b1 = *reinterpret_cast<const float4*>(&P.bias[l][c0 + g * 8 + 4]);
+    float y[8] = {fmaf(__uint_as_float(v[g * 8 + 0]), inv, b0.x), fmaf(__uint_as_float(v[g * 8 + 1]), inv, b0.y),
+                  fmaf(__uint_as_float(v[g * 8 + 2]), inv, b0.z), fmaf(__uint_as_float(v[g * 8 + 3]), inv, b0.w),
+                  fmaf(__uint_as_float(v[g * 8 + 4]), inv, b1.x), fmaf(__uint_as_float(v[g * 8 + 5]), inv, b1.y),
+                  fmaf(__uint_as_float(v[g * 8 + 6]), inv, b1.z), fmaf(__uint_as_float(v[g * 8 + 7]), inv, b1.w)};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], slope * y[j]);
+    if (feat_row) {
+      *reinterpret_cast<float4*>(feat_row + c0 + g * 8) = make_float4(y[0], y[1], y[2], y[3]);
+      *reinterpret_cast<float4*>(feat_row + c0 + g * 8 + 4) = make_float4(y[4], y[5], y[6], y[7]);
+    }
+    uint4 hi, lo;
+    split8(y, hi, lo);
+    uint8_t* p = kb_base + (((c16_0 + g) ^ x7) << 4);
+    *reinterpret_cast<uint4*>(p) = hi;
+    *reinterpret_cast<uint4*>(p + kTileBytesA) = lo;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------- kernel ----
+template <int kMode>
 __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constant__ Params P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sW = smem + kSmemA;
   uint8_t* misc = smem + kSmemA + kSmemW;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);  // full[3], empty[3], a_ready, acc_ready
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 64);
-  float* wts = reinterpret_cast<float*>(misc + 128);     // [128] raw inverse-distance weights (pair) / sigma partials (heads)
-  float* part3 = reinterpret_cast<float*>(misc + 640);   // [128][3]
-  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kStages), bar_a = smem_u32(bars + 2 * kStages),
-                 bar_acc = smem_u32(bars + 2 * kStages + 1);
+  const uint32_t bars = smem_u32(misc + kOffBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + kOffTmem);
+  auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if ((smem_u32(smem) & 1023u) != 0u) {  // SWIZZLE_128B atoms need 1024-byte aligned tiles
@@ -182,9 +268,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
     return;
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
-    mbar_init(bar_a, kEpiThreads);
-    mbar_init(bar_acc, 1);
+    for (int i = 0; i < kStages; ++i) { mbar_init(bar(kBarWFull + i), 1); mbar_init(bar(kBarWEmpty + i), 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(bar(kBarARdy + i), 8); mbar_init(bar(kBarA0Rdy + i), 1); mbar_init(bar(kBarAFree + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(kBarAccRdy + i), 1); mbar_init(bar(kBarAccFree + i), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
@@ -194,22 +280,22 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   const long long S = min(*P.n_samples_dev, P.capacity);
-  const int rows_per_tile = (P.mode == 0) ? 16 : 128;  // samples per tile
-  const long long n_tiles = (S + rows_per_tile - 1) / rows_per_tile;
+  const int n_tiles = (kMode == MODE_PAIR) ? *P.n_tiles_dev : (int)((S + 127) / 128);
+  const int n_layers = P.n_layers;
 
   if (warp == 0) {
-    // ===================================================== producer =====================================================
+    // ================================================= weight producer ==================================================
     if (lane == 0) {
       int st = 0;
       uint32_t ph = 0;
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int l = 0; l < P.n_layers; ++l) {
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int l = 0; l < n_layers; ++l) {
           const int nkb = (P.layers[l].ksteps + 3) >> 2;
           const uint8_t* src = P.layers[l].w;
           for (int t = 0; t < 2 * nkb; ++t) {
-            mbar_wait(bar_empty + 8 * st, ph ^ 1);
-            mbar_expect_tx(bar_full + 8 * st, kTileBytesW);
-            bulk_g2s(smem_u32(sW + st * kTileBytesW), src + (size_t)t * kTileBytesW, kTileBytesW, bar_full + 8 * st);
+            mbar_wait(bar(kBarWEmpty + st), ph ^ 1);
+            mbar_expect_tx(bar(kBarWFull + st), kTileBytesW);
+            bulk_g2s(smem_u32(sW + st * kTileBytesW), src + (size_t)t * kTileBytesW, kTileBytesW, bar(kBarWFull + st));
             if (++st == kStages) { st = 0; ph ^= 1; }
           }
         }
@@ -219,68 +305,170 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
     // ===================================================== MMA issuer ===================================================
     if (lane == 0) {
       int st = 0;
-      uint32_t ph = 0, ph_a = 0;
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int l = 0; l < P.n_layers; ++l) {
-          mbar_wait(bar_a, ph_a);
-          ph_a ^= 1;
+      uint32_t ph_w = 0;
+      uint32_t ph_ar = 0, ph_a0 = 0;  // one parity bit per K-block
+      uint32_t ph_af = 0;             // acc_free parity bits (bit b = accumulator b)
+      uint32_t lc = 0;                // running layer counter: layer lc accumulates into TMEM columns (lc & 1) * 256
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int l = 0; l < n_layers; ++l, ++lc) {
+          const uint32_t ab = lc & 1u;
+          const uint32_t d_tmem = tmem_base + ab * 256u;
+          mbar_wait(bar(kBarAccFree + ab), ((ph_af >> ab) & 1u) ^ 1u);  // every epilogue warp has drained this accumulator
+          ph_af ^= 1u << ab;
           tc_fence_after();
           const int ksteps = P.layers[l].ksteps;
           const int nkb = (ksteps + 3) >> 2;
+          // heads layer 2 (channel_net.0) reads the same operand (feat) as layer 1 (shape_net.0): nothing new to wait for
+          const bool fresh_a = !(kMode == MODE_HEADS && l == 2);
           for (int kb = 0; kb < nkb; ++kb) {
+            if (kMode != MODE_PAIR && l == 0) {
+              mbar_wait(bar(kBarA0Rdy + kb), (ph_a0 >> kb) & 1u);
+              ph_a0 ^= 1u << kb;
+            } else if (fresh_a) {
+              mbar_wait(bar(kBarARdy + kb), (ph_ar >> kb) & 1u);
+              ph_ar ^= 1u << kb;
+            }
+            tc_fence_after();
             const int ks_n = min(4, ksteps - kb * 4);
             const uint32_t a_hi = smem_u32(sA + kb * 2 * kTileBytesA), a_lo = a_hi + kTileBytesA;
             // stage "hi": A_hi*W_hi + A_lo*W_hi
-            mbar_wait(bar_full + 8 * st, ph);
+            mbar_wait(bar(kBarWFull + st), ph_w);
             tc_fence_after();
             uint32_t b = smem_u32(sW + st * kTileBytesW);
             for (int ks = 0; ks < ks_n; ++ks)
-              umma_f16(tmem_base, make_desc(a_hi + ks * 32), make_desc(b + ks * 32), kIdesc, (kb | ks) != 0);
-            for (int ks = 0; ks < ks_n; ++ks) umma_f16(tmem_base, make_desc(a_lo + ks * 32), make_desc(b + ks * 32), kIdesc, 1u);
-            umma_commit(bar_empty + 8 * st);
-            if (++st == kStages) { st = 0; ph ^= 1; }
+              umma_f16(d_tmem, make_desc(a_hi + ks * 32), make_desc(b + ks * 32), kIdesc, (kb | ks) != 0);
+            for (int ks = 0; ks < ks_n; ++ks) umma_f16(d_tmem, make_desc(a_lo + ks * 32), make_desc(b + ks * 32), kIdesc, 1u);
+            umma_commit(bar(kBarWEmpty + st));
+            if (++st == kStages) { st = 0; ph_w ^= 1; }
             // stage "lo": A_hi*W_lo
-            mbar_wait(bar_full + 8 * st, ph);
+            mbar_wait(bar(kBarWFull + st), ph_w);
             tc_fence_after();
             b = smem_u32(sW + st * kTileBytesW);
-            for (int ks = 0; ks < ks_n; ++ks) umma_f16(tmem_base, make_desc(a_hi + ks * 32), make_desc(b + ks * 32), kIdesc, 1u);
-            umma_commit(bar_empty + 8 * st);
-            if (++st == kStages) { st = 0; ph ^= 1; }
+            for (int ks = 0; ks < ks_n; ++ks) umma_f16(d_tmem, make_desc(a_hi + ks * 32), make_desc(b + ks * 32), kIdesc, 1u);
+            umma_commit(bar(kBarWEmpty + st));
+            if (++st == kStages) { st = 0; ph_w ^= 1; }
+            if (l == n_layers - 1) umma_commit(bar(kBarAFree + kb));  // this K-block may take the next tile's first operand
           }
-          umma_commit(bar_acc);
+          umma_commit(bar(kBarAccRdy + ab));
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ======================================== heads / probe: first-operand loader =======================================
+    if (kMode != MODE_PAIR && lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        for (int kb = 0; kb < 4; ++kb) {
+          if (it > 0) mbar_wait(bar(kBarAFree + kb), (it - 1) & 1u);
+          mbar_expect_tx(bar(kBarA0Rdy + kb), 2 * kTileBytesA);
+          bulk_g2s(smem_u32(sA + kb * 2 * kTileBytesA), P.img + (size_t)tile * kImgTileBytes + (size_t)kb * 2 * kTileBytesA,
+                   2 * kTileBytesA, bar(kBarA0Rdy + kb));
         }
       }
     }
   } else {
     // ============================================ prologue / epilogue threads ===========================================
-    const int et = threadIdx.x - 64;         // 0..255
-    const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;        // column half (0: cols 0..127, 1: cols 128..255)
-    const int row = q * 32 + lane;           // tile row == TMEM lane
+    const int et = threadIdx.x - 64;       // 0..255
+    const int q = warp & 3;                // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;      // 0 / 1: which 32-column chunk of every 64-column K-block this thread handles
+    const int row = q * 32 + lane;         // tile row == TMEM lane
+    const int x7 = row & 7;
+    const uint32_t rowbase = (uint32_t)((row >> 3) * 1024 + x7 * 128);
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t ph_acc = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      // ------------------------------------------------------ prologue ---------------------------------------------------
-      if (P.mode == 0) {
-        // pair MLP input, 112 columns: [feat 0..31 | x: d, sin*10, cos*10, 0,0,0 | y: ... | z: ... | 8 zeros]
-        // (the column order is OURS; the first-layer weights are permuted to match when they are packed)
-        const long long s = tile * 16 + (row >> 3);
-        const int idx = (s < S) ? __ldg(P.nbr_idx + s * kK + (row & 7)) : -1;
+    uint32_t ph_acc = 0;                   // acc_ready parity bits
+    uint32_t lc = 0;
+
+    float* wts_all = reinterpret_cast<float*>(misc + kOffWts);
+    uint8_t* row_samp_all = misc + kOffRowSamp;
+    uint8_t* samp_row_all = misc + kOffSampRow;
+    uint8_t* samp_cnt_all = misc + kOffSampCnt;
+    int* info_all = reinterpret_cast<int*>(misc + kOffInfo);
+
+    // publish one K-block of the A operand (all 8 epilogue warps arrive once per K-block)
+    auto publish = [&](int barrier_index) {
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(barrier_index));
+    };
+    auto wait_acc = [&](uint32_t ab) {
+      mbar_wait(bar(kBarAccRdy + ab), (ph_acc >> ab) & 1u);
+      ph_acc ^= 1u << ab;
+      tc_fence_after();
+    };
+    auto release_acc = [&](uint32_t ab) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(kBarAccFree + ab));
+    };
+
+    // ACT / LINEAR epilogue of layer l: four 32-column chunks (2 i + half), software-pipelined TMEM loads
+    auto epilogue_store = [&](int l, float slope, float* feat_row) {
+      const uint32_t ab = lc & 1u;
+      wait_acc(ab);
+      const float inv = P.layers[l].inv_scale;
+      const uint32_t t_acc = t_row + ab * 256u;
+      uint32_t v[2][32];
+      tmem_ld32_async(t_acc + half * 32, v[0]);
+      tmem_wait(v[0]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (i < 3) tmem_ld32_async(t_acc + (2 * (i + 1) + half) * 32, v[(i + 1) & 1]);
+        epi_chunk_store(P, l, inv, slope, v[i & 1], (2 * i + half) * 32, sA, rowbase, x7, feat_row);
+        if (i == 3) release_acc(ab);
+        publish(kBarARdy + i);
+        if (i < 3) tmem_wait(v[(i + 1) & 1]);
+      }
+      ++lc;
+    };
+
+    if (kMode == MODE_PAIR) {
+      // ------------------------------------------------------------------------------------------------- pair mode ----
+      // layer-0 input, 112 columns: [feat 0..31 | x: d, sin*10, cos*10, 0,0,0 | y: ... | z: ... | 8 zeros]
+      // (the column order is OURS; the first-layer weights are permuted to match when they are packed).
+      // half 0 owns columns 0..55 (K-block 0, chunks 0..6); half 1 owns 56..111 (K-block 0 chunk 7, K-block 1 chunks 0..5).
+      uint4 pre_hi[7], pre_lo[7];
+
+      auto prologue_compute = [&](int tile, int buf) {
+        const int s_begin = __ldg(P.tile_start + tile), s_end = __ldg(P.tile_start + tile + 1);
+        const int n_samp = s_end - s_begin;
+        const int base = __ldg(P.pair_off + s_begin);
+        uint8_t* row_samp = row_samp_all + buf * 128;
+        uint8_t* samp_row = samp_row_all + buf * 128;
+        uint8_t* samp_cnt = samp_cnt_all + buf * 128;
+        if (et < n_samp) {
+          const int o = __ldg(P.pair_off + s_begin + et) - base;
+          const int c = __ldg(P.pair_off + s_begin + et + 1) - base - o;
+          samp_row[et] = (uint8_t)o;
+          samp_cnt[et] = (uint8_t)c;
+          for (int j = 0; j < c; ++j) row_samp[o + j] = (uint8_t)et;
+        }
+        if (et == 0) {
+          info_all[buf * 4 + 0] = s_begin;
+          info_all[buf * 4 + 1] = n_samp;
+          info_all[buf * 4 + 2] = __ldg(P.pair_off + s_end) - base;
+        }
+        epi_bar_sync();
+        const int n_rows = info_all[buf * 4 + 2];
+        int idx = -1;
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         float px = 0.f, py = 0.f, pz = 0.f;
-        if (idx >= 0) {
+        if (row < n_rows) {
+          const int sl = row_samp[row];
+          const long long s = (long long)s_begin + sl;
+          idx = __ldg(P.nbr_idx + s * kK + (row - samp_row[sl]));
           x = __ldg(P.sample_pos + s);
           px = __ldg(P.kp_pos + (size_t)idx * 3); py = __ldg(P.kp_pos + (size_t)idx * 3 + 1); pz = __ldg(P.kp_pos + (size_t)idx * 3 + 2);
         }
         const float d3[3] = {x.x - px, x.y - py, x.z - pz};
-        auto enc_group = [&](int c) {  // 24 columns starting at 32 + 24 c
+        auto enc_group = [&](int c, int first_chunk) {  // 24 columns -> pre chunks first_chunk .. first_chunk + 2
           float v[24];
           v[0] = d3[c];
           float fr = 3.14159274101257324f;
 #pragma unroll
           for (int i = 0; i < kFreqs; ++i) {
             float sn, cs;
-            sincosf(d3[c] * fr, &sn, &cs);
+            sincos_small(d3[c] * fr, sn, cs);
             v[1 + i] = sn;
             v[1 + kFreqs + i] = cs;
             fr *= 2.0f;
@@ -293,7 +481,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
 #pragma unroll
           for (int ch = 0; ch < 3; ++ch) {
             const float y[8] = {v[ch * 8], v[ch * 8 + 1], v[ch * 8 + 2], v[ch * 8 + 3], v[ch * 8 + 4], v[ch * 8 + 5], v[ch * 8 + 6], v[ch * 8 + 7]};
-            store_split8(sA, row, 32 + 24 * c + 8 * ch, y);
+            split8(y, pre_hi[first_chunk + ch], pre_lo[first_chunk + ch]);
           }
         };
         if (half == 0) {
@@ -305,177 +493,230 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
               const float4 f1 = __ldg(reinterpret_cast<const float4*>(P.kp_feat + (size_t)idx * 32 + ch * 8 + 4));
               y[0] = f0.x; y[1] = f0.y; y[2] = f0.z; y[3] = f0.w; y[4] = f1.x; y[5] = f1.y; y[6] = f1.z; y[7] = f1.w;
             }
-            store_split8(sA, row, ch * 8, y);
+            split8(y, pre_hi[ch], pre_lo[ch]);
           }
-          enc_group(0);
+          enc_group(0, 4);
           const float nrm = sqrtf(d3[0] * d3[0] + d3[1] * d3[1] + d3[2] * d3[2]);
-          wts[row] = idx >= 0 ? 1.0f / (nrm + 1e-5f) : 0.f;
+          wts_all[buf * 128 + row] = idx >= 0 ? 1.0f / (nrm + 1e-5f) : 0.f;
         } else {
-          enc_group(1);
-          enc_group(2);
-          const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          store_split8(sA, row, 104, z);
+          enc_group(1, 0);
+          enc_group(2, 3);
+          pre_hi[6] = pre_lo[6] = make_uint4(0u, 0u, 0u, 0u);
         }
-      } else {
-        // heads / probe input: 128 consecutive rows of the fp32 [S,256] buffer, coalesced loads
-        const long long s0 = tile * 128;
-#pragma unroll 4
-        for (int i = 0; i < 32; ++i) {
-          const int f = i * kEpiThreads + et;
-          const int r = f >> 6, c = (f & 63) * 4;
-          const long long s = s0 + r;
-          const float4 v = (s < S) ? __ldg(reinterpret_cast<const float4*>(P.agg + s * kHidden + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-          const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-          const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
-          uint8_t* p = sA + (c >> 6) * (2 * kTileBytesA) + swz(r, (c & 63) >> 3) + (c & 7) * 2;
-          *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-          *reinterpret_cast<uint2*>(p + kTileBytesA) =
-              make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+      };
+      // store the K-block-kb part of the staged layer-0 input and publish that K-block
+      auto prologue_store = [&](int kb) {
+        if (kb == 0) {
+          if (half == 0) {
+#pragma unroll
+            for (int c = 0; c < 7; ++c) {
+              uint8_t* p = sA + rowbase + ((c ^ x7) << 4);
+              *reinterpret_cast<uint4*>(p) = pre_hi[c];
+              *reinterpret_cast<uint4*>(p + kTileBytesA) = pre_lo[c];
+            }
+          } else {
+            uint8_t* p = sA + rowbase + ((7 ^ x7) << 4);
+            *reinterpret_cast<uint4*>(p) = pre_hi[0];
+            *reinterpret_cast<uint4*>(p + kTileBytesA) = pre_lo[0];
+          }
+        } else if (half == 1) {
+#pragma unroll
+          for (int c = 0; c < 6; ++c) {
+            uint8_t* p = sA + 2 * kTileBytesA + rowbase + ((c ^ x7) << 4);
+            *reinterpret_cast<uint4*>(p) = pre_hi[c + 1];
+            *reinterpret_cast<uint4*>(p + kTileBytesA) = pre_lo[c + 1];
+          }
         }
-      }
-      fence_proxy_async();
-      mbar_arrive(bar_a);
+        publish(kBarARdy + kb);
+      };
 
-      float sigma = 0.f;
-      // ------------------------------------------------------ layers -----------------------------------------------------
-      for (int l = 0; l < P.n_layers; ++l) {
-        const Layer& L = P.layers[l];
-        mbar_wait(bar_acc, ph_acc);
-        ph_acc ^= 1;
-        tc_fence_after();
-        const float inv = L.inv_scale;
-        if (L.epi == EPI_ACT || L.epi == EPI_LINEAR) {
+      // Iteration -1 primes the pipeline (stages the first tile's input); iteration `it` runs the four layer epilogues of tile
+      // `cur` and, between them, stages the input of the tile after it.  One call site per helper keeps the code I-cache sized.
+      int cur = -1;
+      for (int it = -1;; ++it) {
+        const bool prime = it < 0;
+        const int target = prime ? (int)blockIdx.x : cur + (int)gridDim.x;  // tile whose layer-0 input is staged now
+        const bool has_target = target < n_tiles;
+        if (prime && !has_target) break;
+        const int buf = it & 1;
 #pragma unroll 1
-          for (int ch = 0; ch < 4; ++ch) {
-            const int c0 = half * 128 + ch * 32;
-            uint32_t v[32];
-            tmem_ld32(t_row + c0, v);
+        for (int l = 0; l < 3; ++l) {
+          if (!prime) epilogue_store(l, 0.01f, nullptr);
+          if (l == 0 && has_target) prologue_compute(target, buf ^ 1);
+        }
+        if (has_target) {  // layer 3's MMAs release K-blocks 0 and 1 as they pass them
+#pragma unroll 1
+          for (int kb = 0; kb < 2; ++kb) {
+            if (!prime) mbar_wait(bar(kBarAFree + kb), (uint32_t)it & 1u);
+            prologue_store(kb);
+          }
+        }
+        if (prime) { cur = target; continue; }
+        // ---- layer 3: bias + LeakyReLU, normalised inverse-distance weight, segmented sum over each sample's rows
+        //      (fields/aggregators/mlp.py:86-88,119-121), staged as fp32 in K-blocks 2..3 (free once layer 3's MMAs are done),
+        //      two passes of 128 columns; the sums leave as the pre-split operand image the heads kernel bulk-copies.
+        {
+          const uint32_t ab = lc & 1u;
+          wait_acc(ab);
+          epi_bar_sync();  // wts[] / row maps of this tile were written by other warps
+          const float inv = P.layers[3].inv_scale;
+          const uint32_t t_acc = t_row + ab * 256u;
+          const float* wts = wts_all + buf * 128;
+          const uint8_t* row_samp = row_samp_all + buf * 128;
+          const uint8_t* samp_row = samp_row_all + buf * 128;
+          const uint8_t* samp_cnt = samp_cnt_all + buf * 128;
+          const int s_begin = info_all[buf * 4 + 0], n_samp = info_all[buf * 4 + 1], n_rows = info_all[buf * 4 + 2];
+          float wn = 0.f;
+          if (row < n_rows) {
+            const int sl = row_samp[row];
+            const int r0 = samp_row[sl], cnt = samp_cnt[sl];
+            float wsum = 0.f;
+            for (int j = 0; j < cnt; ++j) wsum += wts[r0 + j];
+            wn = wts[row] / wsum;
+          }
+          float* stage = reinterpret_cast<float*>(sA + 4 * kTileBytesA);  // [128 rows][128 cols] fp32, 16-byte chunks XOR (row & 31)
+          const int x31 = row & 31;
+#pragma unroll 1
+          for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll 1
+            for (int k = 0; k < 2; ++k) {
+              const int cl = 64 * half + 32 * k;  // column within the pass
+              const int c0 = 128 * pass + cl;
+              uint32_t v[32];
+              tmem_ld32_async(t_acc + c0, v);
+              tmem_wait(v);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(L.bias + c0 + g * 8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(L.bias + c0 + g * 8 + 4));
-              float y[8] = {fmaf(__uint_as_float(v[g * 8 + 0]), inv, b0.x), fmaf(__uint_as_float(v[g * 8 + 1]), inv, b0.y),
-                            fmaf(__uint_as_float(v[g * 8 + 2]), inv, b0.z), fmaf(__uint_as_float(v[g * 8 + 3]), inv, b0.w),
-                            fmaf(__uint_as_float(v[g * 8 + 4]), inv, b1.x), fmaf(__uint_as_float(v[g * 8 + 5]), inv, b1.y),
-                            fmaf(__uint_as_float(v[g * 8 + 6]), inv, b1.z), fmaf(__uint_as_float(v[g * 8 + 7]), inv, b1.w)};
-              if (L.epi == EPI_ACT) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) y[j] = lrelu(y[j]);
+              for (int g = 0; g < 8; ++g) {
+                const float4 b = *reinterpret_cast<const float4*>(&P.bias[3][c0 + g * 4]);
+                const float4 o = make_float4(wn * lrelu(fmaf(__uint_as_float(v[g * 4 + 0]), inv, b.x)),
+                                             wn * lrelu(fmaf(__uint_as_float(v[g * 4 + 1]), inv, b.y)),
+                                             wn * lrelu(fmaf(__uint_as_float(v[g * 4 + 2]), inv, b.z)),
+                                             wn * lrelu(fmaf(__uint_as_float(v[g * 4 + 3]), inv, b.w)));
+                const int c4 = (cl >> 2) + g;
+                *reinterpret_cast<float4*>(stage + row * 128 + ((c4 ^ x31) << 2)) = o;
               }
-              if (P.feat_out && L.epi == EPI_LINEAR && P.mode == 1) {
-                const long long s = tile * 128 + row;
-                if (s < S) {
-                  *reinterpret_cast<float4*>(P.feat_out + s * kHidden + c0 + g * 8) = make_float4(y[0], y[1], y[2], y[3]);
-                  *reinterpret_cast<float4*>(P.feat_out + s * kHidden + c0 + g * 8 + 4) = make_float4(y[4], y[5], y[6], y[7]);
-                }
+            }
+            if (pass == 1) release_acc(ab);
+            epi_bar_sync();
+            for (int task = et; task < n_samp * 16; task += kEpiThreads) {
+              const int sl = task >> 4, c8 = task & 15;
+              const int r0 = samp_row[sl], cnt = samp_cnt[sl];
+              float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              for (int j = 0; j < cnt; ++j) {
+                const int r = r0 + j;
+                const float4 t0 = *reinterpret_cast<const float4*>(stage + r * 128 + (((2 * c8) ^ (r & 31)) << 2));
+                const float4 t1 = *reinterpret_cast<const float4*>(stage + r * 128 + (((2 * c8 + 1) ^ (r & 31)) << 2));
+                acc[0] += t0.x; acc[1] += t0.y; acc[2] += t0.z; acc[3] += t0.w;
+                acc[4] += t1.x; acc[5] += t1.y; acc[6] += t1.z; acc[7] += t1.w;
               }
-              store_split8(sA, row, c0 + g * 8, y);
+              const long long s = (long long)s_begin + sl;
+              const int col = 128 * pass + 8 * c8;
+              uint4 hi, lo;
+              split8(acc, hi, lo);
+              uint8_t* p = P.img + (size_t)(s >> 7) * kImgTileBytes + (size_t)(col >> 6) * (2 * kTileBytesA) +
+                           swz((int)(s & 127), (col & 63) >> 3);
+              *reinterpret_cast<uint4*>(p) = hi;
+              *reinterpret_cast<uint4*>(p + kTileBytesA) = lo;
+            }
+            epi_bar_sync();  // the staging area is rewritten by the next pass / the next tile's layer-0 epilogue
+          }
+          ++lc;
+        }
+        if (!has_target) break;
+        cur = target;
+      }
+    } else {
+      // ------------------------------------------------------------------------------------------- heads / probe mode ----
+      float* part = reinterpret_cast<float*>(misc + kOffPart);  // [128][4]
+      // EPI_DOT1 (shape_net.2 -> softplus(x-1)) / EPI_DOT3 (channel_net.8 -> sigmoid): dot products of the activated row with the
+      // 1 or 3 output weight vectors; the two threads of a row combine through shared memory.
+      auto epilogue_dot = [&](int l, int nout, float (&res)[3]) {
+        const uint32_t ab = lc & 1u;
+        wait_acc(ab);
+        const float inv = P.layers[l].inv_scale;
+        const uint32_t t_acc = t_row + ab * 256u;
+        float acc3[3] = {0.f, 0.f, 0.f};
+        uint32_t v[2][32];
+        tmem_ld32_async(t_acc + half * 32, v[0]);
+        tmem_wait(v[0]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i < 3) tmem_ld32_async(t_acc + (2 * (i + 1) + half) * 32, v[(i + 1) & 1]);
+          const int c0 = (2 * i + half) * 32;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 b = *reinterpret_cast<const float4*>(&P.bias[l][c0 + g * 4]);
+            const uint32_t* vv = v[i & 1];
+            const float h0 = lrelu(fmaf(__uint_as_float(vv[g * 4 + 0]), inv, b.x)), h1 = lrelu(fmaf(__uint_as_float(vv[g * 4 + 1]), inv, b.y)),
+                        h2 = lrelu(fmaf(__uint_as_float(vv[g * 4 + 2]), inv, b.z)), h3 = lrelu(fmaf(__uint_as_float(vv[g * 4 + 3]), inv, b.w));
+            if (nout == 1) {
+              const float4 w = *reinterpret_cast<const float4*>(&P.shape_out_w[c0 + g * 4]);
+              acc3[0] = fmaf(h0, w.x, fmaf(h1, w.y, fmaf(h2, w.z, fmaf(h3, w.w, acc3[0]))));
+            } else {
+#pragma unroll
+              for (int o = 0; o < 3; ++o) {
+                const float4 w = *reinterpret_cast<const float4*>(&P.chan_out_w[o][c0 + g * 4]);
+                acc3[o] = fmaf(h0, w.x, fmaf(h1, w.y, fmaf(h2, w.z, fmaf(h3, w.w, acc3[o]))));
+              }
             }
           }
-          tc_fence_before();
-          fence_proxy_async();
-          mbar_arrive(bar_a);
-        } else if (L.epi == EPI_DUMP) {
-#pragma unroll 1
-          for (int ch = 0; ch < 4; ++ch) {
-            const int c0 = half * 128 + ch * 32;
-            uint32_t v[32];
-            tmem_ld32(t_row + c0, v);
-            const long long s = tile * 128 + row;
-            if (s < S) {
+          if (i < 3) tmem_wait(v[(i + 1) & 1]);
+        }
+        release_acc(ab);
+        if (half == 1) { part[row * 4] = acc3[0]; part[row * 4 + 1] = acc3[1]; part[row * 4 + 2] = acc3[2]; }
+        epi_bar_sync();
+        if (half == 0) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) P.feat_out[s * kHidden + c0 + j] = fmaf(__uint_as_float(v[j]), inv, __ldg(L.bias + c0 + j));
-            }
-          }
-          tc_fence_before();
-        } else if (L.epi == EPI_AGG) {
-          // bias + LeakyReLU, scale by the normalised inverse-distance weight of this pair, stage as fp32 in the (now free) A
-          // region with a 16-byte XOR swizzle, then sum the 8 slot rows of every sample (fields/aggregators/mlp.py:86-88,119-121)
-          epi_bar_sync();  // wts[] was written by other warps in the prologue
-          float wsum = 0.f;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) wsum += wts[(row & ~7) + j];
-          const float wn = wts[row] / wsum;  // rows of padded samples have wts = 0 and wsum = 0 -> NaN * never read
-          float* stage = reinterpret_cast<float*>(sA);
-#pragma unroll 1
-          for (int ch = 0; ch < 4; ++ch) {
-            const int c0 = half * 128 + ch * 32;
-            uint32_t v[32];
-            tmem_ld32(t_row + c0, v);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(L.bias + c0 + g * 4));
-              const float w = (wts[row] > 0.f) ? wn : 0.f;
-              const float4 o = make_float4(w * lrelu(fmaf(__uint_as_float(v[g * 4 + 0]), inv, b.x)),
-                                           w * lrelu(fmaf(__uint_as_float(v[g * 4 + 1]), inv, b.y)),
-                                           w * lrelu(fmaf(__uint_as_float(v[g * 4 + 2]), inv, b.z)),
-                                           w * lrelu(fmaf(__uint_as_float(v[g * 4 + 3]), inv, b.w)));
-              const int c4 = (c0 >> 2) + g;  // float4 chunk index within the 64-chunk row
-              *reinterpret_cast<float4*>(stage + row * 256 + ((c4 ^ (row & 7)) << 2)) = o;
-            }
-          }
-          tc_fence_before();
-          epi_bar_sync();
+          for (int o = 0; o < 3; ++o) res[o] = acc3[o] + part[row * 4 + o];
+        }
+        epi_bar_sync();  // part[] is reused by the next dot epilogue
+        ++lc;
+      };
+
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long s = (long long)tile * 128 + row;
+        if (kMode == MODE_PROBE) {
+          // one linear layer, fp32 dump (self-test of descriptors / swizzle / TMEM read-back)
+          const uint32_t ab = lc & 1u;
+          wait_acc(ab);
+          const float inv = P.layers[0].inv_scale;
 #pragma unroll 1
           for (int i = 0; i < 4; ++i) {
-            const int f = i * kEpiThreads + et;  // 0..1023: sample-in-tile * 64 + chunk
-            const int sl = f >> 6, c4 = f & 63;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 t = *reinterpret_cast<const float4*>(stage + (sl * 8 + j) * 256 + ((c4 ^ j) << 2));
-              acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-            }
-            const long long s = tile * 16 + sl;
-            if (s < S) *reinterpret_cast<float4*>(P.agg + s * kHidden + c4 * 4) = acc;
-          }
-          epi_bar_sync();  // staging (== A region) is overwritten by the next tile's prologue
-        } else {
-          // EPI_DOT1 (shape_net.2 -> softplus(x-1)) / EPI_DOT3 (channel_net.8 -> sigmoid): dot of the activated row with 1 or 3
-          // output weight vectors; the two column-half threads of a row combine through shared memory.
-          const int nout = (L.epi == EPI_DOT1) ? 1 : 3;
-          const float* wo = (L.epi == EPI_DOT1) ? P.shape_out_w : P.chan_out_w;
-          float part[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
-          for (int ch = 0; ch < 4; ++ch) {
-            const int c0 = half * 128 + ch * 32;
+            const int c0 = (2 * i + half) * 32;
             uint32_t v[32];
-            tmem_ld32(t_row + c0, v);
+            tmem_ld32_async(t_row + ab * 256u + c0, v);
+            tmem_wait(v);
+            if (s < S) {
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(L.bias + c0 + g * 4));
-              const float h0 = lrelu(fmaf(__uint_as_float(v[g * 4 + 0]), inv, b.x)), h1 = lrelu(fmaf(__uint_as_float(v[g * 4 + 1]), inv, b.y)),
-                          h2 = lrelu(fmaf(__uint_as_float(v[g * 4 + 2]), inv, b.z)), h3 = lrelu(fmaf(__uint_as_float(v[g * 4 + 3]), inv, b.w));
-              for (int o = 0; o < nout; ++o) {
-                const float4 w = __ldg(reinterpret_cast<const float4*>(wo + o * kHidden + c0 + g * 4));
-                part[o] = fmaf(h0, w.x, fmaf(h1, w.y, fmaf(h2, w.z, fmaf(h3, w.w, part[o]))));
-              }
+              for (int j = 0; j < 32; ++j) P.feat_out[s * kHidden + c0 + j] = fmaf(__uint_as_float(v[j]), inv, P.bias[0][c0 + j]);
             }
           }
-          tc_fence_before();
-          if (half == 1) {
-            if (L.epi == EPI_DOT1) wts[row] = part[0];
-            else { part3[row * 3] = part[0]; part3[row * 3 + 1] = part[1]; part3[row * 3 + 2] = part[2]; }
-          }
-          epi_bar_sync();
-          if (half == 0) {
-            if (L.epi == EPI_DOT1) {
-              const float xs = part[0] + wts[row] + __ldg(P.shape_out_b) - 1.0f;
+          release_acc(ab);
+          ++lc;
+          continue;
+        }
+        float* feat_row = (P.feat_out && s < S) ? P.feat_out + s * kHidden : nullptr;
+        float sigma = 0.f;
+        float res[3];
+#pragma unroll 1
+        for (int l = 0; l < 6; ++l) {
+          if (l == 1 || l == 5) {
+            // l = 1: shape_net.0 + LeakyReLU, shape_net.2;  l = 5: channel_net.6 + LeakyReLU, channel_net.8
+            epilogue_dot(l, l == 1 ? 1 : 3, res);
+            if (l == 1 && half == 0) {
+              const float xs = res[0] + P.shape_out_b - 1.0f;
               sigma = xs > 20.f ? xs : log1pf(expf(xs));
-            } else {
-              float rgb[3];
-#pragma unroll
-              for (int o = 0; o < 3; ++o) rgb[o] = 1.0f / (1.0f + expf(-(part[o] + part3[row * 3 + o] + __ldg(P.chan_out_b + o))));
-              const long long s = tile * 128 + row;
-              if (s < S) P.rgbs[s] = make_float4(rgb[0], rgb[1], rgb[2], sigma);
             }
+          } else {
+            // l = 0: local_field.8 (linear) -> feat;  l = 2..4: channel_net.0,2,4 (layer 2 reads feat and overwrites it in place)
+            epilogue_store(l, l == 0 ? 1.0f : 0.01f, l == 0 ? feat_row : nullptr);
           }
-          epi_bar_sync();  // wts / part3 are reused
-          if (L.epi == EPI_DOT1) {  // accumulator consumed, A (= feat) untouched: let the MMA warp start channel_net
-            fence_proxy_async();
-            mbar_arrive(bar_a);
-          }
+        }
+        if (half == 0 && s < S) {
+          float rgb[3];
+#pragma unroll
+          for (int o = 0; o < 3; ++o) rgb[o] = 1.0f / (1.0f + expf(-(res[o] + P.chan_out_b[o])));
+          P.rgbs[s] = make_float4(rgb[0], rgb[1], rgb[2], sigma);
         }
       }
     }
@@ -506,6 +747,73 @@ __global__ void k_pack_weights(const float* __restrict__ w, int k_in, const int*
   *reinterpret_cast<__half*>(tile + kTileBytesW + off) = lo;
 }
 
+// fp32 rows [n,256] <-> the pre-split operand image (per 128-row tile: 4 K-blocks x (hi 16 KB, lo 16 KB), SWIZZLE_128B)
+__global__ void k_rows_to_image(const float* __restrict__ x, long long n, uint8_t* __restrict__ img) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (row, 8-column chunk)
+  if (i >= n * 32) return;
+  const long long s = i >> 5;
+  const int c8 = (int)(i & 31);
+  const float4 a = __ldg(reinterpret_cast<const float4*>(x + s * kHidden + c8 * 8));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(x + s * kHidden + c8 * 8 + 4));
+  const float y[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint4 hi, lo;
+  split8(y, hi, lo);
+  uint8_t* p = img + (size_t)(s >> 7) * kImgTileBytes + (size_t)(c8 >> 3) * (2 * kTileBytesA) + swz((int)(s & 127), c8 & 7);
+  *reinterpret_cast<uint4*>(p) = hi;
+  *reinterpret_cast<uint4*>(p + kTileBytesA) = lo;
+}
+
+__global__ void k_image_to_rows(const uint8_t* __restrict__ img, long long n, float* __restrict__ x) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 32) return;
+  const long long s = i >> 5;
+  const int c8 = (int)(i & 31);
+  const uint8_t* p = img + (size_t)(s >> 7) * kImgTileBytes + (size_t)(c8 >> 3) * (2 * kTileBytesA) + swz((int)(s & 127), c8 & 7);
+  const uint4 hi = *reinterpret_cast<const uint4*>(p), lo = *reinterpret_cast<const uint4*>(p + kTileBytesA);
+  const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
+  float y[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
+    const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&l[j]));
+    y[2 * j] = fh.x + fl.x;
+    y[2 * j + 1] = fh.y + fl.y;
+  }
+  *reinterpret_cast<float4*>(x + s * kHidden + c8 * 8) = make_float4(y[0], y[1], y[2], y[3]);
+  *reinterpret_cast<float4*>(x + s * kHidden + c8 * 8 + 4) = make_float4(y[4], y[5], y[6], y[7]);
+}
+
+// ---- dense pair packing -------------------------------------------------------------------------------------------------
+struct NbrCount {
+  const int* nbr_idx;
+  const long long* n_samples_dev;
+  __device__ int operator()(long long s) const {
+    if (s >= *n_samples_dev) return 0;
+    const int4 a = __ldg(reinterpret_cast<const int4*>(nbr_idx + s * kK));
+    const int4 b = __ldg(reinterpret_cast<const int4*>(nbr_idx + s * kK + 4));
+    return (a.x >= 0) + (a.y >= 0) + (a.z >= 0) + (a.w >= 0) + (b.x >= 0) + (b.y >= 0) + (b.z >= 0) + (b.w >= 0);
+  }
+};
+
+__global__ void k_zero_int(int* p) { p[0] = 0; }
+
+// tile t = samples whose first pair offset lies in [121 t, 121 t + 121): every sample has 1..8 pairs, so consecutive samples
+// cross at most one tile boundary and every tile is non-empty.
+__global__ void k_tile_starts(const int* __restrict__ pair_off, const long long* __restrict__ n_samples_dev, long long capacity,
+                              int* __restrict__ tile_start, int* __restrict__ n_tiles_dev) {
+  const long long S = min(*n_samples_dev, capacity);
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s == 0 && S == 0) { *n_tiles_dev = 0; tile_start[0] = 0; }
+  if (s >= S) return;
+  const int t = pair_off[s] / kPackRows;
+  const int tp = s > 0 ? pair_off[s - 1] / kPackRows : -1;
+  for (int u = tp + 1; u <= t; ++u) tile_start[u] = (int)s;
+  if (s == S - 1) {
+    tile_start[t + 1] = (int)S;
+    *n_tiles_dev = t + 1;
+  }
+}
+
 }  // namespace tc
 }  // namespace npcd
 
@@ -519,74 +827,156 @@ extern "C" int npcd_tc_pack_weights(const float* w, int k_in, const int* perm, i
   return check_launch("npcd_tc_pack_weights");
 }
 
-static int launch_tc(const tc::Params& P, long long tiles, int num_sms, cudaStream_t st, const char* what) {
-  cudaError_t e = cudaFuncSetAttribute(tc::k_field_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal);
+extern "C" int npcd_tc_rows_to_image(const float* rows, long long n, void* image, void* stream) {
+  NPCD_CHECK_ARG(n >= 0 && (n == 0 || (rows && image)), "bad arguments");
+  if (n == 0) return 0;
+  tc::k_rows_to_image<<<(unsigned)((n * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rows, n, (uint8_t*)image);
+  return check_launch("npcd_tc_rows_to_image");
+}
+
+extern "C" int npcd_tc_image_to_rows(const void* image, long long n, float* rows, void* stream) {
+  NPCD_CHECK_ARG(n >= 0 && (n == 0 || (rows && image)), "bad arguments");
+  if (n == 0) return 0;
+  tc::k_image_to_rows<<<(unsigned)((n * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)image, n, rows);
+  return check_launch("npcd_tc_image_to_rows");
+}
+
+// workspace layout: [operand image | pair_off (capacity+1) | tile_start (max_tiles+2) | n_tiles (1, padded) | cub scratch]
+namespace {
+struct TcWorkspace {
+  size_t img_off, img_bytes, pair_off, tile_off, ntiles_off, cub_off, cub_bytes, total;
+  long long max_tiles;
+};
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int tc_workspace_layout(long long capacity, TcWorkspace* w) {
+  w->img_off = 0;
+  w->img_bytes = (size_t)((capacity + 127) / 128) * tc::kImgTileBytes;
+  w->pair_off = align256(w->img_off + w->img_bytes);
+  w->max_tiles = capacity * kK / tc::kPackRows + 2;
+  w->tile_off = align256(w->pair_off + (size_t)(capacity + 1) * sizeof(int));
+  w->ntiles_off = align256(w->tile_off + (size_t)(w->max_tiles + 2) * sizeof(int));
+  w->cub_off = w->ntiles_off + 256;
+  size_t tmp = 0;
+  tc::NbrCount op{nullptr, nullptr};
+  cub::CountingInputIterator<long long> cnt(0);
+  cub::TransformInputIterator<int, tc::NbrCount, cub::CountingInputIterator<long long>> it(cnt, op);
+  cudaError_t e = cub::DeviceScan::InclusiveSum(nullptr, tmp, it, (int*)nullptr, capacity > 0 ? capacity : 1);
+  if (e != cudaSuccess) {
+    set_error("npcd_field_tc_workspace_bytes: %s", cudaGetErrorString(e));
+    return 2;
+  }
+  w->cub_bytes = tmp + 256;
+  w->total = w->cub_off + w->cub_bytes;
+  return 0;
+}
+
+void fill_layer(tc::Params& P, int i, const npcd_tc_layer& src, int epi) {
+  P.layers[i].w = (const uint8_t*)src.packed_w;
+  P.layers[i].inv_scale = src.inv_scale;
+  P.layers[i].ksteps = src.k_pad / 16;
+  P.layers[i].epi = epi;
+  memcpy(P.bias[i], src.bias, sizeof(float) * 256);
+}
+
+template <int kMode>
+int launch_tc(const tc::Params& P, long long tiles, int num_sms, cudaStream_t st, const char* what) {
+  cudaError_t e = cudaFuncSetAttribute(tc::k_field_tc<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal);
   if (e != cudaSuccess) {
     set_error("%s: cannot opt in to %d bytes of shared memory: %s", what, tc::kSmemTotal, cudaGetErrorString(e));
     return 2;
   }
   if (num_sms <= 0) num_sms = 148;
-  const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
-  tc::k_field_tc<<<grid, tc::kThreadsTc, tc::kSmemTotal, st>>>(P);
+  const unsigned grid = (unsigned)(tiles < num_sms ? (tiles > 0 ? tiles : 1) : num_sms);
+  tc::k_field_tc<kMode><<<grid, tc::kThreadsTc, tc::kSmemTotal, st>>>(P);
   return check_launch(what);
 }
+}  // namespace
 
-static void fill_layer(tc::Layer& L, const npcd_tc_layer& src, int epi) {
-  L.w = (const uint8_t*)src.packed_w;
-  L.bias = src.bias;
-  L.inv_scale = src.inv_scale;
-  L.ksteps = src.k_pad / 16;
-  L.epi = epi;
+extern "C" int npcd_field_tc_workspace_bytes(long long capacity, size_t* bytes) {
+  NPCD_CHECK_ARG(bytes && capacity >= 0 && capacity < (1ll << 27), "bad arguments (capacity must be < 2^27 samples per launch)");
+  TcWorkspace w;
+  int rc = tc_workspace_layout(capacity, &w);
+  if (rc) return rc;
+  *bytes = w.total;
+  return 0;
 }
 
 extern "C" int npcd_field_tc_fwd(const int* nbr_idx, const float* sample_pos, const float* kp_pos, const float* kp_feat,
                                  const long long* n_samples_dev, long long capacity, const npcd_mlp_tc_weights* W,
-                                 float* agg_workspace, float* rgbs, float* feat_out, int stages, int* error_flag, int num_sms,
-                                 void* stream) {
+                                 void* workspace, size_t workspace_bytes, float* rgbs, float* feat_out, int stages,
+                                 int* error_flag, int num_sms, void* stream) {
   NPCD_CHECK_ARG(n_samples_dev && W, "null pointer");
-  NPCD_CHECK_ARG(capacity >= 0, "bad capacity");
+  NPCD_CHECK_ARG(capacity >= 0 && capacity < (1ll << 27), "bad capacity (must be < 2^27 samples per launch)");
   if (capacity == 0) return 0;
-  NPCD_CHECK_ARG(nbr_idx && sample_pos && kp_pos && kp_feat && agg_workspace && rgbs, "null pointer");
+  NPCD_CHECK_ARG(nbr_idx && sample_pos && kp_pos && kp_feat && workspace && rgbs, "null pointer");
   NPCD_CHECK_ARG(W->feat_dim == 32, "the tensor-core field kernel is specialised for feat_dim = 32 (configs/npcd_srncars.yaml:6)");
+  TcWorkspace ws;
+  int rc = tc_workspace_layout(capacity, &ws);
+  if (rc) return rc;
+  NPCD_CHECK_ARG(workspace_bytes >= ws.total, "workspace too small (npcd_field_tc_workspace_bytes)");
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = 0;
+  uint8_t* base = (uint8_t*)workspace;
+  uint8_t* img = base + ws.img_off;
+  int* pair_off = (int*)(base + ws.pair_off);
+  int* tile_start = (int*)(base + ws.tile_off);
+  int* n_tiles_dev = (int*)(base + ws.ntiles_off);
   if (stages & 1) {
-    tc::Params P{};
-    for (int i = 0; i < 4; ++i) fill_layer(P.layers[i], W->pair[i], i < 3 ? tc::EPI_ACT : tc::EPI_AGG);
+    // dense packing: pair_off = exclusive scan of the neighbour counts, then the first sample of every 121-offset tile
+    tc::k_zero_int<<<1, 1, 0, st>>>(pair_off);
+    tc::NbrCount op{nbr_idx, n_samples_dev};
+    cub::CountingInputIterator<long long> cnt(0);
+    cub::TransformInputIterator<int, tc::NbrCount, cub::CountingInputIterator<long long>> it(cnt, op);
+    size_t tmp = ws.cub_bytes;
+    cudaError_t e = cub::DeviceScan::InclusiveSum(base + ws.cub_off, tmp, it, pair_off + 1, capacity, st);
+    if (e != cudaSuccess) {
+      set_error("npcd_field_tc_fwd: scan: %s", cudaGetErrorString(e));
+      return 2;
+    }
+    tc::k_tile_starts<<<(unsigned)((capacity + 255) / 256), 256, 0, st>>>(pair_off, n_samples_dev, capacity, tile_start, n_tiles_dev);
+    rc = check_launch("npcd_field_tc_fwd(pack)");
+    if (rc) return rc;
+    static thread_local tc::Params P;  // ~11 KB: keep it off the stack
+    memset(&P, 0, sizeof(P));
+    for (int i = 0; i < 4; ++i) fill_layer(P, i, W->pair[i], i < 3 ? tc::EPI_ACT : tc::EPI_AGG);
     P.n_layers = 4;
-    P.mode = 0;
-    P.nbr_idx = nbr_idx; P.sample_pos = (const float4*)sample_pos; P.kp_pos = kp_pos; P.kp_feat = kp_feat; P.agg = agg_workspace;
+    P.nbr_idx = nbr_idx; P.sample_pos = (const float4*)sample_pos; P.kp_pos = kp_pos; P.kp_feat = kp_feat;
+    P.pair_off = pair_off; P.tile_start = tile_start; P.n_tiles_dev = n_tiles_dev; P.img = img;
     P.n_samples_dev = n_samples_dev; P.capacity = capacity; P.error_flag = error_flag;
-    rc = launch_tc(P, (capacity + 15) / 16, num_sms, st, "npcd_field_tc_fwd(pair)");
+    rc = launch_tc<tc::MODE_PAIR>(P, ws.max_tiles, num_sms, st, "npcd_field_tc_fwd(pair)");
     if (rc) return rc;
   }
   if (stages & 2) {
-    tc::Params P{};
-    fill_layer(P.layers[0], W->agg, tc::EPI_LINEAR);
-    fill_layer(P.layers[1], W->shape, tc::EPI_DOT1);
-    for (int i = 0; i < 3; ++i) fill_layer(P.layers[2 + i], W->chan[i], tc::EPI_ACT);
-    fill_layer(P.layers[5], W->chan[3], tc::EPI_DOT3);
+    static thread_local tc::Params P;
+    memset(&P, 0, sizeof(P));
+    fill_layer(P, 0, W->agg, tc::EPI_LINEAR);
+    fill_layer(P, 1, W->shape, tc::EPI_DOT1);
+    for (int i = 0; i < 3; ++i) fill_layer(P, 2 + i, W->chan[i], tc::EPI_ACT);
+    fill_layer(P, 5, W->chan[3], tc::EPI_DOT3);
     P.n_layers = 6;
-    P.mode = 1;
-    P.agg = agg_workspace; P.rgbs = (float4*)rgbs; P.feat_out = feat_out;
-    P.shape_out_w = W->shape_out_w; P.shape_out_b = W->shape_out_b; P.chan_out_w = W->chan_out_w; P.chan_out_b = W->chan_out_b;
+    P.img = img; P.rgbs = (float4*)rgbs; P.feat_out = feat_out;
+    memcpy(P.shape_out_w, W->shape_out_w, sizeof(float) * 256);
+    memcpy(P.chan_out_w, W->chan_out_w, sizeof(float) * 3 * 256);
+    P.shape_out_b = W->shape_out_b[0];
+    memcpy(P.chan_out_b, W->chan_out_b, sizeof(float) * 3);
     P.n_samples_dev = n_samples_dev; P.capacity = capacity; P.error_flag = error_flag;
-    rc = launch_tc(P, (capacity + 127) / 128, num_sms, st, "npcd_field_tc_fwd(heads)");
+    rc = launch_tc<tc::MODE_HEADS>(P, (capacity + 127) / 128, num_sms, st, "npcd_field_tc_fwd(heads)");
   }
   return rc;
 }
 
 // Probe / self-test: out[s, :] = x[s, :] @ W^T + b for one packed 256x256 layer (validates descriptors, swizzle, TMEM readback).
-extern "C" int npcd_tc_linear_probe(const float* x, const long long* n_rows_dev, long long capacity, const npcd_tc_layer* layer,
+// `image` is the pre-split operand image of x (npcd_tc_rows_to_image), ceil(capacity / 128) * 128 KB.
+extern "C" int npcd_tc_linear_probe(const void* image, const long long* n_rows_dev, long long capacity, const npcd_tc_layer* layer,
                                     float* out, int* error_flag, int num_sms, void* stream) {
-  NPCD_CHECK_ARG(x && n_rows_dev && layer && out, "null pointer");
+  NPCD_CHECK_ARG(image && n_rows_dev && layer && out, "null pointer");
   NPCD_CHECK_ARG(capacity > 0, "bad capacity");
-  tc::Params P{};
-  fill_layer(P.layers[0], *layer, tc::EPI_DUMP);
+  static thread_local tc::Params P;
+  memset(&P, 0, sizeof(P));
+  fill_layer(P, 0, *layer, tc::EPI_DUMP);
   P.n_layers = 1;
-  P.mode = 2;
-  P.agg = const_cast<float*>(x);
+  P.img = (uint8_t*)const_cast<void*>(image);
   P.feat_out = out;
   P.n_samples_dev = n_rows_dev; P.capacity = capacity; P.error_flag = error_flag;
-  return launch_tc(P, (capacity + 127) / 128, num_sms, (cudaStream_t)stream, "npcd_tc_linear_probe");
+  return launch_tc<tc::MODE_PROBE>(P, (capacity + 127) / 128, num_sms, (cudaStream_t)stream, "npcd_tc_linear_probe");
 }

@@ -10,6 +10,7 @@ import math
 from dataclasses import dataclass
 from typing import Optional
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -237,7 +238,8 @@ def pair_input_perm(feat_dim: int = 32, n_freqs: int = 10):
 
 
 class PackedTcWeights:
-    """MLP weights packed for ``npcd_field_tc_fwd``: pre-swizzled fp16 hi/lo tiles, power-of-two scaled (see include/npcd_b200.h)."""
+    """MLP weights packed for ``npcd_field_tc_fwd``: pre-swizzled fp16 hi/lo tiles on the device, power-of-two scaled; biases and
+    the two narrow output layers as HOST arrays (they travel to the kernel by value; see include/npcd_b200.h)."""
 
     def __init__(self, local_field, shape_net, channel_net, feat_dim: int):
         if feat_dim != 32:
@@ -251,55 +253,94 @@ class PackedTcWeights:
         s.feat_dim = feat_dim
         perm0 = torch.tensor(pair_input_perm(), dtype=torch.int32, device=dev)
         self.keep.append(perm0)
+        layers = [lf[0], lf[1], lf[2], lf[3], lf[4], sn[0], cn[0], cn[1], cn[2], cn[3]]
+        # one device->host transfer for everything the host needs: per-layer max|w| (scales), biases, narrow output layers
+        small = torch.cat([torch.stack([l.weight.detach().float().abs().max() for l in layers])]
+                          + [l.bias.detach().float().reshape(-1) for l in layers]
+                          + [sn[1].weight.detach().float().reshape(-1), sn[1].bias.detach().float().reshape(-1),
+                             cn[4].weight.detach().float().reshape(-1), cn[4].bias.detach().float().reshape(-1)]).cpu().numpy()
+        maxabs, off = small[:10], 10
 
-        def layer(dst, l, k_pad, perm=None):
+        def host(n):
+            nonlocal off
+            a = np.ascontiguousarray(small[off:off + n], dtype=np.float32)
+            off += n
+            self.keep.append(a)
+            return a.ctypes.data
+
+        def layer(dst, i, k_pad, perm=None):
+            l = layers[i]
             w = l.weight.detach().float().contiguous()
-            b = l.bias.detach().float().contiguous()
             assert w.shape[0] == HIDDEN
-            maxabs = float(w.abs().max().item())
-            scale = 2.0 ** math.floor(math.log2(4.0 / maxabs)) if maxabs > 0 else 1.0
+            scale = 2.0 ** math.floor(math.log2(4.0 / float(maxabs[i]))) if maxabs[i] > 0 else 1.0
             n_kb = (k_pad + 63) // 64
             out = torch.zeros(n_kb * 2 * 32768, dtype=torch.uint8, device=dev)
             call("npcd_tc_pack_weights", ptr(w), w.shape[1], ptr(perm), k_pad, float(scale), ptr(out), _stream())
             _count(1)
-            self.keep += [w, b, out]
-            dst.packed_w, dst.bias, dst.inv_scale, dst.k_pad = out.data_ptr(), b.data_ptr(), 1.0 / scale, k_pad
+            self.keep += [w, out]
+            dst.packed_w, dst.bias, dst.inv_scale, dst.k_pad = out.data_ptr(), host(HIDDEN), 1.0 / scale, k_pad
 
-        def vec(t):
-            v = t.detach().float().contiguous()
-            self.keep.append(v)
-            return v.data_ptr()
-
-        layer(s.pair[0], lf[0], 112, perm0)
+        layer(s.pair[0], 0, 112, perm0)
         for i in range(1, 4):
-            layer(s.pair[i], lf[i], 256)
-        layer(s.agg, lf[4], 256)
-        layer(s.shape, sn[0], 256)
+            layer(s.pair[i], i, 256)
+        layer(s.agg, 4, 256)
+        layer(s.shape, 5, 256)
         for i in range(4):
-            layer(s.chan[i], cn[i], 256)
-        s.shape_out_w, s.shape_out_b = vec(sn[1].weight.reshape(-1)), vec(sn[1].bias)
-        s.chan_out_w, s.chan_out_b = vec(cn[4].weight), vec(cn[4].bias)
+            layer(s.chan[i], 6 + i, 256)
+        s.shape_out_w, s.shape_out_b = host(HIDDEN), host(1)
+        s.chan_out_w, s.chan_out_b = host(3 * HIDDEN), host(3)
         self.struct = s
         self.error_flag = torch.zeros(1, dtype=torch.int32, device=dev)
 
 
+def tc_workspace_bytes(capacity: int) -> int:
+    n = C.c_size_t()
+    call("npcd_field_tc_workspace_bytes", int(capacity), C.byref(n))
+    return n.value
+
+
 def field_tc_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity: int, weights: PackedTcWeights,
-                 want_feat: bool = False):
-    """Tensor-core (tcgen05) field: rgbs [capacity,4] = (r,g,b,sigma); feat [capacity,256] if requested."""
+                 want_feat: bool = False, want_agg: bool = False):
+    """Tensor-core (tcgen05) field: rgbs [capacity,4] = (r,g,b,sigma); feat [capacity,256] if requested
+    (with want_agg: the aggregated pair features [capacity,256] recovered from the operand image, for tests)."""
     dev = sample_pos.device
     rgbs = torch.empty((capacity, 4), device=dev)
     feat = torch.empty((capacity, HIDDEN), device=dev) if want_feat else None
     if capacity == 0:
-        return rgbs, feat
-    agg = torch.empty((capacity, HIDDEN), device=dev)
+        return (rgbs, feat, None) if want_agg else (rgbs, feat)
+    nbytes = tc_workspace_bytes(capacity)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     kp_pos = kp_pos.detach().contiguous().float()
     kp_feat = kp_feat.detach().contiguous().float()
     args = (ptr(nbr_idx), ptr(sample_pos), ptr(kp_pos), ptr(kp_feat), ptr(n_samples_dev), capacity, C.byref(weights.struct),
-            ptr(agg), ptr(rgbs), ptr(feat))
+            ptr(ws), nbytes, ptr(rgbs), ptr(feat))
     _timed("pair_mlp", lambda: call("npcd_field_tc_fwd", *args, 1, ptr(weights.error_flag), sm_count(dev), _stream()))
     _timed("heads", lambda: call("npcd_field_tc_fwd", *args, 2, ptr(weights.error_flag), sm_count(dev), _stream()))
-    _count(2)
+    _count(6)  # pair-offset scan (3 launches) + tile starts + pair kernel + heads kernel
+    if want_agg:
+        agg = torch.empty((capacity, HIDDEN), device=dev)
+        call("npcd_tc_image_to_rows", ptr(ws), capacity, ptr(agg), _stream())
+        _count(1)
+        return rgbs, feat, agg
     return rgbs, feat
+
+
+def tc_rows_to_image(x):
+    """fp32 rows [n,256] -> the pre-split fp16 hi/lo operand image (uint8 [ceil(n/128) * 131072])."""
+    _need_cuda(x)
+    x = x.contiguous().float()
+    n = x.shape[0]
+    img = torch.zeros(((n + 127) // 128) * 131072, dtype=torch.uint8, device=x.device)
+    call("npcd_tc_rows_to_image", ptr(x), n, ptr(img), _stream())
+    _count(1 if n else 0)
+    return img
+
+
+def tc_image_to_rows(img, n: int):
+    out = torch.empty((n, HIDDEN), device=img.device)
+    call("npcd_tc_image_to_rows", ptr(img), n, ptr(out), _stream())
+    _count(1 if n else 0)
+    return out
 
 
 def tc_linear_probe(x, linear: torch.nn.Linear):
@@ -309,16 +350,17 @@ def tc_linear_probe(x, linear: torch.nn.Linear):
     x = x.contiguous().float()
     n = x.shape[0]
     w = linear.weight.detach().float().contiguous()
-    b = linear.bias.detach().float().contiguous()
+    b = np.ascontiguousarray(linear.bias.detach().float().cpu().numpy())
     maxabs = float(w.abs().max().item())
     scale = 2.0 ** math.floor(math.log2(4.0 / maxabs)) if maxabs > 0 else 1.0
     packed = torch.zeros(4 * 2 * 32768, dtype=torch.uint8, device=dev)
     call("npcd_tc_pack_weights", ptr(w), 256, None, 256, float(scale), ptr(packed), _stream())
-    lay = _lib.TcLayer(packed.data_ptr(), b.data_ptr(), 1.0 / scale, 256)
+    lay = _lib.TcLayer(packed.data_ptr(), b.ctypes.data, 1.0 / scale, 256)
+    img = tc_rows_to_image(x)
     out = torch.zeros((n, HIDDEN), device=dev)
     nrows = torch.tensor([n], dtype=torch.int64, device=dev)
     err = torch.zeros(1, dtype=torch.int32, device=dev)
-    call("npcd_tc_linear_probe", ptr(x), ptr(nrows), n, C.byref(lay), ptr(out), ptr(err), sm_count(dev), _stream())
+    call("npcd_tc_linear_probe", ptr(img), ptr(nrows), n, C.byref(lay), ptr(out), ptr(err), sm_count(dev), _stream())
     _count(2)
     torch.cuda.synchronize()
     if int(err.item()) != 0:

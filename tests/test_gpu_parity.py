@@ -395,6 +395,59 @@ def test_tc_linear_probe(torch_cuda):
     print("tc probe max err vs f64:", err, " torch fp32 err vs f64:", (fp32 - want).abs().max().item())
 
 
+def test_tc_operand_image_round_trip(torch_cuda):
+    """rows -> pre-split fp16 hi/lo SWIZZLE_128B image -> rows: 22 significant bits survive, ragged last tile."""
+    torch = torch_cuda
+    from npcd_b200 import ops
+
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    x = (torch.randn(300, 256, generator=gen) * 2.0).cuda()
+    img = ops.tc_rows_to_image(x)
+    assert img.numel() == 3 * 131072
+    y = ops.tc_image_to_rows(img, 300)
+    # hi keeps 11 significant bits, lo the next 11 (absolute floor: the fp16 subnormal quantum 2^-24)
+    excess = ((y - x).abs() - (x.abs() * 2.0 ** -21 + 2.0 ** -24)).max().item()
+    assert excess <= 0.0, excess
+
+
+def test_tc_pair_aggregate_matches_simt(syn, model, torch_cuda):
+    """Dense-packed tcgen05 pair stage vs the fp32 SIMT pair stage on the same kNN lists (aggregated features, [S,256])."""
+    torch = torch_cuda
+    from npcd_b200 import ops
+
+    g, coords, feats, extr, intr, res = load_case("view32", syn)
+    prev = model.field.mlp_impl
+    try:
+        model.field.mlp_impl = "simt"
+        with torch.no_grad():
+            out = model.renderer(_t(torch, coords), _t(torch, feats), _t(torch, extr), _t(torch, intr), res, False, return_aux=True)
+        aux = out["aux"]
+        nbr, pos = aux["neighbor_idx"], aux["sample_pos"]
+        S = nbr.shape[0]
+        n_dev = torch.tensor([S], dtype=torch.int64, device=nbr.device)
+        kp_pos, kp_feat = _t(torch, coords), _t(torch, feats)
+        simt_w = ops.PackedSimtWeights(model.field.aggregator.local_field, model.field.shape_net, model.field.channel_net, 32)
+        tc_w = ops.PackedTcWeights(model.field.aggregator.local_field, model.field.shape_net, model.field.channel_net, 32)
+        dev = nbr.device
+        rgbs_s = torch.empty((S, 4), device=dev)
+        agg_s = torch.empty((S, 256), device=dev)
+        import ctypes as C
+        from npcd_b200._lib import call, ptr
+        call("npcd_field_simt_fwd", ptr(nbr), ptr(pos), ptr(kp_pos.contiguous()), ptr(kp_feat.contiguous()), ptr(n_dev), S,
+             C.byref(simt_w.struct), ptr(agg_s), ptr(rgbs_s), None, 3, ops.sm_count(dev), torch.cuda.current_stream().cuda_stream)
+        rgbs_t, _, agg_t = ops.field_tc_fwd(nbr, pos, kp_pos, kp_feat, n_dev, S, tc_w, want_agg=True)
+        torch.cuda.synchronize()
+        assert int(tc_w.error_flag.item()) == 0
+    finally:
+        model.field.mlp_impl = prev
+    scale = max(1.0, agg_s.abs().max().item())
+    err_a = (agg_t - agg_s).abs().max().item()
+    err_r = (rgbs_t - rgbs_s).abs().max().item()
+    print("tc vs simt: agg err", err_a, "rgbs err", err_r, "S", S)
+    assert err_a < 2e-5 * scale, err_a
+    assert err_r < 2e-5 * max(1.0, rgbs_s.abs().max().item()), err_r
+
+
 @pytest.fixture()
 def tc_model(model):
     prev = model.field.mlp_impl
