@@ -73,17 +73,29 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or ~20 us pass) instead of
+// re-polling every few cycles (the un-hinted form returned ~10^6 times per CTA per launch and burnt issue slots and power).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(20000u)
         : "memory");
   } while (!ok);
+}
+// true in exactly one lane of a fully active warp (always the same one), and the compiler knows it
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
@@ -285,84 +297,101 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
 
   if (warp == 0) {
     // ================================================= weight producer ==================================================
-    if (lane == 0) {
-      int st = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int l = 0; l < n_layers; ++l) {
-          const int nkb = (P.layers[l].ksteps + 3) >> 2;
-          const uint8_t* src = P.layers[l].w;
-          for (int t = 0; t < 2 * nkb; ++t) {
-            mbar_wait(bar(kBarWEmpty + st), ph ^ 1);
+    // (whole warp runs the loop so every value stays warp-uniform; one elected lane issues the copies)
+    int st = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int l = 0; l < n_layers; ++l) {
+        const int nkb = (P.layers[l].ksteps + 3) >> 2;
+        const uint8_t* src = P.layers[l].w;
+        for (int t = 0; t < 2 * nkb; ++t) {
+          mbar_wait(bar(kBarWEmpty + st), ph ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(bar(kBarWFull + st), kTileBytesW);
             bulk_g2s(smem_u32(sW + st * kTileBytesW), src + (size_t)t * kTileBytesW, kTileBytesW, bar(kBarWFull + st));
-            if (++st == kStages) { st = 0; ph ^= 1; }
           }
+          __syncwarp();
+          if (++st == kStages) { st = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer ===================================================
-    if (lane == 0) {
-      int st = 0;
-      uint32_t ph_w = 0;
-      uint32_t ph_ar = 0, ph_a0 = 0;  // one parity bit per K-block
-      uint32_t ph_af = 0;             // acc_free parity bits (bit b = accumulator b)
-      uint32_t lc = 0;                // running layer counter: layer lc accumulates into TMEM columns (lc & 1) * 256
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int l = 0; l < n_layers; ++l, ++lc) {
-          const uint32_t ab = lc & 1u;
-          const uint32_t d_tmem = tmem_base + ab * 256u;
-          mbar_wait(bar(kBarAccFree + ab), ((ph_af >> ab) & 1u) ^ 1u);  // every epilogue warp has drained this accumulator
-          ph_af ^= 1u << ab;
-          tc_fence_after();
-          const int ksteps = P.layers[l].ksteps;
-          const int nkb = (ksteps + 3) >> 2;
-          // heads layer 2 (channel_net.0) reads the same operand (feat) as layer 1 (shape_net.0): nothing new to wait for
-          const bool fresh_a = !(kMode == MODE_HEADS && l == 2);
-          for (int kb = 0; kb < nkb; ++kb) {
-            if (kMode != MODE_PAIR && l == 0) {
-              mbar_wait(bar(kBarA0Rdy + kb), (ph_a0 >> kb) & 1u);
-              ph_a0 ^= 1u << kb;
-            } else if (fresh_a) {
-              mbar_wait(bar(kBarARdy + kb), (ph_ar >> kb) & 1u);
-              ph_ar ^= 1u << kb;
-            }
-            tc_fence_after();
-            const int ks_n = min(4, ksteps - kb * 4);
-            const uint32_t a_hi = smem_u32(sA + kb * 2 * kTileBytesA), a_lo = a_hi + kTileBytesA;
-            // stage "hi": A_hi*W_hi + A_lo*W_hi
-            mbar_wait(bar(kBarWFull + st), ph_w);
-            tc_fence_after();
-            uint32_t b = smem_u32(sW + st * kTileBytesW);
-            for (int ks = 0; ks < ks_n; ++ks)
-              umma_f16(d_tmem, make_desc(a_hi + ks * 32), make_desc(b + ks * 32), kIdesc, (kb | ks) != 0);
-            for (int ks = 0; ks < ks_n; ++ks) umma_f16(d_tmem, make_desc(a_lo + ks * 32), make_desc(b + ks * 32), kIdesc, 1u);
-            umma_commit(bar(kBarWEmpty + st));
-            if (++st == kStages) { st = 0; ph_w ^= 1; }
-            // stage "lo": A_hi*W_lo
-            mbar_wait(bar(kBarWFull + st), ph_w);
-            tc_fence_after();
-            b = smem_u32(sW + st * kTileBytesW);
-            for (int ks = 0; ks < ks_n; ++ks) umma_f16(d_tmem, make_desc(a_hi + ks * 32), make_desc(b + ks * 32), kIdesc, 1u);
-            umma_commit(bar(kBarWEmpty + st));
-            if (++st == kStages) { st = 0; ph_w ^= 1; }
-            if (l == n_layers - 1) umma_commit(bar(kBarAFree + kb));  // this K-block may take the next tile's first operand
+    // The whole warp walks the schedule and waits on the barriers (all values warp-uniform -> uniform registers, no per-lane
+    // descriptor shuffling); one elected lane -- always the same, tcgen05.commit tracks the issuing thread -- issues the MMAs.
+    int st = 0;
+    uint32_t ph_w = 0;
+    uint32_t ph_ar = 0, ph_a0 = 0;  // one parity bit per K-block
+    uint32_t ph_af = 0;             // acc_free parity bits (bit b = accumulator b)
+    uint32_t lc = 0;                // running layer counter: layer lc accumulates into TMEM columns (lc & 1) * 256
+    const uint64_t desc_a0 = make_desc(smem_u32(sA));
+    const uint64_t desc_w0 = make_desc(smem_u32(sW));
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int l = 0; l < n_layers; ++l, ++lc) {
+        const uint32_t ab = lc & 1u;
+        const uint32_t d_tmem = tmem_base + ab * 256u;
+        mbar_wait(bar(kBarAccFree + ab), ((ph_af >> ab) & 1u) ^ 1u);  // every epilogue warp has drained this accumulator
+        ph_af ^= 1u << ab;
+        const int ksteps = P.layers[l].ksteps;
+        const int nkb = (ksteps + 3) >> 2;
+        // heads layer 2 (channel_net.0) reads the same operand (feat) as layer 1 (shape_net.0): nothing new to wait for
+        const bool fresh_a = !(kMode == MODE_HEADS && l == 2);
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (kMode != MODE_PAIR && l == 0) {
+            mbar_wait(bar(kBarA0Rdy + kb), (ph_a0 >> kb) & 1u);
+            ph_a0 ^= 1u << kb;
+          } else if (fresh_a) {
+            mbar_wait(bar(kBarARdy + kb), (ph_ar >> kb) & 1u);
+            ph_ar ^= 1u << kb;
           }
-          umma_commit(bar(kBarAccRdy + ab));
+          const int ks_n = min(4, ksteps - kb * 4);
+          // descriptor start-address field counts 16-byte units: +2 per 16-column K step, +1024 per 16 KB tile
+          const uint64_t a_hi = desc_a0 + (uint64_t)(kb * 2 * (kTileBytesA >> 4)), a_lo = a_hi + (kTileBytesA >> 4);
+          // stage "hi": A_hi*W_hi + A_lo*W_hi
+          mbar_wait(bar(kBarWFull + st), ph_w);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t b = desc_w0 + (uint64_t)(st * (kTileBytesW >> 4));
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              if (ks < ks_n) umma_f16(d_tmem, a_hi + 2 * ks, b + 2 * ks, kIdesc, (kb | ks) != 0);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              if (ks < ks_n) umma_f16(d_tmem, a_lo + 2 * ks, b + 2 * ks, kIdesc, 1u);
+            umma_commit(bar(kBarWEmpty + st));
+          }
+          __syncwarp();
+          if (++st == kStages) { st = 0; ph_w ^= 1; }
+          // stage "lo": A_hi*W_lo
+          mbar_wait(bar(kBarWFull + st), ph_w);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t b = desc_w0 + (uint64_t)(st * (kTileBytesW >> 4));
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              if (ks < ks_n) umma_f16(d_tmem, a_hi + 2 * ks, b + 2 * ks, kIdesc, 1u);
+            umma_commit(bar(kBarWEmpty + st));
+            if (l == n_layers - 1) umma_commit(bar(kBarAFree + kb));  // this K-block may take the next tile's first operand
+            if (kb == nkb - 1) umma_commit(bar(kBarAccRdy + ab));
+          }
+          __syncwarp();
+          if (++st == kStages) { st = 0; ph_w ^= 1; }
         }
       }
     }
   } else if (warp == 10) {
     // ======================================== heads / probe: first-operand loader =======================================
-    if (kMode != MODE_PAIR && lane == 0) {
+    if (kMode != MODE_PAIR) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         for (int kb = 0; kb < 4; ++kb) {
           if (it > 0) mbar_wait(bar(kBarAFree + kb), (it - 1) & 1u);
-          mbar_expect_tx(bar(kBarA0Rdy + kb), 2 * kTileBytesA);
-          bulk_g2s(smem_u32(sA + kb * 2 * kTileBytesA), P.img + (size_t)tile * kImgTileBytes + (size_t)kb * 2 * kTileBytesA,
-                   2 * kTileBytesA, bar(kBarA0Rdy + kb));
+          if (elect_one()) {
+            mbar_expect_tx(bar(kBarA0Rdy + kb), 2 * kTileBytesA);
+            bulk_g2s(smem_u32(sA + kb * 2 * kTileBytesA), P.img + (size_t)tile * kImgTileBytes + (size_t)kb * 2 * kTileBytesA,
+                     2 * kTileBytesA, bar(kBarA0Rdy + kb));
+          }
+          __syncwarp();
         }
       }
     }
