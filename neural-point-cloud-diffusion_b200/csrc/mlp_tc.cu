@@ -162,6 +162,39 @@ __host__ __device__ __forceinline__ uint32_t swz(int row, int c16) {
 
 __device__ __forceinline__ float lrelu(float x) { return fmaxf(x, 0.01f * x); }
 
+// Packed fp32 pairs (FFMA2 / FMUL2 / FADD2 on sm_100): one issue slot for two lanes of arithmetic; the epilogues are issue-bound.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// y = max(t, slope * t) with t = v * inv + b, for the pair (v0, v1)
+__device__ __forceinline__ void act2(uint32_t v0, uint32_t v1, uint64_t inv2, float b0, float b1, uint64_t slope2, float& y0, float& y1) {
+  const uint64_t t = fma2(pack2(__uint_as_float(v0), __uint_as_float(v1)), inv2, pack2(b0, b1));
+  const uint64_t u = mul2(t, slope2);
+  float t0, t1, u0, u1;
+  unpack2(t, t0, t1);
+  unpack2(u, u0, u1);
+  y0 = fmaxf(t0, u0);
+  y1 = fmaxf(t1, u1);
+}
+
 // sin and cos of |a| < ~1e4 to ~1e-7 absolute: two-term Cody-Waite reduction by pi/2 (exact first step under FMA), Taylor
 // polynomials to r^9 / r^8 on |r| <= pi/4 (truncation 2e-9 / 2e-8), quadrant from the low bits of the rounding magic number.
 // The positional-encoding arguments are |x_rel * 2^i pi| <= 129 (utils/positional_encoder.py:17-20); this replaces sincosf,
@@ -193,7 +226,9 @@ __device__ __forceinline__ void split8(const float (&y)[8], uint4& hi, uint4& lo
   for (int j = 0; j < 4; ++j) {
     const __half2 hh = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
     const float2 f = __half22float2(hh);
-    const __half2 ll = __floats2half2_rn(y[2 * j] - f.x, y[2 * j + 1] - f.y);
+    float r0, r1;
+    unpack2(sub2(pack2(y[2 * j], y[2 * j + 1]), pack2(f.x, f.y)), r0, r1);
+    const __half2 ll = __floats2half2_rn(r0, r1);
     h[j] = *reinterpret_cast<const uint32_t*>(&hh);
     l[j] = *reinterpret_cast<const uint32_t*>(&ll);
   }
@@ -241,16 +276,16 @@ __device__ __forceinline__ void epi_chunk_store(const Params& P, int l, float in
                                                 uint8_t* sA, uint32_t rowbase, int x7, float* feat_row) {
   uint8_t* kb_base = sA + (c0 >> 6) * (2 * kTileBytesA) + rowbase;
   const int c16_0 = (c0 & 63) >> 3;
+  const uint64_t inv2 = pack2(inv, inv), slope2 = pack2(slope, slope);
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const float4 b0 = *reinterpret_cast<const float4*>(&P.bias[l][c0 + g * 8]);
     const float4 b1 = *reinterpret_cast<const float4*>(&P.bias[l][c0 + g * 8 + 4]);
-    float y[8] = {fmaf(__uint_as_float(v[g * 8 + 0]), inv, b0.x), fmaf(__uint_as_float(v[g * 8 + 1]), inv, b0.y),
-                  fmaf(__uint_as_float(v[g * 8 + 2]), inv, b0.z), fmaf(__uint_as_float(v[g * 8 + 3]), inv, b0.w),
-                  fmaf(__uint_as_float(v[g * 8 + 4]), inv, b1.x), fmaf(__uint_as_float(v[g * 8 + 5]), inv, b1.y),
-                  fmaf(__uint_as_float(v[g * 8 + 6]), inv, b1.z), fmaf(__uint_as_float(v[g * 8 + 7]), inv, b1.w)};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], slope * y[j]);
+    float y[8];
+    act2(v[g * 8 + 0], v[g * 8 + 1], inv2, b0.x, b0.y, slope2, y[0], y[1]);
+    act2(v[g * 8 + 2], v[g * 8 + 3], inv2, b0.z, b0.w, slope2, y[2], y[3]);
+    act2(v[g * 8 + 4], v[g * 8 + 5], inv2, b1.x, b1.y, slope2, y[4], y[5]);
+    act2(v[g * 8 + 6], v[g * 8 + 7], inv2, b1.z, b1.w, slope2, y[6], y[7]);
     if (feat_row) {
       *reinterpret_cast<float4*>(feat_row + c0 + g * 8) = make_float4(y[0], y[1], y[2], y[3]);
       *reinterpret_cast<float4*>(feat_row + c0 + g * 8 + 4) = make_float4(y[4], y[5], y[6], y[7]);
@@ -603,8 +638,11 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
             for (int j = 0; j < cnt; ++j) wsum += wts[r0 + j];
             wn = wts[row] / wsum;
           }
-          float* stage = reinterpret_cast<float*>(sA + 4 * kTileBytesA);  // [128 rows][128 cols] fp32, 16-byte chunks XOR (row & 31)
-          const int x31 = row & 31;
+          // staging: [128 rows][128 cols] fp32 in K-blocks 2..3.  16-byte chunk c4 of a row sits at position
+          // ((c4 >> 1) | ((c4 & 1) << 4)) ^ (row & 7): conflict-free for the row-per-lane stores AND for the sum phase, where
+          // 16 lanes read chunks 2 c8 and 2 c8 + 1 of one row.
+          float* stage = reinterpret_cast<float*>(sA + 4 * kTileBytesA);
+          const uint64_t inv2 = pack2(inv, inv), slope2 = pack2(0.01f, 0.01f), wn2 = pack2(wn, wn);
 #pragma unroll 1
           for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll 1
@@ -617,12 +655,15 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
 #pragma unroll
               for (int g = 0; g < 8; ++g) {
                 const float4 b = *reinterpret_cast<const float4*>(&P.bias[3][c0 + g * 4]);
-                const float4 o = make_float4(wn * lrelu(fmaf(__uint_as_float(v[g * 4 + 0]), inv, b.x)),
-                                             wn * lrelu(fmaf(__uint_as_float(v[g * 4 + 1]), inv, b.y)),
-                                             wn * lrelu(fmaf(__uint_as_float(v[g * 4 + 2]), inv, b.z)),
-                                             wn * lrelu(fmaf(__uint_as_float(v[g * 4 + 3]), inv, b.w)));
+                float y0, y1, y2, y3;
+                act2(v[g * 4 + 0], v[g * 4 + 1], inv2, b.x, b.y, slope2, y0, y1);
+                act2(v[g * 4 + 2], v[g * 4 + 3], inv2, b.z, b.w, slope2, y2, y3);
+                float4 o;
+                unpack2(mul2(pack2(y0, y1), wn2), o.x, o.y);
+                unpack2(mul2(pack2(y2, y3), wn2), o.z, o.w);
                 const int c4 = (cl >> 2) + g;
-                *reinterpret_cast<float4*>(stage + row * 128 + ((c4 ^ x31) << 2)) = o;
+                const int pos = ((c4 >> 1) | ((c4 & 1) << 4)) ^ x7;
+                *reinterpret_cast<float4*>(stage + row * 128 + (pos << 2)) = o;
               }
             }
             if (pass == 1) release_acc(ab);
@@ -633,8 +674,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
               float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
               for (int j = 0; j < cnt; ++j) {
                 const int r = r0 + j;
-                const float4 t0 = *reinterpret_cast<const float4*>(stage + r * 128 + (((2 * c8) ^ (r & 31)) << 2));
-                const float4 t1 = *reinterpret_cast<const float4*>(stage + r * 128 + (((2 * c8 + 1) ^ (r & 31)) << 2));
+                const float* rp = stage + r * 128 + ((c8 ^ (r & 7)) << 2);
+                const float4 t0 = *reinterpret_cast<const float4*>(rp);
+                const float4 t1 = *reinterpret_cast<const float4*>(rp + 64);
                 acc[0] += t0.x; acc[1] += t0.y; acc[2] += t0.z; acc[3] += t0.w;
                 acc[4] += t1.x; acc[5] += t1.y; acc[6] += t1.z; acc[7] += t1.w;
               }
