@@ -55,7 +55,7 @@ class VolumeRenderer(nn.Module):
         self.disparity_space_sampling = disparity_space_sampling
         self.white_back = white_back
         self.randomize_depth_samples = False  # toggled by PointNeRF.train() (pointnerf.py:30-33)
-        self.max_samples_per_chunk = 1 << 24  # kept shading samples per fused field launch (bounds the workspace)
+        self.max_samples_per_chunk = 1 << 25  # kept shading samples per fused field launch (bounds the workspace: ~1.1 KB each)
         self.last_stats = {}
 
     # ---- train-mode valid-ray subsampling (fields/aggregators/aggregator.py:78-119) ----
@@ -145,26 +145,35 @@ class VolumeRenderer(nn.Module):
                 aux = dict(neighbor_idx=nbr, sample_pos=pos, rgbs=rgbs, feat=feat, ray_offset=ray_offset, ray_count=ray_count,
                            rays=rays, ray_ids=ray_ids)
         else:
-            # inference: chunk rays so the per-launch workspace stays bounded; the depth clamp range is shared by all chunks
+            # inference: one scan over all rays gives the kept-sample total (the single host sync); if it fits the workspace
+            # bound the whole batch is ONE launch group, otherwise rays are chunked by the measured sample density.  The depth
+            # clamp range is shared by all chunks.
             rng_scratch = torch.empty(2, dtype=torch.int32, device=dev)
             n_rays = N * R
-            rays_per_chunk = max(R, (self.max_samples_per_chunk // max(SR, 1)) // R * R) if R > 0 else 1
             ray_end = rays.end.reshape(-1)
-            S_total = 0
             first = True
-            for r0 in range(0, max(n_rays, 1), rays_per_chunk):
-                r1 = min(n_rays, r0 + rays_per_chunk)
-                if r1 <= r0:
-                    break
-                ids = None if (r0 == 0 and r1 == n_rays) else torch.arange(r0, r1, dtype=torch.int32, device=dev)
-                ray_offset = ops.scan_counts(ray_count, ids) if ids is not None else ops.scan_counts(ray_count)
-                S = int(ray_offset[-1].item())
-                S_total += S
-                nbr, pos, _ = ops.knn_fill(rays, grid, T, radius, valid_bits, ray_offset, S, ids, jitter)
-                rgbs, _ = self.field.evaluate(nbr, pos, kp_pos, kp_feat, ray_offset[-1:], S)
-                ops.composite_fwd(pos, rgbs, ray_offset, ray_end, ids, self.white_back, range_scratch=rng_scratch, init_range=first,
-                                  out=(mask[r0:r1], depth[r0:r1], rgb[r0:r1]))
-                first = False
+            S_total = 0
+            if n_rays > 0:
+                ray_offset = ops.scan_counts(ray_count)
+                S_total = int(ray_offset[-1].item())
+                cap = int(self.max_samples_per_chunk)
+                if S_total <= cap:
+                    chunks = [(0, n_rays, ray_offset, S_total)]
+                else:
+                    per_ray = S_total / n_rays
+                    rays_per_chunk = max(R, int(cap / (1.25 * per_ray)) // R * R)
+                    chunks = [(r0, min(n_rays, r0 + rays_per_chunk), None, None) for r0 in range(0, n_rays, rays_per_chunk)]
+                for r0, r1, ray_offset, S in chunks:
+                    ids = None
+                    if ray_offset is None:
+                        ids = torch.arange(r0, r1, dtype=torch.int32, device=dev)
+                        ray_offset = ops.scan_counts(ray_count, ids)
+                        S = int(ray_offset[-1].item())
+                    nbr, pos, _ = ops.knn_fill(rays, grid, T, radius, valid_bits, ray_offset, S, ids, jitter)
+                    rgbs, _ = self.field.evaluate(nbr, pos, kp_pos, kp_feat, ray_offset[-1:], S)
+                    ops.composite_fwd(pos, rgbs, ray_offset, ray_end, ids, self.white_back, range_scratch=rng_scratch,
+                                      init_range=first, out=(mask[r0:r1], depth[r0:r1], rgb[r0:r1]))
+                    first = False
             if first:  # no rays at all
                 ops.composite_fwd(None, None, torch.zeros(1, dtype=torch.int64, device=dev), ray_end, None, self.white_back,
                                   range_scratch=rng_scratch, init_range=True, out=(mask, depth, rgb))

@@ -304,7 +304,7 @@ def test_full_size_properties(syn, model, cameras, torch_cuda):
             assert torch.equal(a[k], b[k]), k
         # chunked == unchunked (the clamp range is shared across chunks)
         prev = r.max_samples_per_chunk
-        r.max_samples_per_chunk = 50 * 16384 * 2
+        r.max_samples_per_chunk = 200_000  # < the ~600 k kept samples of these 8 views: forces 2-view chunks
         try:
             cch = r(c, f, e, i, 128, False)
         finally:
