@@ -138,6 +138,21 @@ int npcd_tc_image_to_rows(const void* image, long long n, float* rows, void* str
 int npcd_tc_linear_probe(const void* image, const long long* n_rows_dev, long long capacity, const npcd_tc_layer* layer, float* out,
                          int* error_flag, int num_sms, void* stream);
 
+/* ---- generic fp32-accurate tensor-core GEMM (training path: forward / dgrad / wgrad of the nn.Linear layers, row B* of
+ * SURVEY.md section 8; the reference runs them as fp32 cuBLAS GEMMs under autograd) ------------------------------------------
+ * npcd_tc_pack_rows builds the pre-split fp16 hi/lo operand image (see npcd_tc_rows_to_image; here any K, padded to 64) of
+ *   X'[r',k'] = src[r',k'] (transpose = 0, src is [rows, cols] with row stride ld) or src[k',r'] (transpose = 1),
+ *   times (mask_src[same position] > 0 ? 1 : slope) if mask_src != NULL (LeakyReLU derivative), times *scale_dev (device scalar,
+ *   a power of two; NULL = 1).  npcd_tc_image_bytes(rows', k') sizes it.
+ * npcd_tc_gemm:  C[M,N] = act((A . B^T) * *out_scale_dev + bias),  A image [M,K], B image [N,K], N <= 256, act = LeakyReLU with
+ *   slope act_slope (1 = identity); split_k > 1 reduces partial sums from `workspace` in a fixed order (deterministic).        */
+int npcd_tc_image_bytes(long long rows, long long k, size_t* bytes);
+int npcd_tc_pack_rows(const float* src, long long rows, int cols, long long ld, int transpose, const float* mask_src, float slope,
+                      const float* scale_dev, void* image, void* stream);
+int npcd_tc_gemm_workspace_bytes(int M, int split_k, size_t* bytes);
+int npcd_tc_gemm(const void* a_image, const void* b_image, int M, int N, long long K, float* C, long long ldc, const float* bias,
+                 const float* out_scale_dev, float act_slope, int split_k, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- compositing: replaces Renderer.get_depths_from_shading_pts (renderers/renderer.py:95-110), VolumeRenderer.get_alpha
  * (renderers/volume_renderer.py:23-39), Renderer.ray_march (renderers/renderer.py:120-185).
  *   out_mask [n_sel], out_depth [n_sel] (UNCLAMPED, NaN -> +inf), out_rgb [n_sel,3]; range_scratch (8 bytes) accumulates the

@@ -80,6 +80,10 @@ SIGNATURES = {
     "npcd_tc_rows_to_image": [P, L, P, P],
     "npcd_tc_image_to_rows": [P, L, P, P],
     "npcd_tc_linear_probe": [P, P, L, P, P, P, I, P],
+    "npcd_tc_image_bytes": [L, L, P],
+    "npcd_tc_pack_rows": [P, L, I, L, I, P, F, P, P, P],
+    "npcd_tc_gemm_workspace_bytes": [I, I, P],
+    "npcd_tc_gemm": [P, P, I, I, L, P, L, P, P, F, I, P, C.c_size_t, P],
     "npcd_composite_fwd": [P, P, P, P, P, L, I, P, P, P, P, I, P],
     "npcd_clamp_depth": [P, L, P, P, P],
     "npcd_composite_bwd": [P, P, P, L, I, P, P, P, P, P, P, P, P],

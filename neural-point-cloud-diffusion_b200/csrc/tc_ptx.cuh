@@ -1,0 +1,191 @@
+// tcgen05 / TMEM / mbarrier / bulk-copy PTX wrappers and the fp16 hi/lo operand-image helpers shared by the tensor-core kernels
+// (mlp_tc.cu: fused field; gemm_tc.cu: generic fp32-accurate GEMM of the training path).  sm_100a only.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace npcd {
+namespace tc {
+
+constexpr int kTileBytesA = 128 * 128;  // one K-block (64 fp16) of 128 rows
+constexpr uint32_t kIdescBase = (1u << 4);  // D = f32, A = B = f16, both K-major
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t m, uint32_t n) { return kIdescBase | ((n >> 3) << 17) | ((m >> 4) << 24); }
+
+// ---------------------------------------------------------------------------------------------------------------- PTX ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or ~20 us pass) instead of
+// re-polling every few cycles (the un-hinted form returned ~10^6 times per CTA per launch and burnt issue slots and power).
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(20000u)
+        : "memory");
+  } while (!ok);
+}
+// true in exactly one lane of a fully active warp (always the same one), and the compiler knows it
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// asynchronous TMEM -> register load of 32 consecutive fp32 columns of this thread's lane; complete after tmem_wait(v)
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+// tcgen05.wait::ld with the destination registers as in/out operands, so no use of them can be scheduled above the wait
+__device__ __forceinline__ void tmem_wait(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                 "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                 "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(1)<<16 | SBO(1024B>>4)<<32 |
+// version 1 <<46 | layout SWIZZLE_128B(2) <<61.  Rows are 128 B (64 fp16), 8-row groups are 1024 B apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// byte offset of the 16-byte chunk holding columns [8*c16, 8*c16+8) of `row` inside a K-block tile
+__host__ __device__ __forceinline__ uint32_t swz(int row, int c16) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((c16 ^ (row & 7)) << 4));
+}
+
+__device__ __forceinline__ float lrelu(float x) { return fmaxf(x, 0.01f * x); }
+
+// Packed fp32 pairs (FFMA2 / FMUL2 / FADD2 on sm_100): one issue slot for two lanes of arithmetic; the epilogues are issue-bound.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// y = max(t, slope * t) with t = v * inv + b, for the pair (v0, v1)
+__device__ __forceinline__ void act2(uint32_t v0, uint32_t v1, uint64_t inv2, float b0, float b1, uint64_t slope2, float& y0, float& y1) {
+  const uint64_t t = fma2(pack2(__uint_as_float(v0), __uint_as_float(v1)), inv2, pack2(b0, b1));
+  const uint64_t u = mul2(t, slope2);
+  float t0, t1, u0, u1;
+  unpack2(t, t0, t1);
+  unpack2(u, u0, u1);
+  y0 = fmaxf(t0, u0);
+  y1 = fmaxf(t1, u1);
+}
+
+// sin and cos of |a| < ~1e4 to ~1e-7 absolute: two-term Cody-Waite reduction by pi/2 (exact first step under FMA), Taylor
+// polynomials to r^9 / r^8 on |r| <= pi/4 (truncation 2e-9 / 2e-8), quadrant from the low bits of the rounding magic number.
+// The positional-encoding arguments are |x_rel * 2^i pi| <= 129 (utils/positional_encoder.py:17-20); this replaces sincosf,
+// whose (never taken) Payne-Hanek slow path would be inlined thirty times.
+__device__ __forceinline__ void sincos_small(float a, float& sn, float& cs) {
+  const float t = fmaf(a, 0.636619747f, 12582912.0f);
+  const int quad = __float_as_int(t);
+  const float q = t - 12582912.0f;
+  float r = fmaf(q, -1.57079637f, a);
+  r = fmaf(q, 4.37113883e-8f, r);
+  const float r2 = r * r;
+  float s = fmaf(r2, 2.75573192e-6f, -1.98412698e-4f);
+  s = fmaf(s, r2, 8.33333333e-3f);
+  s = fmaf(s, r2, -1.66666667e-1f);
+  s = fmaf(s * r2, r, r);
+  float c = fmaf(r2, 2.48015873e-5f, -1.38888889e-3f);
+  c = fmaf(c, r2, 4.16666667e-2f);
+  c = fmaf(c, r2, -0.5f);
+  c = fmaf(c, r2, 1.0f);
+  const float u = (quad & 1) ? c : s, w = (quad & 1) ? s : c;
+  sn = (quad & 2) ? -u : u;
+  cs = ((quad + 1) & 2) ? -w : w;
+}
+
+// fp16 hi / lo halves of 8 fp32 values as two 16-byte vectors
+__device__ __forceinline__ void split8(const float (&y)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __half2 hh = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
+    const float2 f = __half22float2(hh);
+    float r0, r1;
+    unpack2(sub2(pack2(y[2 * j], y[2 * j + 1]), pack2(f.x, f.y)), r0, r1);
+    const __half2 ll = __floats2half2_rn(r0, r1);
+    h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+}  // namespace tc
+}  // namespace npcd

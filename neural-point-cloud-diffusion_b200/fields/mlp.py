@@ -3,8 +3,9 @@
 
 Two evaluation routes over the same parameters:
   * ``evaluate``        -- no-grad inference: ONE fused CUDA call (gather + posenc + pair MLP + aggregation + heads).
-  * ``evaluate_autograd`` -- training: custom CUDA gather/posenc + composite kernels, dense layers through ``F.linear`` so
-                           autograd produces dgrad/wgrad (round-1 state; see DESIGN.md "training path").
+  * ``evaluate_autograd`` -- training: every dense layer (forward, dgrad, wgrad) runs on the tcgen05 GEMM ``npcd_tc_gemm`` through
+                           ``ops.LinearTC``; gather / posenc / aggregation / output activations are elementwise torch ops
+                           under autograd (see DESIGN.md "training path").
 """
 from __future__ import annotations
 
@@ -71,8 +72,9 @@ class MLP(Module):
         freq = (2.0 ** torch.arange(self.aggregator.n_freqs, dtype=torch.float32, device=w.device)) * torch.pi
         spec = x_rel[..., None] * freq
         enc = torch.cat([spec.sin(), spec.cos()], -1).flatten(-2)
-        local = self.aggregator.local_field(torch.cat([feat, x_rel, enc], -1))
+        dense = ops.mlp_tc if self.mlp_impl == "tc" else (lambda seq, t: seq(t))
+        local = dense(self.aggregator.local_field, torch.cat([feat, x_rel, enc], -1))
         agg = torch.zeros(S, local.shape[1], device=w.device).index_add_(0, sidx, w[:, None] * local)
-        sigma = F.softplus(self.shape_net(agg) - 1)
-        rgb = torch.sigmoid(self.channel_net(agg))
+        sigma = F.softplus(dense(self.shape_net, agg) - 1)
+        rgb = torch.sigmoid(dense(self.channel_net, agg))
         return torch.cat([rgb, sigma], -1)

@@ -368,6 +368,109 @@ def tc_linear_probe(x, linear: torch.nn.Linear):
     return out
 
 
+# ---- generic tensor-core GEMM (training path) ----------------------------------------------------------------------------
+@dataclass
+class OperandImage:
+    data: torch.Tensor   # uint8 image
+    scale: torch.Tensor  # [1] fp32 device, power of two the values were multiplied by
+    rows: int
+    k: int
+
+
+def _pow2_scale(x):
+    """device scalar 2^floor(log2(2 / max|x|)) (1 if x == 0): keeps fp16 hi/lo halves in the normal range, no host sync"""
+    amax = x.detach().abs().amax().float()
+    s = torch.exp2(torch.floor(torch.log2(2.0 / amax.clamp_min(1e-30))))
+    return torch.where(amax > 0, s, torch.ones_like(s)).reshape(1).contiguous()
+
+
+def tc_pack(src, transpose: bool = False, mask=None, slope: float = 1.0) -> OperandImage:
+    """fp32 [rows, cols] -> operand image of src (or src^T), optionally times the LeakyReLU-derivative mask of `mask`."""
+    _need_cuda(src, mask)
+    src = src.contiguous().float()
+    rows, cols = src.shape
+    if mask is not None:
+        mask = mask.contiguous().float()
+        assert mask.shape == src.shape
+    img_rows, img_k = (cols, rows) if transpose else (rows, cols)
+    n = C.c_size_t()
+    call("npcd_tc_image_bytes", img_rows, img_k, C.byref(n))
+    img = torch.empty(n.value, dtype=torch.uint8, device=src.device)
+    scale = _pow2_scale(src)
+    call("npcd_tc_pack_rows", ptr(src), rows, cols, cols, int(transpose), ptr(mask), float(slope), ptr(scale), ptr(img), _stream())
+    _count(1)
+    return OperandImage(img, scale, img_rows, img_k)
+
+
+def tc_gemm(a: OperandImage, b: OperandImage, bias=None, slope: float = 1.0, split_k: int = 1):
+    """C[M,N] = lrelu_slope((A . B^T) + bias) on tcgen05 with fp32-level accuracy (3-product fp16 hi/lo emulation)."""
+    assert a.k == b.k, (a.k, b.k)
+    M, N, K = a.rows, b.rows, a.k
+    dev = a.data.device
+    out = torch.empty((M, N), device=dev)
+    inv = (1.0 / (a.scale * b.scale)).contiguous()
+    nkb = (K + 63) // 64
+    split_k = max(1, min(split_k, nkb))
+    n = C.c_size_t()
+    call("npcd_tc_gemm_workspace_bytes", M, split_k, C.byref(n))
+    ws = torch.empty(max(n.value, 1), dtype=torch.uint8, device=dev)
+    if bias is not None:
+        bias = bias.detach().contiguous().float()
+    call("npcd_tc_gemm", ptr(a.data), ptr(b.data), M, N, K, ptr(out), N, ptr(bias), ptr(inv), float(slope), split_k, ptr(ws),
+         n.value, _stream())
+    _count(2 if split_k > 1 else 1)
+    return out
+
+
+class LinearTC(torch.autograd.Function):
+    """y = lrelu_slope(x W^T + b) with forward, dgrad and wgrad on the tcgen05 GEMM (`npcd_tc_gemm`); slope 1 = plain Linear.
+    Replaces the F.linear / LeakyReLU pairs of `npcd/utils/model.py:22-36` on the training path."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, slope: float):
+        y = tc_gemm(tc_pack(x), tc_pack(weight), bias, slope)
+        ctx.save_for_backward(x, weight, y)
+        ctx.slope = slope
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        slope = ctx.slope
+        mask = y if slope != 1.0 else None
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = tc_gemm(tc_pack(dy, mask=mask, slope=slope), tc_pack(weight, transpose=True))
+        if ctx.needs_input_grad[1]:
+            rows = x.shape[0]
+            tiles_m = (weight.shape[0] + 127) // 128
+            split = max(1, min((rows + 63) // 64, (2 * sm_count(x.device)) // max(tiles_m, 1)))
+            dw = tc_gemm(tc_pack(dy, transpose=True, mask=mask, slope=slope), tc_pack(x, transpose=True), split_k=split)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            g = dy if mask is None else dy * torch.where(y > 0, 1.0, slope)
+            db = g.sum(0)
+        return dx, dw, db, None
+
+
+def mlp_tc(seq, x):
+    """Runs an nn.Sequential of Linear / LeakyReLU modules (`define_mlp`) through LinearTC, fusing each activation."""
+    mods = list(seq)
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        if isinstance(m, torch.nn.Linear):
+            slope = 1.0
+            if i + 1 < len(mods) and isinstance(mods[i + 1], torch.nn.LeakyReLU):
+                slope = float(mods[i + 1].negative_slope)
+                i += 1
+            x = LinearTC.apply(x, m.weight, m.bias, slope)
+        else:
+            raise NotImplementedError(f"mlp_tc: unsupported module {type(m).__name__}")
+        i += 1
+    return x
+
+
 _SM_COUNT = {}
 
 

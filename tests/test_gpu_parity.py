@@ -448,6 +448,54 @@ def test_tc_pair_aggregate_matches_simt(syn, model, torch_cuda):
     assert err_r < 2e-5 * max(1.0, rgbs_s.abs().max().item()), err_r
 
 
+@pytest.mark.parametrize("M,N,K,split", [(300, 256, 256, 1), (1000, 3, 256, 1), (257, 95, 256, 1), (129, 256, 95, 1),
+                                         (256, 256, 5000, 16), (3, 256, 777, 8), (256, 95, 130, 3)])
+def test_tc_gemm_vs_float64(M, N, K, split, torch_cuda):
+    """npcd_tc_gemm (tcgen05, fp16 hi/lo 3-product emulation) against float64: fp32-level error for every operand shape the
+    training path produces (ragged M, narrow N, K = 95, long split-K reductions)."""
+    torch = torch_cuda
+    from npcd_b200 import ops
+
+    gen = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, generator=gen) * 0.7
+    b = torch.randn(N, K, generator=gen) * 0.05
+    bias = torch.randn(N, generator=gen)
+    got = ops.tc_gemm(ops.tc_pack(a.cuda()), ops.tc_pack(b.cuda()), bias.cuda(), slope=0.01, split_k=split).cpu()
+    want = torch.nn.functional.leaky_relu(a.double() @ b.double().t() + bias.double(), 0.01).float()
+    ref32 = torch.nn.functional.leaky_relu(a @ b.t() + bias, 0.01)
+    err, err32 = (got - want).abs().max().item(), (ref32 - want).abs().max().item()
+    print(f"tc_gemm {M}x{N}x{K} split {split}: err {err:.3e} (torch fp32 CPU: {err32:.3e})")
+    assert err < 4e-6 * max(1.0, want.abs().max().item()) * max(1.0, (K / 256) ** 0.5), err
+    # transposed packing: (A^T)^T . B^T must give the same numbers
+    got_t = ops.tc_gemm(ops.tc_pack(a.t().contiguous().cuda(), transpose=True), ops.tc_pack(b.cuda()), bias.cuda(), slope=0.01,
+                        split_k=split).cpu()
+    assert torch.equal(got, got_t)
+
+
+def test_linear_tc_gradients(torch_cuda):
+    """LinearTC (forward, dgrad, wgrad on the tcgen05 GEMM) against float64 autograd of Linear + LeakyReLU."""
+    torch = torch_cuda
+    from npcd_b200 import ops
+
+    gen = torch.Generator(device="cpu").manual_seed(11)
+    for rows, kin, nout, slope in [(777, 95, 256, 0.01), (1500, 256, 256, 0.01), (400, 256, 3, 1.0), (400, 256, 1, 1.0)]:
+        x = torch.randn(rows, kin, generator=gen)
+        w = torch.empty(nout, kin).uniform_(-0.1, 0.1, generator=gen)
+        b = torch.empty(nout).uniform_(-0.1, 0.1, generator=gen)
+        g = torch.randn(rows, nout, generator=gen) * 1e-3
+        xd, wd, bd = (t.double().requires_grad_() for t in (x, w, b))
+        yd = torch.nn.functional.leaky_relu(xd @ wd.t() + bd, slope)
+        yd.backward(g.double())
+        xc, wc, bc = (t.cuda().requires_grad_() for t in (x, w, b))
+        yc = ops.LinearTC.apply(xc, wc, bc, slope)
+        yc.backward(g.cuda())
+        for name, got, want in (("y", yc, yd), ("dx", xc.grad, xd.grad), ("dw", wc.grad, wd.grad), ("db", bc.grad, bd.grad)):
+            err = (got.detach().cpu().double() - want.detach()).abs().max().item()
+            scale = max(want.detach().abs().max().item(), 1e-12)
+            print(f"LinearTC {rows}x{kin}->{nout} {name}: rel err {err / scale:.3e}")
+            assert err < 2e-5 * scale, (name, err, scale)
+
+
 @pytest.fixture()
 def tc_model(model):
     prev = model.field.mlp_impl
