@@ -153,6 +153,23 @@ int npcd_tc_gemm_workspace_bytes(int M, int split_k, size_t* bytes);
 int npcd_tc_gemm(const void* a_image, const void* b_image, int M, int N, long long K, float* C, long long ldc, const float* bias,
                  const float* out_scale_dev, float act_slope, int split_k, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Weight gradient on the tensor cores, straight from ROW-major operand images (the same bytes the forward / dgrad kernels use as
+ * K-major operands are consumed here as MN-major operands, so no transposed copy is built):
+ *   C[m, j] (+)= *out_scale_dev * sum_{row < rows} A[row, m] * B[row, col_perm ? col_perm[j] : j],   m < a_cols, j < n_out,
+ * A image [rows, a_cols], B image [rows, b_cols <= 256]; rows of A beyond `rows` (up to the next multiple of 128) must be zero
+ * (npcd_tc_pack_rows zero-fills them).  rows_dev (optional, device int64) overrides `rows` (clamped to it).  row_splits CTAs per
+ * 128-wide M half reduce disjoint row ranges into `workspace`; the partials are summed in a fixed order (deterministic).
+ * flags: 0 (bit 0 swaps the descriptor's leading / stride offsets; descriptor probe only).
+ * npcd_tc_image_colsum: out[j] (+)= *out_scale_dev * sum_rows X[row, col_perm ? col_perm[j] : j]  (bias gradients);
+ *   workspace >= row_splits * 64 * ceil(cols / 64) floats.                                                                     */
+int npcd_tc_wgrad_workspace_bytes(int a_cols, int row_splits, size_t* bytes);
+int npcd_tc_wgrad(const void* a_image, int a_cols, const void* b_image, int b_cols, long long rows, const long long* rows_dev,
+                  float* C, long long ldc, int n_out, const int* col_perm, const float* out_scale_dev, int accumulate,
+                  int row_splits, void* workspace, size_t workspace_bytes, int flags, void* stream);
+int npcd_tc_image_colsum(const void* image, int cols, long long rows, const long long* rows_dev, float* out, int n_out,
+                         const int* col_perm, const float* out_scale_dev, int accumulate, int row_splits, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 /* ---- compositing: replaces Renderer.get_depths_from_shading_pts (renderers/renderer.py:95-110), VolumeRenderer.get_alpha
  * (renderers/volume_renderer.py:23-39), Renderer.ray_march (renderers/renderer.py:120-185).
  *   out_mask [n_sel], out_depth [n_sel] (UNCLAMPED, NaN -> +inf), out_rgb [n_sel,3]; range_scratch (8 bytes) accumulates the

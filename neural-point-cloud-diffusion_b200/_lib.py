@@ -84,6 +84,9 @@ SIGNATURES = {
     "npcd_tc_pack_rows": [P, L, I, L, I, P, F, P, P, P],
     "npcd_tc_gemm_workspace_bytes": [I, I, P],
     "npcd_tc_gemm": [P, P, I, I, L, P, L, P, P, F, I, P, C.c_size_t, P],
+    "npcd_tc_wgrad_workspace_bytes": [I, I, P],
+    "npcd_tc_wgrad": [P, I, P, I, L, P, P, L, I, P, P, I, I, P, C.c_size_t, I, P],
+    "npcd_tc_image_colsum": [P, I, L, P, P, I, P, P, I, I, P, C.c_size_t, P],
     "npcd_composite_fwd": [P, P, P, P, P, L, I, P, P, P, P, I, P],
     "npcd_clamp_depth": [P, L, P, P, P],
     "npcd_composite_bwd": [P, P, P, L, I, P, P, P, P, P, P, P, P],

@@ -157,17 +157,19 @@ __global__ void k_splitk_reduce(const float* __restrict__ partial, int splits, l
 }
 
 // Operand image of X' (image rows r', K index k'):  X'[r', k'] = src[r', k'] (transpose = 0) or src[k', r'] (transpose = 1),
-// times (mask_src > 0 ? 1 : slope) at the same source position if mask_src is given, times *scale_dev.  K padding is zero-filled.
+// times (mask_src > 0 ? 1 : slope) at the same source position if mask_src is given, times *scale_dev.  K padding and the rows up
+// to the next multiple of 128 are zero-filled.
 __global__ void k_pack_rows(const float* __restrict__ src, long long rows, int cols, long long ld, int transpose,
                             const float* __restrict__ mask_src, float slope, const float* __restrict__ scale_dev,
                             long long img_rows, long long img_k, int nkb, uint8_t* __restrict__ img) {
-  const long long n_chunks = img_rows * (nkb * 8);
+  const long long rows_pad = (img_rows + 127) & ~127ll;  // rows up to the tile boundary are zero-filled (wgrad reduces over rows)
+  const long long n_chunks = rows_pad * (nkb * 8);
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_chunks) return;
   // consecutive threads: consecutive image rows when transposed (coalesced source reads), consecutive chunks otherwise
   long long r;
   int c;
-  if (transpose) { r = i % img_rows; c = (int)(i / img_rows); }
+  if (transpose) { r = i % rows_pad; c = (int)(i / rows_pad); }
   else { r = i / (nkb * 8); c = (int)(i % (nkb * 8)); }
   const float scale = scale_dev ? __ldg(scale_dev) : 1.0f;
   float y[8];
@@ -175,7 +177,7 @@ __global__ void k_pack_rows(const float* __restrict__ src, long long rows, int c
   for (int j = 0; j < 8; ++j) {
     const long long k = (long long)c * 8 + j;
     float v = 0.f;
-    if (k < img_k) {
+    if (k < img_k && r < img_rows) {
       const long long off = transpose ? k * ld + r : r * ld + k;
       v = __ldg(src + off);
       if (mask_src) v *= (__ldg(mask_src + off) > 0.f) ? 1.0f : slope;
@@ -206,7 +208,7 @@ extern "C" int npcd_tc_pack_rows(const float* src, long long rows, int cols, lon
   NPCD_CHECK_ARG(src && image && rows > 0 && cols > 0 && ld >= cols, "bad arguments");
   const long long img_rows = transpose ? cols : rows, img_k = transpose ? rows : cols;
   const int nkb = (int)((img_k + 63) / 64);
-  const long long n_chunks = img_rows * (nkb * 8);
+  const long long n_chunks = ((img_rows + 127) & ~127ll) * (nkb * 8);
   tc::k_pack_rows<<<(unsigned)((n_chunks + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, rows, cols, ld, transpose, mask_src, slope,
                                                                                        scale_dev, img_rows, img_k, nkb,
                                                                                        (uint8_t*)image);

@@ -422,34 +422,77 @@ def tc_gemm(a: OperandImage, b: OperandImage, bias=None, slope: float = 1.0, spl
     return out
 
 
+def tc_wgrad(a: OperandImage, b: OperandImage, n_out: int = None, col_perm=None, out_scale=None, out=None, accumulate: bool = False,
+             rows_dev=None, row_splits: int = 0, flags: int = 0):
+    """C[m, j] = sum_rows A[row, m] * B[row, j]  from two ROW-major operand images (MN-major tcgen05 operands, no transposes).
+    A, B: images of [rows, a_cols] / [rows, b_cols] built by ``tc_pack`` (or stashed by the fused kernels)."""
+    assert a.rows == b.rows, (a.rows, b.rows)
+    dev = a.data.device
+    n_out = b.k if n_out is None else n_out
+    if out is None:
+        out = torch.empty((a.k, n_out), device=dev)
+    if out_scale is None:
+        out_scale = (1.0 / (a.scale * b.scale)).contiguous()
+    halves = (a.k + 127) // 128
+    if row_splits <= 0:
+        row_splits = max(1, min((a.rows + 63) // 64, sm_count(dev) // halves))
+    n = C.c_size_t()
+    call("npcd_tc_wgrad_workspace_bytes", a.k, row_splits, C.byref(n))
+    ws = torch.empty(n.value, dtype=torch.uint8, device=dev)
+    call("npcd_tc_wgrad", ptr(a.data), a.k, ptr(b.data), b.k, a.rows, ptr(rows_dev), ptr(out), out.stride(0), n_out, ptr(col_perm),
+         ptr(out_scale), int(accumulate), row_splits, ptr(ws), n.value, flags, _stream())
+    _count(2)
+    return out
+
+
+def tc_image_colsum(a: OperandImage, n_out: int = None, col_perm=None, out_scale=None, out=None, accumulate: bool = False,
+                    rows_dev=None, row_splits: int = 0):
+    """out[j] = sum_rows A[row, j] of an operand image (bias gradients), deterministic two-level sum."""
+    dev = a.data.device
+    n_out = a.k if n_out is None else n_out
+    if out is None:
+        out = torch.empty((n_out,), device=dev)
+    if out_scale is None:
+        out_scale = (1.0 / a.scale).contiguous()
+    if row_splits <= 0:
+        row_splits = max(1, min((a.rows + 255) // 256, 2 * sm_count(dev)))
+    nbytes = row_splits * 64 * ((a.k + 63) // 64) * 4
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    call("npcd_tc_image_colsum", ptr(a.data), a.k, a.rows, ptr(rows_dev), ptr(out), n_out, ptr(col_perm), ptr(out_scale),
+         int(accumulate), row_splits, ptr(ws), nbytes, _stream())
+    _count(2)
+    return out
+
+
 class LinearTC(torch.autograd.Function):
-    """y = lrelu_slope(x W^T + b) with forward, dgrad and wgrad on the tcgen05 GEMM (`npcd_tc_gemm`); slope 1 = plain Linear.
-    Replaces the F.linear / LeakyReLU pairs of `npcd/utils/model.py:22-36` on the training path."""
+    """y = lrelu_slope(x W^T + b) with forward, dgrad and wgrad on the tcgen05 GEMMs (`npcd_tc_gemm`, `npcd_tc_wgrad`); slope 1 =
+    plain Linear.  Replaces the F.linear / LeakyReLU pairs of `npcd/utils/model.py:22-36` on the training path.  The operand image
+    of x built for the forward is kept for the weight gradient, and the masked dy image serves dgrad (K-major), wgrad (MN-major)
+    and the bias gradient (column sums), so each tensor is packed once."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, slope: float):
-        y = tc_gemm(tc_pack(x), tc_pack(weight), bias, slope)
-        ctx.save_for_backward(x, weight, y)
+        xi = tc_pack(x)
+        y = tc_gemm(xi, tc_pack(weight), bias, slope)
+        ctx.save_for_backward(weight, y)
+        ctx.xi = xi
         ctx.slope = slope
         ctx.has_bias = bias is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight, y = ctx.saved_tensors
+        weight, y = ctx.saved_tensors
+        xi = ctx.xi
         slope = ctx.slope
-        mask = y if slope != 1.0 else None
+        dyi = tc_pack(dy, mask=y if slope != 1.0 else None, slope=slope)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = tc_gemm(tc_pack(dy, mask=mask, slope=slope), tc_pack(weight, transpose=True))
+            dx = tc_gemm(dyi, tc_pack(weight, transpose=True))
         if ctx.needs_input_grad[1]:
-            rows = x.shape[0]
-            tiles_m = (weight.shape[0] + 127) // 128
-            split = max(1, min((rows + 63) // 64, (2 * sm_count(x.device)) // max(tiles_m, 1)))
-            dw = tc_gemm(tc_pack(dy, transpose=True, mask=mask, slope=slope), tc_pack(x, transpose=True), split_k=split)
+            dw = tc_wgrad(dyi, xi)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            g = dy if mask is None else dy * torch.where(y > 0, 1.0, slope)
-            db = g.sum(0)
+            db = tc_image_colsum(dyi)
         return dx, dw, db, None
 
 

@@ -472,6 +472,33 @@ def test_tc_gemm_vs_float64(M, N, K, split, torch_cuda):
     assert torch.equal(got, got_t)
 
 
+@pytest.mark.parametrize("rows,m,n", [(1000, 256, 256), (64, 256, 112), (129, 3, 256), (5000, 256, 95), (300, 1, 256), (20000, 256, 256)])
+def test_tc_wgrad_vs_float64(rows, m, n, torch_cuda):
+    """npcd_tc_wgrad: C = A^T B reduced over ROWS straight from row-major operand images (MN-major tcgen05 descriptors)."""
+    torch = torch_cuda
+    from npcd_b200 import ops
+
+    gen = torch.Generator(device="cpu").manual_seed(rows + 3 * m + 7 * n)
+    a = torch.randn(rows, m, generator=gen) * 1e-3
+    b = torch.randn(rows, n, generator=gen) * 0.7
+    want = a.double().t() @ b.double()
+    scale = want.abs().max().item()
+    ia, ib = ops.tc_pack(a.cuda()), ops.tc_pack(b.cuda())
+    got = ops.tc_wgrad(ia, ib).cpu().double()
+    err = (got - want).abs().max().item()
+    ref32 = (a.t() @ b).double()
+    print(f"tc_wgrad rows {rows} {m}x{n}: rel err {err / scale:.3e} (torch fp32 CPU: {(ref32 - want).abs().max().item() / scale:.3e})")
+    assert err < 1e-5 * scale, (err, scale)
+    cs = ops.tc_image_colsum(ia).cpu().double()
+    wc = a.double().sum(0)
+    assert (cs - wc).abs().max().item() < 1e-5 * max(wc.abs().max().item(), 1e-12)
+    # deterministic: bit-identical run to run, and independent partial sums when accumulating into an existing tensor
+    again = ops.tc_wgrad(ia, ib)
+    assert torch.equal(again.cpu().double(), got)
+    acc = ops.tc_wgrad(ia, ib, out=again.clone(), accumulate=True).cpu().double()
+    assert (acc - 2 * got).abs().max().item() < 1e-6 * scale
+
+
 def test_linear_tc_gradients(torch_cuda):
     """LinearTC (forward, dgrad, wgrad on the tcgen05 GEMM) against float64 autograd of Linear + LeakyReLU."""
     torch = torch_cuda
