@@ -170,6 +170,39 @@ int npcd_tc_image_colsum(const void* image, int cols, long long rows, const long
                          const int* col_perm, const float* out_scale_dev, int accumulate, int row_splits, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* ---- fused training path of the per-(sample, neighbour) MLP (autograd of fields/aggregators/mlp.py:69-88,119-121 and the four
+ * hidden layers of `local_field`, utils/model.py:22-36; the reference gets it from torch autograd) --------------------------
+ * npcd_pair_tc_train_fwd = stage 1 of npcd_field_tc_fwd (dense packing + gather + posenc + 4 layers + weighted aggregation into
+ *   the operand image at the start of `workspace`; read it back with npcd_tc_image_to_rows) that additionally writes the STASH:
+ *   per dense pair tile the operand images of the layer inputs X_0..X_3, the LeakyReLU sign masks of the four layer outputs, and
+ *   each row's normalised weight / point index / sample index.  npcd_pair_stash_layout_for(capacity) gives the byte offsets.
+ * npcd_pair_tc_bwd: d_agg [S,256] = dL/d(aggregated feature) -> d_kp_feat [n_obj*P,32] (+= with fp32 atomics, like the
+ *   reference's index_add_) and the dP_l operand images (stash offsets dp[l]); w_t_packed[l] = npcd_tc_pack_weights of W_l^T
+ *   ([in, out] row-major; l = 0: only the 32 feature rows, zero-padded to 256 rows), inv_scale[l] (HOST) their inverse scales;
+ *   scale_dev [2] = {s, 1/s} from npcd_absmax_scale(d_agg, ..., target_exp = 6).
+ *   Then, per layer l, with rows = max_tiles * 128 and rows_dev = stash + rows_dev:
+ *     dW_l = npcd_tc_wgrad(A = stash + dp[l] (256 cols), B = stash + x[l] (l = 0: 112 cols in OUR column order), scale 1/s)
+ *     db_l = npcd_tc_image_colsum(stash + dp[l]).                                                                             */
+typedef struct {
+  long long max_tiles;
+  size_t x[4];     /* operand images of X_0 (2 K-blocks per tile) and X_1..X_3 (4 K-blocks per tile) */
+  size_t dp[4];    /* operand images of dP_0..dP_3 (4 K-blocks per tile), written by npcd_pair_tc_bwd */
+  size_t mask[4];  /* [tile][128][8] uint32 sign bits of the outputs of layers 0..3 */
+  size_t wn, idx, samp; /* [tile][128] float / int32 / int32 */
+  size_t rows_dev; /* int64: n_tiles * 128 */
+  size_t total;
+} npcd_pair_stash_layout;
+int npcd_pair_stash_layout_for(long long capacity, npcd_pair_stash_layout* out);
+int npcd_pair_tc_train_fwd(const int* nbr_idx, const float* sample_pos, const float* kp_pos, const float* kp_feat,
+                           const long long* n_samples_dev, long long capacity, const npcd_mlp_tc_weights* weights, void* workspace,
+                           size_t workspace_bytes, const npcd_pair_stash_layout* layout, void* stash, size_t stash_bytes,
+                           int* error_flag, int num_sms, void* stream);
+/* scale_out [2] = {s, 1/s}, s a power of two with s * max|x| in [2^target_exp, 2^(target_exp+1)) (s = 1 if x == 0);
+ * scratch4: 4 bytes of device scratch.                                                                                         */
+int npcd_absmax_scale(const float* x, long long n, int target_exp, void* scratch4, float* scale_out, void* stream);
+int npcd_pair_tc_bwd(const float* d_agg, const npcd_pair_stash_layout* layout, void* stash, const void* const* w_t_packed,
+                     const float* inv_scale, const float* scale_dev, float* d_kp_feat, int* error_flag, int num_sms, void* stream);
+
 /* ---- compositing: replaces Renderer.get_depths_from_shading_pts (renderers/renderer.py:95-110), VolumeRenderer.get_alpha
  * (renderers/volume_renderer.py:23-39), Renderer.ray_march (renderers/renderer.py:120-185).
  *   out_mask [n_sel], out_depth [n_sel] (UNCLAMPED, NaN -> +inf), out_rgb [n_sel,3]; range_scratch (8 bytes) accumulates the

@@ -63,6 +63,13 @@ class TcWeights(C.Structure):
     ]
 
 
+class PairStashLayout(C.Structure):
+    """mirror of ``npcd_pair_stash_layout``"""
+
+    _fields_ = [("max_tiles", C.c_longlong), ("x", C.c_size_t * 4), ("dp", C.c_size_t * 4), ("mask", C.c_size_t * 4),
+                ("wn", C.c_size_t), ("idx", C.c_size_t), ("samp", C.c_size_t), ("rows_dev", C.c_size_t), ("total", C.c_size_t)]
+
+
 # name -> argtypes; every entry point declared in include/npcd_b200.h (tests check the header against this table)
 SIGNATURES = {
     "npcd_rays_generate": [P, P, I, I, P, I, F, P, P, P, P, P, P, P],
@@ -87,6 +94,10 @@ SIGNATURES = {
     "npcd_tc_wgrad_workspace_bytes": [I, I, P],
     "npcd_tc_wgrad": [P, I, P, I, L, P, P, L, I, P, P, I, I, P, C.c_size_t, I, P],
     "npcd_tc_image_colsum": [P, I, L, P, P, I, P, P, I, I, P, C.c_size_t, P],
+    "npcd_pair_stash_layout_for": [L, P],
+    "npcd_pair_tc_train_fwd": [P, P, P, P, P, L, P, P, C.c_size_t, P, P, C.c_size_t, P, I, P],
+    "npcd_absmax_scale": [P, L, I, P, P, P],
+    "npcd_pair_tc_bwd": [P, P, P, P, P, P, P, P, I, P],
     "npcd_composite_fwd": [P, P, P, P, P, L, I, P, P, P, P, I, P],
     "npcd_clamp_depth": [P, L, P, P, P],
     "npcd_composite_bwd": [P, P, P, L, I, P, P, P, P, P, P, P, P],

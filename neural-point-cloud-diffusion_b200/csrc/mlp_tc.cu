@@ -43,7 +43,7 @@ constexpr int kPackRows = 121;                // pair offsets per dense tile
 constexpr int kImgTileBytes = 4 * 2 * kTileBytesA;  // one 128-sample tile of the pre-split [S,256] operand image (128 KB)
 
 enum Epi { EPI_ACT = 0, EPI_LINEAR = 1, EPI_AGG = 2, EPI_DOT1 = 3, EPI_DOT3 = 4, EPI_DUMP = 5 };
-enum Mode { MODE_PAIR = 0, MODE_HEADS = 1, MODE_PROBE = 2 };
+enum Mode { MODE_PAIR = 0, MODE_HEADS = 1, MODE_PROBE = 2, MODE_PAIR_TRAIN = 3 };
 
 // misc shared-memory layout (byte offsets)
 constexpr int kOffBars = 0;       // 24 mbarriers
@@ -54,9 +54,11 @@ constexpr int kOffRowSamp = 1280; // u8[2][128] row -> sample-in-tile           
 constexpr int kOffSampRow = 1536; // u8[2][128] sample-in-tile -> first row                (pair)
 constexpr int kOffSampCnt = 1792; // u8[2][128] sample-in-tile -> rows                     (pair)
 constexpr int kOffPart = 256;     // float[128][4] cross-half partial dot products         (heads; aliases the pair arrays)
+constexpr int kOffStashBars = 2048;  // 4 mbarriers: K-block kb of the A operand has been copied to the training stash
 
 // barrier indices
 constexpr int kBarWFull = 0, kBarWEmpty = 3, kBarARdy = 6, kBarA0Rdy = 10, kBarAFree = 14, kBarAccRdy = 18, kBarAccFree = 20;
+constexpr int kBarStash = kOffStashBars / 8;
 
 struct Layer {
   const uint8_t* w;  // packed tiles: for each K-block: hi tile (32 KB) then lo tile (32 KB)
@@ -89,13 +91,20 @@ struct Params {
   const long long* n_samples_dev;
   long long capacity;
   int* error_flag;
+  // training stash (MODE_PAIR_TRAIN): everything the fused backward (pair_bwd_tc.cu) and the weight-gradient GEMMs need
+  uint8_t* stash_x[4];      // operand images of the layer inputs X_0 (112 columns, 2 K-blocks) and X_1..X_3 (4 K-blocks), per tile
+  uint32_t* stash_mask[4];  // [tile][128 rows][8] sign bits (y > 0) of the outputs of layers 0..3 (LeakyReLU derivative)
+  float* stash_wn;          // [tile][128] normalised inverse-distance weight of every row
+  int* stash_idx;           // [tile][128] global point index of every row (-1 = padding)
+  int* stash_samp;          // [tile][128] sample index of every row (-1 = padding)
 };
 
 // One chunk (32 accumulator columns starting at c0) of an ACT / LINEAR epilogue: y = [lrelu](acc * inv + b) -> fp16 hi/lo ->
 // K-block (c0 >> 6) of the A operand, 16-byte chunks (c0 & 63) / 8 .. +3.
 // slope = 0.01 (LeakyReLU) or 1 (linear layer: max(y, y) = y).
 __device__ __forceinline__ void epi_chunk_store(const Params& P, int l, float inv, float slope, const uint32_t (&v)[32], int c0,
-                                                uint8_t* sA, uint32_t rowbase, int x7, float* feat_row) {
+                                                uint8_t* sA, uint32_t rowbase, int x7, float* feat_row, uint32_t* mask_out = nullptr) {
+  uint32_t mbits = 0u;
   uint8_t* kb_base = sA + (c0 >> 6) * (2 * kTileBytesA) + rowbase;
   const int c16_0 = (c0 & 63) >> 3;
   const uint64_t inv2 = pack2(inv, inv), slope2 = pack2(slope, slope);
@@ -112,17 +121,24 @@ __device__ __forceinline__ void epi_chunk_store(const Params& P, int l, float in
       *reinterpret_cast<float4*>(feat_row + c0 + g * 8) = make_float4(y[0], y[1], y[2], y[3]);
       *reinterpret_cast<float4*>(feat_row + c0 + g * 8 + 4) = make_float4(y[4], y[5], y[6], y[7]);
     }
+    if (mask_out) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mbits |= (y[j] > 0.f ? 1u : 0u) << (g * 8 + j);
+    }
     uint4 hi, lo;
     split8(y, hi, lo);
     uint8_t* p = kb_base + (((c16_0 + g) ^ x7) << 4);
     *reinterpret_cast<uint4*>(p) = hi;
     *reinterpret_cast<uint4*>(p + kTileBytesA) = lo;
   }
+  if (mask_out) *mask_out = mbits;
 }
 
 // ------------------------------------------------------------------------------------------------------------- kernel ----
 template <int kMode>
 __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constant__ Params P) {
+  constexpr bool kPair = kMode == MODE_PAIR || kMode == MODE_PAIR_TRAIN;
+  constexpr bool kTrain = kMode == MODE_PAIR_TRAIN;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sW = smem + kSmemA;
@@ -140,6 +156,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
     for (int i = 0; i < kStages; ++i) { mbar_init(bar(kBarWFull + i), 1); mbar_init(bar(kBarWEmpty + i), 1); }
     for (int i = 0; i < 4; ++i) { mbar_init(bar(kBarARdy + i), 8); mbar_init(bar(kBarA0Rdy + i), 1); mbar_init(bar(kBarAFree + i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar(kBarAccRdy + i), 1); mbar_init(bar(kBarAccFree + i), 8); }
+    for (int i = 0; i < 4; ++i) mbar_init(bar(kBarStash + i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
@@ -149,7 +166,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   const long long S = min(*P.n_samples_dev, P.capacity);
-  const int n_tiles = (kMode == MODE_PAIR) ? *P.n_tiles_dev : (int)((S + 127) / 128);
+  const int n_tiles = kPair ? *P.n_tiles_dev : (int)((S + 127) / 128);
   const int n_layers = P.n_layers;
 
   if (warp == 0) {
@@ -194,7 +211,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
         // heads layer 2 (channel_net.0) reads the same operand (feat) as layer 1 (shape_net.0): nothing new to wait for
         const bool fresh_a = !(kMode == MODE_HEADS && l == 2);
         for (int kb = 0; kb < nkb; ++kb) {
-          if (kMode != MODE_PAIR && l == 0) {
+          if (!kPair && l == 0) {
             mbar_wait(bar(kBarA0Rdy + kb), (ph_a0 >> kb) & 1u);
             ph_a0 ^= 1u << kb;
           } else if (fresh_a) {
@@ -238,7 +255,40 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
     }
   } else if (warp == 10) {
     // ======================================== heads / probe: first-operand loader =======================================
-    if (kMode != MODE_PAIR) {
+    if (kTrain) {
+      // ---- training stash: every published K-block of the A operand (X_0 from the prologue, X_1..X_3 from the epilogues of
+      //      layers 0..2) is bulk-copied to HBM as-is (it already IS the operand image the backward GEMMs consume); the epilogue
+      //      threads wait on kBarStash + kb before they overwrite that K-block.  Same event order as the epilogue code below.
+      uint32_t ph_ar = 0;
+      auto stash_block = [&](int kb, uint8_t* dst) {
+        mbar_wait(bar(kBarARdy + kb), (ph_ar >> kb) & 1u);
+        ph_ar ^= 1u << kb;
+        if (elect_one()) {
+          bulk_s2g(dst, smem_u32(sA + kb * 2 * kTileBytesA), 2 * kTileBytesA);
+          bulk_commit();
+          bulk_wait_read0();
+          mbar_arrive(bar(kBarStash + kb));
+        }
+        __syncwarp();
+      };
+      int cur = -1;
+      for (int it = -1;; ++it) {
+        const bool prime = it < 0;
+        const int target = prime ? (int)blockIdx.x : cur + (int)gridDim.x;
+        const bool has_target = target < n_tiles;
+        if (prime && !has_target) break;
+        if (!prime) {
+          for (int l = 0; l < 3; ++l)
+            for (int kb = 0; kb < 4; ++kb) stash_block(kb, P.stash_x[l + 1] + ((size_t)cur * 4 + kb) * (2 * kTileBytesA));
+        }
+        if (has_target)
+          for (int kb = 0; kb < 2; ++kb) stash_block(kb, P.stash_x[0] + ((size_t)target * 2 + kb) * (2 * kTileBytesA));
+        if (!has_target) break;
+        cur = target;
+      }
+      if (elect_one()) bulk_wait_all0();  // the copies must have landed before the CTA retires its shared memory
+      __syncwarp();
+    } else if (!kPair) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         for (int kb = 0; kb < 4; ++kb) {
@@ -288,6 +338,17 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
       if (lane == 0) mbar_arrive(bar(kBarAccFree + ab));
     };
 
+    // training: K-block kb may only be overwritten once the stash warp has copied its previous contents out
+    uint32_t sd_pending = 0, ph_sd = 0;
+    int tile_now = 0;  // tile the layer epilogues currently work on (stash addressing)
+    auto stash_wait = [&](int kb) {
+      if (kTrain && ((sd_pending >> kb) & 1u)) {
+        mbar_wait(bar(kBarStash + kb), (ph_sd >> kb) & 1u);
+        ph_sd ^= 1u << kb;
+        sd_pending &= ~(1u << kb);
+      }
+    };
+
     // ACT / LINEAR epilogue of layer l: four 32-column chunks (2 i + half), software-pipelined TMEM loads
     auto epilogue_store = [&](int l, float slope, float* feat_row) {
       const uint32_t ab = lc & 1u;
@@ -300,15 +361,18 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         if (i < 3) tmem_ld32_async(t_acc + (2 * (i + 1) + half) * 32, v[(i + 1) & 1]);
-        epi_chunk_store(P, l, inv, slope, v[i & 1], (2 * i + half) * 32, sA, rowbase, x7, feat_row);
+        stash_wait(i);
+        epi_chunk_store(P, l, inv, slope, v[i & 1], (2 * i + half) * 32, sA, rowbase, x7, feat_row,
+                        kTrain ? P.stash_mask[l] + ((size_t)tile_now * 128 + row) * 8 + (2 * i + half) : nullptr);
         if (i == 3) release_acc(ab);
         publish(kBarARdy + i);
+        if (kTrain) sd_pending |= 1u << i;
         if (i < 3) tmem_wait(v[(i + 1) & 1]);
       }
       ++lc;
     };
 
-    if (kMode == MODE_PAIR) {
+    if (kPair) {
       // ------------------------------------------------------------------------------------------------- pair mode ----
       // layer-0 input, 112 columns: [feat 0..31 | x: d, sin*10, cos*10, 0,0,0 | y: ... | z: ... | 8 zeros]
       // (the column order is OURS; the first-layer weights are permuted to match when they are packed).
@@ -345,6 +409,10 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
           idx = __ldg(P.nbr_idx + s * kK + (row - samp_row[sl]));
           x = __ldg(P.sample_pos + s);
           px = __ldg(P.kp_pos + (size_t)idx * 3); py = __ldg(P.kp_pos + (size_t)idx * 3 + 1); pz = __ldg(P.kp_pos + (size_t)idx * 3 + 2);
+        }
+        if (kTrain && half == 0) {
+          P.stash_idx[(size_t)tile * 128 + row] = idx;
+          P.stash_samp[(size_t)tile * 128 + row] = row < n_rows ? s_begin + (int)row_samp[row] : -1;
         }
         const float d3[3] = {x.x - px, x.y - py, x.z - pz};
         auto enc_group = [&](int c, int first_chunk) {  // 24 columns -> pre chunks first_chunk .. first_chunk + 2
@@ -392,6 +460,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
       };
       // store the K-block-kb part of the staged layer-0 input and publish that K-block
       auto prologue_store = [&](int kb) {
+        stash_wait(kb);
         if (kb == 0) {
           if (half == 0) {
 #pragma unroll
@@ -414,6 +483,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
           }
         }
         publish(kBarARdy + kb);
+        if (kTrain) sd_pending |= 1u << kb;
       };
 
       // Iteration -1 primes the pipeline (stages the first tile's input); iteration `it` runs the four layer epilogues of tile
@@ -437,7 +507,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
             prologue_store(kb);
           }
         }
-        if (prime) { cur = target; continue; }
+        if (prime) { cur = target; tile_now = cur; continue; }
         // ---- layer 3: bias + LeakyReLU, normalised inverse-distance weight, segmented sum over each sample's rows
         //      (fields/aggregators/mlp.py:86-88,119-121), staged as fp32 in K-blocks 2..3 (free once layer 3's MMAs are done),
         //      two passes of 128 columns; the sums leave as the pre-split operand image the heads kernel bulk-copies.
@@ -460,6 +530,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
             for (int j = 0; j < cnt; ++j) wsum += wts[r0 + j];
             wn = wts[row] / wsum;
           }
+          if (kTrain && half == 0) P.stash_wn[(size_t)cur * 128 + row] = wn;
+          stash_wait(2);  // the fp32 staging below overwrites K-blocks 2..3 (X_3)
+          stash_wait(3);
           // staging: [128 rows][128 cols] fp32 in K-blocks 2..3.  16-byte chunk c4 of a row sits at position
           // ((c4 >> 1) | ((c4 & 1) << 4)) ^ (row & 7): conflict-free for the row-per-lane stores AND for the sum phase, where
           // 16 lanes read chunks 2 c8 and 2 c8 + 1 of one row.
@@ -474,12 +547,15 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
               uint32_t v[32];
               tmem_ld32_async(t_acc + c0, v);
               tmem_wait(v);
+              uint32_t mbits = 0u;
 #pragma unroll
               for (int g = 0; g < 8; ++g) {
                 const float4 b = *reinterpret_cast<const float4*>(&P.bias[3][c0 + g * 4]);
                 float y0, y1, y2, y3;
                 act2(v[g * 4 + 0], v[g * 4 + 1], inv2, b.x, b.y, slope2, y0, y1);
                 act2(v[g * 4 + 2], v[g * 4 + 3], inv2, b.z, b.w, slope2, y2, y3);
+                if (kTrain)
+                  mbits |= ((y0 > 0.f ? 1u : 0u) | (y1 > 0.f ? 2u : 0u) | (y2 > 0.f ? 4u : 0u) | (y3 > 0.f ? 8u : 0u)) << (g * 4);
                 float4 o;
                 unpack2(mul2(pack2(y0, y1), wn2), o.x, o.y);
                 unpack2(mul2(pack2(y2, y3), wn2), o.z, o.w);
@@ -487,6 +563,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
                 const int pos = ((c4 >> 1) | ((c4 & 1) << 4)) ^ x7;
                 *reinterpret_cast<float4*>(stage + row * 128 + (pos << 2)) = o;
               }
+              if (kTrain) P.stash_mask[3][((size_t)cur * 128 + row) * 8 + (c0 >> 5)] = mbits;
             }
             if (pass == 1) release_acc(ab);
             epi_bar_sync();
@@ -517,6 +594,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
         }
         if (!has_target) break;
         cur = target;
+        tile_now = cur;
       }
     } else {
       // ------------------------------------------------------------------------------------------- heads / probe mode ----
@@ -693,10 +771,10 @@ __global__ void k_zero_int(int* p) { p[0] = 0; }
 // tile t = samples whose first pair offset lies in [121 t, 121 t + 121): every sample has 1..8 pairs, so consecutive samples
 // cross at most one tile boundary and every tile is non-empty.
 __global__ void k_tile_starts(const int* __restrict__ pair_off, const long long* __restrict__ n_samples_dev, long long capacity,
-                              int* __restrict__ tile_start, int* __restrict__ n_tiles_dev) {
+                              int* __restrict__ tile_start, int* __restrict__ n_tiles_dev, long long* __restrict__ rows_dev) {
   const long long S = min(*n_samples_dev, capacity);
   const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s == 0 && S == 0) { *n_tiles_dev = 0; tile_start[0] = 0; }
+  if (s == 0 && S == 0) { *n_tiles_dev = 0; tile_start[0] = 0; if (rows_dev) *rows_dev = 0; }
   if (s >= S) return;
   const int t = pair_off[s] / kPackRows;
   const int tp = s > 0 ? pair_off[s - 1] / kPackRows : -1;
@@ -704,6 +782,7 @@ __global__ void k_tile_starts(const int* __restrict__ pair_off, const long long*
   if (s == S - 1) {
     tile_start[t + 1] = (int)S;
     *n_tiles_dev = t + 1;
+    if (rows_dev) *rows_dev = (long long)(t + 1) * 128;  // training stash: rows of the per-tile operand images
   }
 }
 
@@ -786,6 +865,50 @@ int launch_tc(const tc::Params& P, long long tiles, int num_sms, cudaStream_t st
 }
 }  // namespace
 
+namespace {
+// dense packing (pair_off = exclusive scan of the neighbour counts, first sample of every 121-offset tile) + the pair kernel
+template <int kMode>
+int pair_stage(const int* nbr_idx, const float* sample_pos, const float* kp_pos, const float* kp_feat, const long long* n_samples_dev,
+               long long capacity, const npcd_mlp_tc_weights* W, const TcWorkspace& ws, uint8_t* base,
+               const npcd_pair_stash_layout* layout, uint8_t* stash, int* error_flag, int num_sms, cudaStream_t st) {
+  uint8_t* img = base + ws.img_off;
+  int* pair_off = (int*)(base + ws.pair_off);
+  int* tile_start = (int*)(base + ws.tile_off);
+  int* n_tiles_dev = (int*)(base + ws.ntiles_off);
+  tc::k_zero_int<<<1, 1, 0, st>>>(pair_off);
+  tc::NbrCount op{nbr_idx, n_samples_dev};
+  cub::CountingInputIterator<long long> cnt(0);
+  cub::TransformInputIterator<int, tc::NbrCount, cub::CountingInputIterator<long long>> it(cnt, op);
+  size_t tmp = ws.cub_bytes;
+  cudaError_t e = cub::DeviceScan::InclusiveSum(base + ws.cub_off, tmp, it, pair_off + 1, capacity, st);
+  if (e != cudaSuccess) {
+    set_error("npcd_field_tc_fwd: scan: %s", cudaGetErrorString(e));
+    return 2;
+  }
+  tc::k_tile_starts<<<(unsigned)((capacity + 255) / 256), 256, 0, st>>>(pair_off, n_samples_dev, capacity, tile_start, n_tiles_dev,
+                                                                      stash ? (long long*)(stash + layout->rows_dev) : nullptr);
+  int rc = check_launch("npcd_field_tc_fwd(pack)");
+  if (rc) return rc;
+  static thread_local tc::Params P;  // ~11 KB: keep it off the stack
+  memset(&P, 0, sizeof(P));
+  for (int i = 0; i < 4; ++i) fill_layer(P, i, W->pair[i], i < 3 ? tc::EPI_ACT : tc::EPI_AGG);
+  P.n_layers = 4;
+  P.nbr_idx = nbr_idx; P.sample_pos = (const float4*)sample_pos; P.kp_pos = kp_pos; P.kp_feat = kp_feat;
+  P.pair_off = pair_off; P.tile_start = tile_start; P.n_tiles_dev = n_tiles_dev; P.img = img;
+  P.n_samples_dev = n_samples_dev; P.capacity = capacity; P.error_flag = error_flag;
+  if (stash) {
+    for (int l = 0; l < 4; ++l) {
+      P.stash_x[l] = stash + layout->x[l];
+      P.stash_mask[l] = (uint32_t*)(stash + layout->mask[l]);
+    }
+    P.stash_wn = (float*)(stash + layout->wn);
+    P.stash_idx = (int*)(stash + layout->idx);
+    P.stash_samp = (int*)(stash + layout->samp);
+  }
+  return launch_tc<kMode>(P, ws.max_tiles, num_sms, st, "npcd_field_tc_fwd(pair)");
+}
+}  // namespace
+
 extern "C" int npcd_field_tc_workspace_bytes(long long capacity, size_t* bytes) {
   NPCD_CHECK_ARG(bytes && capacity >= 0 && capacity < (1ll << 27), "bad arguments (capacity must be < 2^27 samples per launch)");
   TcWorkspace w;
@@ -815,28 +938,8 @@ extern "C" int npcd_field_tc_fwd(const int* nbr_idx, const float* sample_pos, co
   int* tile_start = (int*)(base + ws.tile_off);
   int* n_tiles_dev = (int*)(base + ws.ntiles_off);
   if (stages & 1) {
-    // dense packing: pair_off = exclusive scan of the neighbour counts, then the first sample of every 121-offset tile
-    tc::k_zero_int<<<1, 1, 0, st>>>(pair_off);
-    tc::NbrCount op{nbr_idx, n_samples_dev};
-    cub::CountingInputIterator<long long> cnt(0);
-    cub::TransformInputIterator<int, tc::NbrCount, cub::CountingInputIterator<long long>> it(cnt, op);
-    size_t tmp = ws.cub_bytes;
-    cudaError_t e = cub::DeviceScan::InclusiveSum(base + ws.cub_off, tmp, it, pair_off + 1, capacity, st);
-    if (e != cudaSuccess) {
-      set_error("npcd_field_tc_fwd: scan: %s", cudaGetErrorString(e));
-      return 2;
-    }
-    tc::k_tile_starts<<<(unsigned)((capacity + 255) / 256), 256, 0, st>>>(pair_off, n_samples_dev, capacity, tile_start, n_tiles_dev);
-    rc = check_launch("npcd_field_tc_fwd(pack)");
-    if (rc) return rc;
-    static thread_local tc::Params P;  // ~11 KB: keep it off the stack
-    memset(&P, 0, sizeof(P));
-    for (int i = 0; i < 4; ++i) fill_layer(P, i, W->pair[i], i < 3 ? tc::EPI_ACT : tc::EPI_AGG);
-    P.n_layers = 4;
-    P.nbr_idx = nbr_idx; P.sample_pos = (const float4*)sample_pos; P.kp_pos = kp_pos; P.kp_feat = kp_feat;
-    P.pair_off = pair_off; P.tile_start = tile_start; P.n_tiles_dev = n_tiles_dev; P.img = img;
-    P.n_samples_dev = n_samples_dev; P.capacity = capacity; P.error_flag = error_flag;
-    rc = launch_tc<tc::MODE_PAIR>(P, ws.max_tiles, num_sms, st, "npcd_field_tc_fwd(pair)");
+    rc = pair_stage<tc::MODE_PAIR>(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, W, ws, base, nullptr, nullptr,
+                                   error_flag, num_sms, st);
     if (rc) return rc;
   }
   if (stages & 2) {
@@ -872,4 +975,43 @@ extern "C" int npcd_tc_linear_probe(const void* image, const long long* n_rows_d
   P.feat_out = out;
   P.n_samples_dev = n_rows_dev; P.capacity = capacity; P.error_flag = error_flag;
   return launch_tc<tc::MODE_PROBE>(P, (capacity + 127) / 128, num_sms, (cudaStream_t)stream, "npcd_tc_linear_probe");
+}
+
+// ---- training forward of the pair stage: same kernel, plus the stash the fused backward needs ------------------------------
+extern "C" int npcd_pair_stash_layout_for(long long capacity, npcd_pair_stash_layout* out) {
+  NPCD_CHECK_ARG(out && capacity >= 0 && capacity < (1ll << 27), "bad arguments");
+  TcWorkspace ws;
+  int rc = tc_workspace_layout(capacity, &ws);
+  if (rc) return rc;
+  const size_t tiles = (size_t)ws.max_tiles;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align256(off + bytes); return o; };
+  out->max_tiles = ws.max_tiles;
+  out->x[0] = take(tiles * 2 * (2 * tc::kTileBytesA));
+  for (int l = 1; l < 4; ++l) out->x[l] = take(tiles * 4 * (2 * tc::kTileBytesA));
+  for (int l = 0; l < 4; ++l) out->dp[l] = take(tiles * 4 * (2 * tc::kTileBytesA));
+  for (int l = 0; l < 4; ++l) out->mask[l] = take(tiles * 128 * 8 * sizeof(uint32_t));
+  out->wn = take(tiles * 128 * sizeof(float));
+  out->idx = take(tiles * 128 * sizeof(int));
+  out->samp = take(tiles * 128 * sizeof(int));
+  out->rows_dev = take(256);
+  out->total = off;
+  return 0;
+}
+
+extern "C" int npcd_pair_tc_train_fwd(const int* nbr_idx, const float* sample_pos, const float* kp_pos, const float* kp_feat,
+                                      const long long* n_samples_dev, long long capacity, const npcd_mlp_tc_weights* W,
+                                      void* workspace, size_t workspace_bytes, const npcd_pair_stash_layout* layout, void* stash,
+                                      size_t stash_bytes, int* error_flag, int num_sms, void* stream) {
+  NPCD_CHECK_ARG(n_samples_dev && W && layout && stash, "null pointer");
+  NPCD_CHECK_ARG(capacity > 0 && capacity < (1ll << 27), "bad capacity (0 < capacity < 2^27 samples per launch)");
+  NPCD_CHECK_ARG(nbr_idx && sample_pos && kp_pos && kp_feat && workspace, "null pointer");
+  NPCD_CHECK_ARG(W->feat_dim == 32, "the tensor-core field kernel is specialised for feat_dim = 32 (configs/npcd_srncars.yaml:6)");
+  TcWorkspace ws;
+  int rc = tc_workspace_layout(capacity, &ws);
+  if (rc) return rc;
+  NPCD_CHECK_ARG(workspace_bytes >= ws.total, "workspace too small (npcd_field_tc_workspace_bytes)");
+  NPCD_CHECK_ARG(layout->max_tiles == ws.max_tiles && stash_bytes >= layout->total, "stash layout does not match the capacity");
+  return pair_stage<tc::MODE_PAIR_TRAIN>(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, W, ws, (uint8_t*)workspace,
+                                         layout, (uint8_t*)stash, error_flag, num_sms, (cudaStream_t)stream);
 }

@@ -260,6 +260,9 @@ class PackedTcWeights:
                           + [sn[1].weight.detach().float().reshape(-1), sn[1].bias.detach().float().reshape(-1),
                              cn[4].weight.detach().float().reshape(-1), cn[4].bias.detach().float().reshape(-1)]).cpu().numpy()
         maxabs, off = small[:10], 10
+        self.maxabs = maxabs
+        self.pair_linears = lf[:4]
+        self._dgrad = None
 
         def host(n):
             nonlocal off
@@ -291,6 +294,24 @@ class PackedTcWeights:
         s.chan_out_w, s.chan_out_b = host(3 * HIDDEN), host(3)
         self.struct = s
         self.error_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def dgrad_pack(self):
+        """W_l^T of the four pair layers packed as B operands of the fused backward (`npcd_pair_tc_bwd`): [in, out] row-major;
+        layer 0 keeps only its 32 feature rows (the other input columns have no gradient consumer), zero-padded to 256 rows."""
+        if self._dgrad is None:
+            dev = self.error_flag.device
+            ptrs, invs, keep = (C.c_void_p * 4)(), (C.c_float * 4)(), []
+            for l, lin in enumerate(self.pair_linears):
+                w = lin.weight.detach().float()
+                wt = w.t().contiguous() if l > 0 else torch.cat([w[:, :32].t(), w.new_zeros(HIDDEN - 32, HIDDEN)]).contiguous()
+                scale = 2.0 ** math.floor(math.log2(4.0 / float(self.maxabs[l]))) if self.maxabs[l] > 0 else 1.0
+                out = torch.zeros(4 * 2 * 32768, dtype=torch.uint8, device=dev)
+                call("npcd_tc_pack_weights", ptr(wt), HIDDEN, None, HIDDEN, float(scale), ptr(out), _stream())
+                _count(1)
+                keep += [wt, out]
+                ptrs[l], invs[l] = out.data_ptr(), 1.0 / scale
+            self._dgrad = (ptrs, invs, keep)
+        return self._dgrad
 
 
 def tc_workspace_bytes(capacity: int) -> int:
@@ -462,6 +483,121 @@ def tc_image_colsum(a: OperandImage, n_out: int = None, col_perm=None, out_scale
          int(accumulate), row_splits, ptr(ws), nbytes, _stream())
     _count(2)
     return out
+
+
+# ---- fused training path of the pair MLP ----------------------------------------------------------------------------------
+_PAIR_COL_OF_REF = None
+
+
+def pair_ref_col_map(dev):
+    """int32 [95]: position, in OUR 112-column first-layer input order, of every reference input column (wgrad un-permutation)."""
+    global _PAIR_COL_OF_REF
+    if _PAIR_COL_OF_REF is None or _PAIR_COL_OF_REF.device != dev:
+        perm = pair_input_perm()
+        inv = [0] * 95
+        for k, src in enumerate(perm):
+            if src >= 0:
+                inv[src] = k
+        _PAIR_COL_OF_REF = torch.tensor(inv, dtype=torch.int32, device=dev)
+    return _PAIR_COL_OF_REF
+
+
+@dataclass
+class PairStash:
+    layout: "_lib.PairStashLayout"
+    buf: torch.Tensor
+
+    def image(self, off: int, n_kblocks: int, cols: int, scale) -> OperandImage:
+        nbytes = self.layout.max_tiles * n_kblocks * 32768
+        return OperandImage(self.buf[off:off + nbytes], scale, self.layout.max_tiles * 128, cols)
+
+    @property
+    def rows_dev(self):
+        return self.buf[self.layout.rows_dev:self.layout.rows_dev + 8]
+
+
+def pair_tc_train_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity: int, weights: "PackedTcWeights"):
+    """Training forward of the pair stage: agg [capacity,256] = sum_j w_j lrelu(local_field[0..6](pair features)) and the stash
+    for `pair_tc_bwd`."""
+    dev = sample_pos.device
+    lay = _lib.PairStashLayout()
+    call("npcd_pair_stash_layout_for", int(capacity), C.byref(lay))
+    stash = PairStash(lay, torch.empty(lay.total, dtype=torch.uint8, device=dev))
+    nbytes = tc_workspace_bytes(capacity)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    kp_pos = kp_pos.detach().contiguous().float()
+    kp_feat = kp_feat.detach().contiguous().float()
+    _timed("pair_mlp_train", lambda: call(
+        "npcd_pair_tc_train_fwd", ptr(nbr_idx), ptr(sample_pos), ptr(kp_pos), ptr(kp_feat), ptr(n_samples_dev), capacity,
+        C.byref(weights.struct), ptr(ws), nbytes, C.byref(lay), ptr(stash.buf), lay.total, ptr(weights.error_flag), sm_count(dev),
+        _stream()))
+    agg = torch.empty((capacity, HIDDEN), device=dev)
+    call("npcd_tc_image_to_rows", ptr(ws), capacity, ptr(agg), _stream())
+    _count(6)
+    return agg, stash
+
+
+def absmax_scale(x, target_exp: int = 6):
+    """[2] device tensor {s, 1/s}: power of two with s * max|x| in [2^target_exp, 2^(target_exp+1))."""
+    x = x.contiguous()
+    out = torch.empty(3, device=x.device)
+    call("npcd_absmax_scale", ptr(x), x.numel(), target_exp, out[2:].data_ptr(), ptr(out), _stream())
+    _count(2)
+    return out
+
+
+def pair_tc_bwd(d_agg, stash: PairStash, weights: "PackedTcWeights", n_points_total: int):
+    """-> d_kp_feat [n_points_total,32], [dW_0 [256,95], dW_1..3 [256,256]], [db_0..3 [256]]."""
+    dev = d_agg.device
+    d_agg = d_agg.contiguous().float()
+    scale = absmax_scale(d_agg)
+    d_feat = torch.zeros((n_points_total, 32), device=dev)
+    ptrs, invs, _ = weights.dgrad_pack()
+    lay = stash.layout
+    _timed("pair_mlp_bwd", lambda: call("npcd_pair_tc_bwd", ptr(d_agg), C.byref(lay), ptr(stash.buf), ptrs, invs, ptr(scale),
+                                        ptr(d_feat), ptr(weights.error_flag), sm_count(dev), _stream()))
+    _count(1)
+    inv_s = scale[1:2]
+    rows_dev = stash.rows_dev
+    splits = max(1, sm_count(dev) // 2)
+    dws, dbs = [], []
+
+    def grads():
+        for l in range(4):
+            dp = stash.image(lay.dp[l], 4, HIDDEN, None)
+            x = stash.image(lay.x[l], 2 if l == 0 else 4, 112 if l == 0 else HIDDEN, None)
+            dws.append(tc_wgrad(dp, x, n_out=95 if l == 0 else HIDDEN, col_perm=pair_ref_col_map(dev) if l == 0 else None,
+                                out_scale=inv_s, rows_dev=rows_dev, row_splits=splits))
+            dbs.append(tc_image_colsum(dp, out_scale=inv_s, rows_dev=rows_dev))
+
+    _timed("pair_mlp_wgrad", grads)
+    return d_feat, dws, dbs
+
+
+class PairFieldFn(torch.autograd.Function):
+    """agg = sum_j w_j lrelu(Lin3(lrelu(Lin2(lrelu(Lin1(lrelu(Lin0([feat | x_rel | enc])))))))) per shading sample: gather,
+    positional encoding, the four hidden layers of `local_field` and the weighted aggregation
+    (`aggregators/mlp.py:69-88,119-121`) with forward AND backward in fused tcgen05 kernels."""
+
+    @staticmethod
+    def forward(ctx, kp_feat, w0, b0, w1, b1, w2, b2, w3, b3, nbr_idx, sample_pos, kp_pos, n_samples_dev, packed):
+        capacity = nbr_idx.shape[0]
+        agg, stash = pair_tc_train_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, packed)
+        ctx.stash, ctx.packed, ctx.feat_shape = stash, packed, kp_feat.shape
+        return agg
+
+    @staticmethod
+    def backward(ctx, d_agg):
+        shape = ctx.feat_shape
+        n_pts = 1
+        for d in shape[:-1]:
+            n_pts *= d
+        d_feat, dws, dbs = pair_tc_bwd(d_agg, ctx.stash, ctx.packed, n_pts)
+        ctx.stash = None
+        out = [d_feat.view(shape) if ctx.needs_input_grad[0] else None]
+        for l in range(4):
+            out += [dws[l], dbs[l]]
+        return tuple(out) + (None, None, None, None, None)
 
 
 class LinearTC(torch.autograd.Function):

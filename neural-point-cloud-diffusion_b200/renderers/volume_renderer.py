@@ -135,7 +135,7 @@ class VolumeRenderer(nn.Module):
             S = int(ray_offset[-1].item())
             nbr, pos, _ = ops.knn_fill(rays, grid, T, radius, valid_bits, ray_offset, S, ray_ids, jitter)
             if needs_grad:
-                rgbs = self.field.evaluate_autograd(nbr, pos, kp_pos, kp_feat) if S > 0 else torch.zeros((0, 4), device=dev)
+                rgbs = self.field.evaluate_autograd(nbr, pos, kp_pos, kp_feat, ray_offset[-1:]) if S > 0 else torch.zeros((0, 4), device=dev)
                 feat = None
             else:
                 rgbs, feat = self.field.evaluate(nbr, pos, kp_pos, kp_feat, ray_offset[-1:], S, want_feat=return_aux)

@@ -163,6 +163,142 @@ def test_field_autograd_route_matches_fused(syn, model, torch_cuda):
         np.testing.assert_allclose(a[k].cpu().numpy(), b[k].detach().cpu().numpy(), atol=2e-5, rtol=0, err_msg=k)
 
 
+@pytest.mark.parametrize("name", ["view32", "b2t3_16"])
+def test_pair_fused_training_kernels_match_per_layer_route(name, syn, model, torch_cuda):
+    """Fused pair-MLP training kernels (stashing forward, dgrad chain, MN-major weight gradients, feature scatter) against the
+    per-layer route (torch gather / posenc / index_add under autograd + LinearTC): same rgbs, same gradients."""
+    torch = torch_cuda
+    g, coords, feats, extr, intr, res = load_case(name, syn)
+    c, e, i = _t(torch, coords), _t(torch, extr), _t(torch, intr)
+    with torch.no_grad():
+        aux = model.renderer(c, _t(torch, feats), e, i, res, False, return_aux=True)["aux"]
+    nbr, pos = aux["neighbor_idx"], aux["sample_pos"]
+    S = nbr.shape[0]
+    assert S > 300
+    up = torch.randn(S, 4, generator=torch.Generator().manual_seed(3)).cuda() * 1e-3
+    prev = model.field.mlp_impl
+    model.field.mlp_impl = "tc"
+    results = []
+    try:
+        for fused in (True, False):
+            for p in model.parameters():
+                p.grad = None
+            f = _t(torch, feats).requires_grad_(True)
+            fn = model.field.evaluate_autograd if fused else model.field.evaluate_autograd_unfused
+            out = fn(nbr, pos, c, f)
+            (out * up).sum().backward()
+            grads = {k: p.grad.clone() for k, p in model.field.named_parameters()}
+            results.append((out.detach(), f.grad.clone(), grads))
+    finally:
+        model.field.mlp_impl = prev
+    (oa, fa, ga), (ob, fb, gb) = results
+    assert (oa - ob).abs().max().item() < 2e-5 * max(1.0, ob.abs().max().item())
+
+    def close(a, b, what):
+        # The two routes sum layer 0 in different column orders, so a pre-activation within one ulp of zero can take the other
+        # LeakyReLU branch (a handful among ~20 M activations; same caveat as GRAD_TOL).  The exact check of the backward kernels
+        # is test_pair_backward_exact_given_stash below.
+        err, scale = (a - b).abs(), b.abs().max().item()
+        print(f"{what}: max err {err.max().item() / scale:.2e} of max, median {err.median().item() / scale:.2e}")
+        assert err.median().item() < 5e-4 * scale, (what, err.median().item(), scale)
+        assert err.max().item() < GRAD_TOL * scale, (what, err.max().item(), scale)
+
+    close(fa, fb, "d kp_feat")
+    assert (fa != 0).any(dim=-1).sum().item() == (fb != 0).any(dim=-1).sum().item()  # the same points receive gradient
+    for k in gb:
+        close(ga[k], gb[k], k)
+
+
+def _decode_image(buf, off, n_tiles, nkb):
+    """operand image (fp16 hi/lo, SWIZZLE_128B K-blocks) -> float64 [n_tiles*128, nkb*64]"""
+    raw = buf[off:off + n_tiles * nkb * 32768].view(np.float16).reshape(n_tiles, nkb, 2, 128, 64).astype(np.float64)
+    r = np.arange(128)[:, None]
+    c16 = np.arange(8)[None, :]
+    src = (((c16 ^ (r & 7)) * 8)[:, :, None] + np.arange(8)[None, None, :]).reshape(128, 64)  # stored position of column k
+    val = raw[:, :, 0] + raw[:, :, 1]
+    val = np.take_along_axis(val, np.broadcast_to(src, val.shape), axis=-1)
+    return val.transpose(0, 2, 1, 3).reshape(n_tiles * 128, nkb * 64)
+
+
+def test_pair_backward_exact_given_stash(syn, model, torch_cuda):
+    """The fused backward (npcd_pair_tc_bwd + npcd_tc_wgrad + column sums) against a float64 restatement that uses the SAME stash
+    (sign masks, weights, indices, stashed layer inputs) -- no LeakyReLU-branch ambiguity, so the bar is fp32 rounding."""
+    torch = torch_cuda
+    from npcd_b200 import ops
+
+    g, coords, feats, extr, intr, res = load_case("view32", syn)
+    c, f, e, i = _t(torch, coords), _t(torch, feats), _t(torch, extr), _t(torch, intr)
+    with torch.no_grad():
+        aux = model.renderer(c, f, e, i, res, False, return_aux=True)["aux"]
+    nbr, pos = aux["neighbor_idx"], aux["sample_pos"]
+    S = nbr.shape[0]
+    prev = model.field.mlp_impl
+    model.field.mlp_impl = "tc"
+    try:
+        packed = model.field.packed_weights()
+        n_dev = torch.full((1,), S, dtype=torch.int64, device="cuda")
+        agg, stash = ops.pair_tc_train_fwd(nbr, pos, c, f, n_dev, S, packed)
+        d_agg = torch.randn(S, 256, generator=torch.Generator().manual_seed(5)).cuda() * 1e-4
+        d_feat, dws, dbs = ops.pair_tc_bwd(d_agg, stash, packed, coords.shape[0] * coords.shape[1])
+        torch.cuda.synchronize()
+        assert int(packed.error_flag.item()) == 0
+    finally:
+        model.field.mlp_impl = prev
+    lay = stash.layout
+    buf = stash.buf.cpu().numpy()
+    n_tiles = int(buf[lay.rows_dev:lay.rows_dev + 8].view(np.int64)[0]) // 128
+    assert 0 < n_tiles <= lay.max_tiles
+    rows = n_tiles * 128
+    wn = buf[lay.wn:lay.wn + rows * 4].view(np.float32).astype(np.float64)
+    idx = buf[lay.idx:lay.idx + rows * 4].view(np.int32)
+    samp = buf[lay.samp:lay.samp + rows * 4].view(np.int32)
+    # every (sample, neighbour) pair appears exactly once, in order
+    nb = nbr.cpu().numpy()
+    assert (idx >= 0).sum() == (nb >= 0).sum() and np.array_equal(idx[idx >= 0], nb[nb >= 0])
+    assert np.array_equal(samp[idx >= 0], np.repeat(np.arange(S), (nb >= 0).sum(1)))
+    masks = []
+    for l in range(4):
+        m = buf[lay.mask[l]:lay.mask[l] + rows * 32].view(np.uint32).reshape(rows, 8)
+        masks.append(((m[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).reshape(rows, 256).astype(bool))
+    X = [_decode_image(buf, lay.x[0], n_tiles, 2)] + [_decode_image(buf, lay.x[l], n_tiles, 4) for l in (1, 2, 3)]
+    lf = [m for m in model.field.aggregator.local_field if hasattr(m, "weight")]
+    W = [l.weight.detach().cpu().numpy().astype(np.float64) for l in lf[:4]]
+    Bv = [l.bias.detach().cpu().numpy().astype(np.float64) for l in lf[:4]]
+    perm = np.array(ops.pair_input_perm())
+    W0p = np.zeros((256, 128))
+    W0p[:, np.nonzero(perm >= 0)[0]] = W[0][:, perm[perm >= 0]]  # first layer in OUR column order
+    Wp = [W0p] + W[1:]
+    # forward stash: X_{l+1} = lrelu(X_l W_l^T + b_l), masks = sign of the outputs
+    lrelu = lambda t: np.where(t > 0, t, 0.01 * t)
+    for l in range(3):
+        want = lrelu(X[l] @ Wp[l].T + Bv[l])
+        assert np.abs(X[l + 1] - want).max() < 2e-5 * max(1.0, np.abs(want).max()), l
+        near = np.abs(want) > 1e-5
+        assert np.array_equal(masks[l][near], (want > 0)[near]), l
+    # backward in float64 from the stash
+    valid = samp >= 0
+    dP = [None] * 4
+    G = np.where(valid[:, None], wn[:, None] * d_agg.cpu().numpy().astype(np.float64)[np.maximum(samp, 0)], 0.0)
+    for l in (3, 2, 1, 0):
+        dP[l] = G * np.where(masks[l], 1.0, 0.01)
+        G = dP[l] @ Wp[l]
+    want_feat = np.zeros((coords.shape[0] * coords.shape[1], 32))
+    np.add.at(want_feat, idx[idx >= 0], G[idx >= 0, :32])
+
+    def check(got, want, what, tol=2e-5):
+        err, scale = np.abs(got.cpu().numpy().astype(np.float64) - want).max(), np.abs(want).max()
+        print(f"{what}: rel err {err / scale:.2e}")
+        assert err < tol * scale, (what, err, scale)
+
+    check(d_feat, want_feat, "d kp_feat")
+    for l in range(4):
+        dW = dP[l].T @ X[l]
+        if l == 0:
+            dW = dW[:, [int(np.nonzero(perm == j)[0][0]) for j in range(95)]]
+        check(dws[l], dW, f"dW{l}")
+        check(dbs[l], dP[l].sum(0), f"db{l}")
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 def test_composite_fwd_bwd_vs_torch(syn, torch_cuda):
     """Random sigma/rgb on ragged per-ray lists (n = 0, 1, 2, 33, 50, 128) against a dense torch restatement + autograd."""
