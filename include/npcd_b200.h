@@ -190,6 +190,13 @@ typedef struct {
   size_t mask[4];  /* [tile][128][8] uint32 sign bits of the outputs of layers 0..3 */
   size_t wn, idx, samp; /* [tile][128] float / int32 / int32 */
   size_t rows_dev; /* int64: n_tiles * 128 */
+  /* heads stage, per 128-sample tile (h_tiles = ceil(capacity / 128)) */
+  long long h_tiles;
+  size_t hx[6];    /* operand images of F (local_field.8 output), C1, C2, C3 (channel_net hidden), C4, H (shape_net hidden) */
+  size_t hdp[6];   /* operand images of dP_c3, dP_c2, dP_c1, dP_c0, dP_s, dF, written by npcd_heads_tc_bwd */
+  size_t hmask[5]; /* sign bits of H, C1, C2, C3, C4 */
+  size_t g4;       /* fp32 [capacity,4]: dL/d(pre-sigmoid rgb, pre-softplus sigma), written by npcd_heads_tc_bwd */
+  size_t d_agg;    /* fp32 [capacity,256]: dL/d(aggregated pair feature), written by npcd_heads_tc_bwd */
   size_t total;
 } npcd_pair_stash_layout;
 int npcd_pair_stash_layout_for(long long capacity, npcd_pair_stash_layout* out);
@@ -197,6 +204,21 @@ int npcd_pair_tc_train_fwd(const int* nbr_idx, const float* sample_pos, const fl
                            const long long* n_samples_dev, long long capacity, const npcd_mlp_tc_weights* weights, void* workspace,
                            size_t workspace_bytes, const npcd_pair_stash_layout* layout, void* stash, size_t stash_bytes,
                            int* error_flag, int num_sms, void* stream);
+/* Training forward of the WHOLE field: npcd_pair_tc_train_fwd, then the heads stage (local_field.8, shape_net, channel_net,
+ * output activations -> rgbs [capacity,4]) stashing its layer inputs / sign masks too.  The aggregate operand image (input of
+ * local_field.8, needed by its weight gradient) stays at the start of `workspace`: keep it until the backward is done.
+ * npcd_heads_tc_bwd: d_rgbs [S,4] = dL/d(r,g,b,sigma), rgbs = the forward output -> stash d_agg (input of npcd_pair_tc_bwd), g4
+ *   and the six dP images; w_t_packed / inv_scale (HOST) in order W_c3^T, W_c2^T, W_c1^T, W_c0^T, W_s0^T, W_4^T
+ *   (channel_net.6,4,2,0, shape_net.0, local_field.8; entries 3 and 4 packed with ONE common scale); chan_out_w [3,256] and
+ *   shape_out_w [256] are HOST pointers (they travel by value); scale_dev from npcd_absmax_scale(d_rgbs, ..., target_exp = 8).  */
+int npcd_field_tc_train_fwd(const int* nbr_idx, const float* sample_pos, const float* kp_pos, const float* kp_feat,
+                            const long long* n_samples_dev, long long capacity, const npcd_mlp_tc_weights* weights, void* workspace,
+                            size_t workspace_bytes, const npcd_pair_stash_layout* layout, void* stash, size_t stash_bytes,
+                            float* rgbs, int* error_flag, int num_sms, void* stream);
+int npcd_heads_tc_bwd(const float* d_rgbs, const float* rgbs, const long long* n_samples_dev, long long capacity,
+                      const npcd_pair_stash_layout* layout, void* stash, const void* const* w_t_packed, const float* inv_scale,
+                      const float* chan_out_w, const float* shape_out_w, const float* scale_dev, int* error_flag, int num_sms,
+                      void* stream);
 /* scale_out [2] = {s, 1/s}, s a power of two with s * max|x| in [2^target_exp, 2^(target_exp+1)) (s = 1 if x == 0);
  * scratch4: 4 bytes of device scratch.                                                                                         */
 int npcd_absmax_scale(const float* x, long long n, int target_exp, void* scratch4, float* scale_out, void* stream);

@@ -67,7 +67,9 @@ class PairStashLayout(C.Structure):
     """mirror of ``npcd_pair_stash_layout``"""
 
     _fields_ = [("max_tiles", C.c_longlong), ("x", C.c_size_t * 4), ("dp", C.c_size_t * 4), ("mask", C.c_size_t * 4),
-                ("wn", C.c_size_t), ("idx", C.c_size_t), ("samp", C.c_size_t), ("rows_dev", C.c_size_t), ("total", C.c_size_t)]
+                ("wn", C.c_size_t), ("idx", C.c_size_t), ("samp", C.c_size_t), ("rows_dev", C.c_size_t),
+                ("h_tiles", C.c_longlong), ("hx", C.c_size_t * 6), ("hdp", C.c_size_t * 6), ("hmask", C.c_size_t * 5),
+                ("g4", C.c_size_t), ("d_agg", C.c_size_t), ("total", C.c_size_t)]
 
 
 # name -> argtypes; every entry point declared in include/npcd_b200.h (tests check the header against this table)
@@ -96,6 +98,8 @@ SIGNATURES = {
     "npcd_tc_image_colsum": [P, I, L, P, P, I, P, P, I, I, P, C.c_size_t, P],
     "npcd_pair_stash_layout_for": [L, P],
     "npcd_pair_tc_train_fwd": [P, P, P, P, P, L, P, P, C.c_size_t, P, P, C.c_size_t, P, I, P],
+    "npcd_field_tc_train_fwd": [P, P, P, P, P, L, P, P, C.c_size_t, P, P, C.c_size_t, P, P, I, P],
+    "npcd_heads_tc_bwd": [P, P, P, L, P, P, P, P, P, P, P, P, I, P],
     "npcd_absmax_scale": [P, L, I, P, P, P],
     "npcd_pair_tc_bwd": [P, P, P, P, P, P, P, P, I, P],
     "npcd_composite_fwd": [P, P, P, P, P, L, I, P, P, P, P, I, P],

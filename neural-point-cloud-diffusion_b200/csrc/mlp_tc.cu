@@ -30,6 +30,7 @@ namespace npcd {
 namespace tc {
 
 constexpr int kThreadsTc = 352;
+constexpr int kThreadsTcTrainHeads = 384;  // + warp 11: stash copies (warp 10 is the first-operand loader in heads mode)
 constexpr int kEpiThreads = 256;
 constexpr int kTileBytesW = 256 * 128;        // one K-block of 256 output rows
 constexpr int kStages = 3;
@@ -43,7 +44,7 @@ constexpr int kPackRows = 121;                // pair offsets per dense tile
 constexpr int kImgTileBytes = 4 * 2 * kTileBytesA;  // one 128-sample tile of the pre-split [S,256] operand image (128 KB)
 
 enum Epi { EPI_ACT = 0, EPI_LINEAR = 1, EPI_AGG = 2, EPI_DOT1 = 3, EPI_DOT3 = 4, EPI_DUMP = 5 };
-enum Mode { MODE_PAIR = 0, MODE_HEADS = 1, MODE_PROBE = 2, MODE_PAIR_TRAIN = 3 };
+enum Mode { MODE_PAIR = 0, MODE_HEADS = 1, MODE_PROBE = 2, MODE_PAIR_TRAIN = 3, MODE_HEADS_TRAIN = 4 };
 
 // misc shared-memory layout (byte offsets)
 constexpr int kOffBars = 0;       // 24 mbarriers
@@ -97,6 +98,9 @@ struct Params {
   float* stash_wn;          // [tile][128] normalised inverse-distance weight of every row
   int* stash_idx;           // [tile][128] global point index of every row (-1 = padding)
   int* stash_samp;          // [tile][128] sample index of every row (-1 = padding)
+  // training stash of the heads stage (MODE_HEADS_TRAIN), per 128-sample tile
+  uint8_t* hstash_x[6];      // operand images of F (local_field.8 output), C1, C2, C3 (channel_net hidden 1..3), C4, H (shape hidden)
+  uint32_t* hstash_mask[5];  // sign bits of H, C1, C2, C3, C4
 };
 
 // One chunk (32 accumulator columns starting at c0) of an ACT / LINEAR epilogue: y = [lrelu](acc * inv + b) -> fp16 hi/lo ->
@@ -136,9 +140,13 @@ __device__ __forceinline__ void epi_chunk_store(const Params& P, int l, float in
 
 // ------------------------------------------------------------------------------------------------------------- kernel ----
 template <int kMode>
-__global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(kMode == MODE_HEADS_TRAIN ? kThreadsTcTrainHeads : kThreadsTc, 1)
+    k_field_tc(const __grid_constant__ Params P) {
   constexpr bool kPair = kMode == MODE_PAIR || kMode == MODE_PAIR_TRAIN;
-  constexpr bool kTrain = kMode == MODE_PAIR_TRAIN;
+  constexpr bool kTrainP = kMode == MODE_PAIR_TRAIN;
+  constexpr bool kTrainH = kMode == MODE_HEADS_TRAIN;
+  constexpr bool kTrain = kTrainP || kTrainH;
+  constexpr bool kHeads = kMode == MODE_HEADS || kMode == MODE_HEADS_TRAIN;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sW = smem + kSmemA;
@@ -154,7 +162,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(bar(kBarWFull + i), 1); mbar_init(bar(kBarWEmpty + i), 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(bar(kBarARdy + i), 8); mbar_init(bar(kBarA0Rdy + i), 1); mbar_init(bar(kBarAFree + i), 1); }
+    // heads training: a K-block is free for the next tile's first operand once the last layer's MMAs AND the stash copy are done
+    for (int i = 0; i < 4; ++i) { mbar_init(bar(kBarARdy + i), 8); mbar_init(bar(kBarA0Rdy + i), 1); mbar_init(bar(kBarAFree + i), kTrainH ? 2 : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar(kBarAccRdy + i), 1); mbar_init(bar(kBarAccFree + i), 8); }
     for (int i = 0; i < 4; ++i) mbar_init(bar(kBarStash + i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -209,7 +218,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
         const int ksteps = P.layers[l].ksteps;
         const int nkb = (ksteps + 3) >> 2;
         // heads layer 2 (channel_net.0) reads the same operand (feat) as layer 1 (shape_net.0): nothing new to wait for
-        const bool fresh_a = !(kMode == MODE_HEADS && l == 2);
+        const bool fresh_a = !(kHeads && l == 2);
         for (int kb = 0; kb < nkb; ++kb) {
           if (!kPair && l == 0) {
             mbar_wait(bar(kBarA0Rdy + kb), (ph_a0 >> kb) & 1u);
@@ -255,7 +264,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
     }
   } else if (warp == 10) {
     // ======================================== heads / probe: first-operand loader =======================================
-    if (kTrain) {
+    if (kTrainP) {
       // ---- training stash: every published K-block of the A operand (X_0 from the prologue, X_1..X_3 from the epilogues of
       //      layers 0..2) is bulk-copied to HBM as-is (it already IS the operand image the backward GEMMs consume); the epilogue
       //      threads wait on kBarStash + kb before they overwrite that K-block.  Same event order as the epilogue code below.
@@ -301,6 +310,29 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
           __syncwarp();
         }
       }
+    }
+  } else if (warp == 11) {
+    // ================================ heads training: stash of F, C1, C2, C3 (operand images) ===========================
+    if (kTrainH) {
+      uint32_t ph_ar = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int j = 0; j < 4; ++j) {
+          for (int kb = 0; kb < 4; ++kb) {
+            mbar_wait(bar(kBarARdy + kb), (ph_ar >> kb) & 1u);
+            ph_ar ^= 1u << kb;
+            if (elect_one()) {
+              bulk_s2g(P.hstash_x[j] + ((size_t)tile * 4 + kb) * (2 * kTileBytesA), smem_u32(sA + kb * 2 * kTileBytesA), 2 * kTileBytesA);
+              bulk_commit();
+              bulk_wait_read0();
+              mbar_arrive(bar(kBarStash + kb));
+              if (j == 3) mbar_arrive(bar(kBarAFree + kb));  // C3 is out: the loader may take this K-block after the last MMAs
+            }
+            __syncwarp();
+          }
+        }
+      }
+      if (elect_one()) bulk_wait_all0();
+      __syncwarp();
     }
   } else {
     // ============================================ prologue / epilogue threads ===========================================
@@ -362,8 +394,10 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
       for (int i = 0; i < 4; ++i) {
         if (i < 3) tmem_ld32_async(t_acc + (2 * (i + 1) + half) * 32, v[(i + 1) & 1]);
         stash_wait(i);
-        epi_chunk_store(P, l, inv, slope, v[i & 1], (2 * i + half) * 32, sA, rowbase, x7, feat_row,
-                        kTrain ? P.stash_mask[l] + ((size_t)tile_now * 128 + row) * 8 + (2 * i + half) : nullptr);
+        uint32_t* mptr = nullptr;
+        if (kTrainP) mptr = P.stash_mask[l] + ((size_t)tile_now * 128 + row) * 8 + (2 * i + half);
+        if (kTrainH && l >= 2) mptr = P.hstash_mask[l - 1] + ((size_t)tile_now * 128 + row) * 8 + (2 * i + half);
+        epi_chunk_store(P, l, inv, slope, v[i & 1], (2 * i + half) * 32, sA, rowbase, x7, feat_row, mptr);
         if (i == 3) release_acc(ab);
         publish(kBarARdy + i);
         if (kTrain) sd_pending |= 1u << i;
@@ -614,12 +648,28 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
         for (int i = 0; i < 4; ++i) {
           if (i < 3) tmem_ld32_async(t_acc + (2 * (i + 1) + half) * 32, v[(i + 1) & 1]);
           const int c0 = (2 * i + half) * 32;
+          uint32_t mbits = 0u;
+          float hp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const float4 b = *reinterpret_cast<const float4*>(&P.bias[l][c0 + g * 4]);
             const uint32_t* vv = v[i & 1];
             const float h0 = lrelu(fmaf(__uint_as_float(vv[g * 4 + 0]), inv, b.x)), h1 = lrelu(fmaf(__uint_as_float(vv[g * 4 + 1]), inv, b.y)),
                         h2 = lrelu(fmaf(__uint_as_float(vv[g * 4 + 2]), inv, b.z)), h3 = lrelu(fmaf(__uint_as_float(vv[g * 4 + 3]), inv, b.w));
+            if (kTrainH) {  // the activated row is an operand of the narrow output layer's weight gradient: stash it as an image
+              mbits |= ((h0 > 0.f ? 1u : 0u) | (h1 > 0.f ? 2u : 0u) | (h2 > 0.f ? 4u : 0u) | (h3 > 0.f ? 8u : 0u)) << (g * 4);
+              if (g & 1) {
+                const float y[8] = {hp[0], hp[1], hp[2], hp[3], h0, h1, h2, h3};
+                uint4 hi, lo;
+                split8(y, hi, lo);
+                uint8_t* p = P.hstash_x[nout == 1 ? 5 : 4] + ((size_t)tile_now * 4 + (c0 >> 6)) * (2 * kTileBytesA) +
+                             swz(row, ((c0 & 63) >> 3) + (g >> 1));
+                *reinterpret_cast<uint4*>(p) = hi;
+                *reinterpret_cast<uint4*>(p + kTileBytesA) = lo;
+              } else {
+                hp[0] = h0; hp[1] = h1; hp[2] = h2; hp[3] = h3;
+              }
+            }
             if (nout == 1) {
               const float4 w = *reinterpret_cast<const float4*>(&P.shape_out_w[c0 + g * 4]);
               acc3[0] = fmaf(h0, w.x, fmaf(h1, w.y, fmaf(h2, w.z, fmaf(h3, w.w, acc3[0]))));
@@ -631,6 +681,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
               }
             }
           }
+          if (kTrainH) P.hstash_mask[nout == 1 ? 0 : 4][((size_t)tile_now * 128 + row) * 8 + (2 * i + half)] = mbits;
           if (i < 3) tmem_wait(v[(i + 1) & 1]);
         }
         release_acc(ab);
@@ -646,6 +697,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) k_field_tc(const __grid_constan
 
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long s = (long long)tile * 128 + row;
+        tile_now = tile;
         if (kMode == MODE_PROBE) {
           // one linear layer, fp32 dump (self-test of descriptors / swizzle / TMEM read-back)
           const uint32_t ab = lc & 1u;
@@ -860,7 +912,7 @@ int launch_tc(const tc::Params& P, long long tiles, int num_sms, cudaStream_t st
   }
   if (num_sms <= 0) num_sms = 148;
   const unsigned grid = (unsigned)(tiles < num_sms ? (tiles > 0 ? tiles : 1) : num_sms);
-  tc::k_field_tc<kMode><<<grid, tc::kThreadsTc, tc::kSmemTotal, st>>>(P);
+  tc::k_field_tc<kMode><<<grid, kMode == tc::MODE_HEADS_TRAIN ? tc::kThreadsTcTrainHeads : tc::kThreadsTc, tc::kSmemTotal, st>>>(P);
   return check_launch(what);
 }
 }  // namespace
@@ -909,6 +961,31 @@ int pair_stage(const int* nbr_idx, const float* sample_pos, const float* kp_pos,
 }
 }  // namespace
 
+namespace {
+template <int kMode>
+int heads_stage(const npcd_mlp_tc_weights* W, uint8_t* img, float* rgbs, float* feat_out, const long long* n_samples_dev,
+                long long capacity, const npcd_pair_stash_layout* layout, uint8_t* stash, int* error_flag, int num_sms, cudaStream_t st) {
+  static thread_local tc::Params P;
+  memset(&P, 0, sizeof(P));
+  fill_layer(P, 0, W->agg, tc::EPI_LINEAR);
+  fill_layer(P, 1, W->shape, tc::EPI_DOT1);
+  for (int i = 0; i < 3; ++i) fill_layer(P, 2 + i, W->chan[i], tc::EPI_ACT);
+  fill_layer(P, 5, W->chan[3], tc::EPI_DOT3);
+  P.n_layers = 6;
+  P.img = img; P.rgbs = (float4*)rgbs; P.feat_out = feat_out;
+  memcpy(P.shape_out_w, W->shape_out_w, sizeof(float) * 256);
+  memcpy(P.chan_out_w, W->chan_out_w, sizeof(float) * 3 * 256);
+  P.shape_out_b = W->shape_out_b[0];
+  memcpy(P.chan_out_b, W->chan_out_b, sizeof(float) * 3);
+  P.n_samples_dev = n_samples_dev; P.capacity = capacity; P.error_flag = error_flag;
+  if (stash) {
+    for (int i = 0; i < 6; ++i) P.hstash_x[i] = stash + layout->hx[i];
+    for (int i = 0; i < 5; ++i) P.hstash_mask[i] = (uint32_t*)(stash + layout->hmask[i]);
+  }
+  return launch_tc<kMode>(P, (capacity + 127) / 128, num_sms, st, "npcd_field_tc_fwd(heads)");
+}
+}  // namespace
+
 extern "C" int npcd_field_tc_workspace_bytes(long long capacity, size_t* bytes) {
   NPCD_CHECK_ARG(bytes && capacity >= 0 && capacity < (1ll << 27), "bad arguments (capacity must be < 2^27 samples per launch)");
   TcWorkspace w;
@@ -942,22 +1019,7 @@ extern "C" int npcd_field_tc_fwd(const int* nbr_idx, const float* sample_pos, co
                                    error_flag, num_sms, st);
     if (rc) return rc;
   }
-  if (stages & 2) {
-    static thread_local tc::Params P;
-    memset(&P, 0, sizeof(P));
-    fill_layer(P, 0, W->agg, tc::EPI_LINEAR);
-    fill_layer(P, 1, W->shape, tc::EPI_DOT1);
-    for (int i = 0; i < 3; ++i) fill_layer(P, 2 + i, W->chan[i], tc::EPI_ACT);
-    fill_layer(P, 5, W->chan[3], tc::EPI_DOT3);
-    P.n_layers = 6;
-    P.img = img; P.rgbs = (float4*)rgbs; P.feat_out = feat_out;
-    memcpy(P.shape_out_w, W->shape_out_w, sizeof(float) * 256);
-    memcpy(P.chan_out_w, W->chan_out_w, sizeof(float) * 3 * 256);
-    P.shape_out_b = W->shape_out_b[0];
-    memcpy(P.chan_out_b, W->chan_out_b, sizeof(float) * 3);
-    P.n_samples_dev = n_samples_dev; P.capacity = capacity; P.error_flag = error_flag;
-    rc = launch_tc<tc::MODE_HEADS>(P, (capacity + 127) / 128, num_sms, st, "npcd_field_tc_fwd(heads)");
-  }
+  if (stages & 2) rc = heads_stage<tc::MODE_HEADS>(W, img, rgbs, feat_out, n_samples_dev, capacity, nullptr, nullptr, error_flag, num_sms, st);
   return rc;
 }
 
@@ -995,6 +1057,13 @@ extern "C" int npcd_pair_stash_layout_for(long long capacity, npcd_pair_stash_la
   out->idx = take(tiles * 128 * sizeof(int));
   out->samp = take(tiles * 128 * sizeof(int));
   out->rows_dev = take(256);
+  const size_t ht = (size_t)((capacity + 127) / 128);
+  out->h_tiles = (long long)ht;
+  for (int i = 0; i < 6; ++i) out->hx[i] = take(ht * 4 * (2 * tc::kTileBytesA));
+  for (int i = 0; i < 6; ++i) out->hdp[i] = take(ht * 4 * (2 * tc::kTileBytesA));
+  for (int i = 0; i < 5; ++i) out->hmask[i] = take(ht * 128 * 8 * sizeof(uint32_t));
+  out->g4 = take(ht * 128 * 4 * sizeof(float));
+  out->d_agg = take(ht * 128 * (size_t)kHidden * sizeof(float));
   out->total = off;
   return 0;
 }
@@ -1014,4 +1083,25 @@ extern "C" int npcd_pair_tc_train_fwd(const int* nbr_idx, const float* sample_po
   NPCD_CHECK_ARG(layout->max_tiles == ws.max_tiles && stash_bytes >= layout->total, "stash layout does not match the capacity");
   return pair_stage<tc::MODE_PAIR_TRAIN>(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, W, ws, (uint8_t*)workspace,
                                          layout, (uint8_t*)stash, error_flag, num_sms, (cudaStream_t)stream);
+}
+
+extern "C" int npcd_field_tc_train_fwd(const int* nbr_idx, const float* sample_pos, const float* kp_pos, const float* kp_feat,
+                                       const long long* n_samples_dev, long long capacity, const npcd_mlp_tc_weights* W,
+                                       void* workspace, size_t workspace_bytes, const npcd_pair_stash_layout* layout, void* stash,
+                                       size_t stash_bytes, float* rgbs, int* error_flag, int num_sms, void* stream) {
+  NPCD_CHECK_ARG(rgbs && workspace && layout, "null pointer");
+  NPCD_CHECK_ARG(capacity > 0 && (capacity + 127) / 128 == layout->h_tiles, "stash layout does not match the capacity");
+  cudaStream_t st = (cudaStream_t)stream;
+  // rows of the last 128-sample tile beyond `capacity` are never written by the pair stage: zero them so that the stashed layer
+  // inputs of those rows are finite (they meet zero gradients in the weight-gradient GEMMs)
+  cudaError_t e = cudaMemsetAsync((uint8_t*)workspace + (size_t)(layout->h_tiles - 1) * tc::kImgTileBytes, 0, tc::kImgTileBytes, st);
+  if (e != cudaSuccess) {
+    set_error("npcd_field_tc_train_fwd: %s", cudaGetErrorString(e));
+    return 2;
+  }
+  int rc = npcd_pair_tc_train_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, W, workspace, workspace_bytes, layout,
+                                  stash, stash_bytes, error_flag, num_sms, stream);
+  if (rc) return rc;
+  return heads_stage<tc::MODE_HEADS_TRAIN>(W, (uint8_t*)workspace, rgbs, nullptr, n_samples_dev, capacity, layout, (uint8_t*)stash,
+                                           error_flag, num_sms, st);
 }

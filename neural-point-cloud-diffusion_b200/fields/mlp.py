@@ -59,19 +59,16 @@ class MLP(Module):
 
     def evaluate_autograd(self, nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev=None):
         """Differentiable w.r.t. kp_feat and the MLP parameters (`aggregators/mlp.py:69-88,119-121`, `field.py:126-141`).
-        ``mlp_impl == "tc"``: the pair stage (85 % of the FLOPs) runs forward and backward in the fused tcgen05 kernels
-        (`ops.PairFieldFn`); `local_field.8` commutes with the normalised weighted sum and is applied after it, like at inference."""
+        ``mlp_impl == "tc"``: forward and backward of the whole field run in the fused tcgen05 kernels (`ops.FieldFn`);
+        `local_field.8` commutes with the normalised weighted sum and is applied after it, like at inference."""
         S = nbr_idx.shape[0]
         if self.mlp_impl == "tc" and self.aggregator.in_dim == 32:
-            lf = [m for m in self.aggregator.local_field if isinstance(m, torch.nn.Linear)]
             if n_samples_dev is None:
                 n_samples_dev = torch.full((1,), S, dtype=torch.int64, device=nbr_idx.device)
-            pair_params = [t for l in lf[:4] for t in (l.weight, l.bias)]
-            agg = ops.PairFieldFn.apply(kp_feat, *pair_params, nbr_idx, sample_pos, kp_pos, n_samples_dev, self.packed_weights())
-            agg = ops.LinearTC.apply(agg, lf[4].weight, lf[4].bias, 1.0)
-            sigma = F.softplus(ops.mlp_tc(self.shape_net, agg) - 1)
-            rgb = torch.sigmoid(ops.mlp_tc(self.channel_net, agg))
-            return torch.cat([rgb, sigma], -1)
+            lin = lambda seq: [m for m in seq if isinstance(m, torch.nn.Linear)]
+            params = [t for l in lin(self.aggregator.local_field) + lin(self.shape_net) + lin(self.channel_net)
+                      for t in (l.weight, l.bias)]
+            return ops.FieldFn.apply(kp_feat, nbr_idx, sample_pos, kp_pos, n_samples_dev, self.packed_weights(), *params)
         return self.evaluate_autograd_unfused(nbr_idx, sample_pos, kp_pos, kp_feat)
 
     def evaluate_autograd_unfused(self, nbr_idx, sample_pos, kp_pos, kp_feat):

@@ -262,7 +262,9 @@ class PackedTcWeights:
         maxabs, off = small[:10], 10
         self.maxabs = maxabs
         self.pair_linears = lf[:4]
+        self.head_linears = [cn[3], cn[2], cn[1], cn[0], sn[0], lf[4]]  # order of use in npcd_heads_tc_bwd
         self._dgrad = None
+        self._hdgrad = None
 
         def host(n):
             nonlocal off
@@ -312,6 +314,25 @@ class PackedTcWeights:
                 ptrs[l], invs[l] = out.data_ptr(), 1.0 / scale
             self._dgrad = (ptrs, invs, keep)
         return self._dgrad
+
+    def heads_dgrad_pack(self):
+        """W^T of channel_net.6,4,2,0, shape_net.0 and local_field.8 as B operands of `npcd_heads_tc_bwd`; channel_net.0 and
+        shape_net.0 share one scale (their two GEMMs accumulate into one TMEM accumulator)."""
+        if self._hdgrad is None:
+            dev = self.error_flag.device
+            idx = [9, 8, 7, 6, 5, 4]  # positions of those layers in the maxabs table
+            scales = [2.0 ** math.floor(math.log2(4.0 / float(self.maxabs[i]))) if self.maxabs[i] > 0 else 1.0 for i in idx]
+            scales[3] = scales[4] = min(scales[3], scales[4])
+            ptrs, invs, keep = (C.c_void_p * 6)(), (C.c_float * 6)(), []
+            for j, lin in enumerate(self.head_linears):
+                wt = lin.weight.detach().float().t().contiguous()
+                out = torch.zeros(4 * 2 * 32768, dtype=torch.uint8, device=dev)
+                call("npcd_tc_pack_weights", ptr(wt), HIDDEN, None, HIDDEN, float(scales[j]), ptr(out), _stream())
+                _count(1)
+                keep += [wt, out]
+                ptrs[j], invs[j] = out.data_ptr(), 1.0 / scales[j]
+            self._hdgrad = (ptrs, invs, keep)
+        return self._hdgrad
 
 
 def tc_workspace_bytes(capacity: int) -> int:
@@ -399,10 +420,11 @@ class OperandImage:
 
 
 def _pow2_scale(x):
-    """device scalar 2^floor(log2(2 / max|x|)) (1 if x == 0): keeps fp16 hi/lo halves in the normal range, no host sync"""
-    amax = x.detach().abs().amax().float()
-    s = torch.exp2(torch.floor(torch.log2(2.0 / amax.clamp_min(1e-30))))
-    return torch.where(amax > 0, s, torch.ones_like(s)).reshape(1).contiguous()
+    """device scalar 2^k with 2 <= 2^k * max|x| < 4 (1 if x == 0): keeps the fp16 hi/lo halves in range, no host sync"""
+    out = torch.empty(3, device=x.device)
+    call("npcd_absmax_scale", ptr(x), x.numel(), 1, out[2:].data_ptr(), ptr(out), _stream())
+    _count(2)
+    return out[:1]
 
 
 def tc_pack(src, transpose: bool = False, mask=None, slope: float = 1.0) -> OperandImage:
@@ -447,7 +469,7 @@ def tc_wgrad(a: OperandImage, b: OperandImage, n_out: int = None, col_perm=None,
              rows_dev=None, row_splits: int = 0, flags: int = 0):
     """C[m, j] = sum_rows A[row, m] * B[row, j]  from two ROW-major operand images (MN-major tcgen05 operands, no transposes).
     A, B: images of [rows, a_cols] / [rows, b_cols] built by ``tc_pack`` (or stashed by the fused kernels)."""
-    assert a.rows == b.rows, (a.rows, b.rows)
+    assert a.rows <= b.rows, (a.rows, b.rows)  # the reduction runs over A's rows (rows of A beyond them are zero)
     dev = a.data.device
     n_out = b.k if n_out is None else n_out
     if out is None:
@@ -514,6 +536,13 @@ class PairStash:
     @property
     def rows_dev(self):
         return self.buf[self.layout.rows_dev:self.layout.rows_dev + 8]
+
+    def himage(self, off: int) -> OperandImage:
+        n = self.layout.h_tiles
+        return OperandImage(self.buf[off:off + n * 4 * 32768], None, n * 128, HIDDEN)
+
+    def f32(self, off: int, rows: int, cols: int):
+        return self.buf[off:off + rows * cols * 4].view(torch.float32).view(rows, cols)
 
 
 def pair_tc_train_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity: int, weights: "PackedTcWeights"):
@@ -600,16 +629,120 @@ class PairFieldFn(torch.autograd.Function):
         return tuple(out) + (None, None, None, None, None)
 
 
+def field_tc_train_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity: int, weights: "PackedTcWeights"):
+    """Training forward of the whole field (pair stage + heads) -> rgbs [capacity,4], the stash and the workspace whose head is
+    the aggregate operand image (input of local_field.8)."""
+    dev = sample_pos.device
+    lay = _lib.PairStashLayout()
+    call("npcd_pair_stash_layout_for", int(capacity), C.byref(lay))
+    stash = PairStash(lay, torch.empty(lay.total, dtype=torch.uint8, device=dev))
+    nbytes = tc_workspace_bytes(capacity)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    rgbs = torch.empty((capacity, 4), device=dev)
+    kp_pos = kp_pos.detach().contiguous().float()
+    kp_feat = kp_feat.detach().contiguous().float()
+    _timed("field_train_fwd", lambda: call(
+        "npcd_field_tc_train_fwd", ptr(nbr_idx), ptr(sample_pos), ptr(kp_pos), ptr(kp_feat), ptr(n_samples_dev), capacity,
+        C.byref(weights.struct), ptr(ws), nbytes, C.byref(lay), ptr(stash.buf), lay.total, ptr(rgbs), ptr(weights.error_flag),
+        sm_count(dev), _stream()))
+    _count(7)
+    return rgbs, stash, ws
+
+
+def field_tc_bwd(d_rgbs, rgbs, stash: PairStash, ws, n_samples_dev, weights: "PackedTcWeights", n_points_total: int):
+    """Backward of the whole field.  Returns d_kp_feat and the 24 parameter gradients in the order
+    local_field.{0,2,4,6,8}.(weight, bias), shape_net.{0,2}.(weight, bias), channel_net.{0,2,4,6,8}.(weight, bias)."""
+    dev = d_rgbs.device
+    S = rgbs.shape[0]
+    lay = stash.layout
+    d_rgbs = d_rgbs.contiguous().float()
+    scale = absmax_scale(d_rgbs, 8)
+    ptrs, invs, _ = weights.heads_dgrad_pack()
+    _timed("heads_bwd", lambda: call(
+        "npcd_heads_tc_bwd", ptr(d_rgbs), ptr(rgbs), ptr(n_samples_dev), S, C.byref(lay), ptr(stash.buf), ptrs, invs,
+        weights.struct.chan_out_w, weights.struct.shape_out_w, ptr(scale), ptr(weights.error_flag), sm_count(dev), _stream()))
+    _count(1)
+    d_agg = stash.f32(lay.d_agg, S, HIDDEN)
+    d_feat, dw_pair, db_pair = pair_tc_bwd(d_agg, stash, weights, n_points_total)
+    inv_s = scale[1:2]
+    splits = max(1, sm_count(dev) // 2)
+    res = {}
+
+    def grads():
+        agg_img = OperandImage(ws[:lay.h_tiles * 4 * 32768], None, lay.h_tiles * 128, HIDDEN)
+        x_of = [stash.himage(lay.hx[3]), stash.himage(lay.hx[2]), stash.himage(lay.hx[1]), stash.himage(lay.hx[0]),
+                stash.himage(lay.hx[0]), agg_img]
+        for j, name in enumerate(("c3", "c2", "c1", "c0", "s0", "l4")):
+            dp = stash.himage(lay.hdp[j])
+            res[name] = (tc_wgrad(dp, x_of[j], out_scale=inv_s, row_splits=splits), tc_image_colsum(dp, out_scale=inv_s))
+        g4i = tc_pack(stash.f32(lay.g4, S, 4))
+        inv_g = (1.0 / g4i.scale).contiguous()
+        res["cout"] = tc_wgrad(g4i, stash.himage(lay.hx[4]), out_scale=inv_g, row_splits=splits)[:3]
+        res["sout"] = tc_wgrad(g4i, stash.himage(lay.hx[5]), out_scale=inv_g, row_splits=splits)[3:4]
+        res["bout"] = tc_image_colsum(g4i, out_scale=inv_g)
+
+    _timed("heads_wgrad", grads)
+    out = []
+    for l in range(4):
+        out += [dw_pair[l], db_pair[l]]
+    out += list(res["l4"])
+    out += [res["s0"][0], res["s0"][1], res["sout"], res["bout"][3:4]]
+    for name in ("c0", "c1", "c2", "c3"):
+        out += list(res[name])
+    out += [res["cout"], res["bout"][:3]]
+    return d_feat, out
+
+
+class FieldFn(torch.autograd.Function):
+    """rgbs [S,4] = (rgb, sigma) of every kept shading sample: gather, positional encoding, `local_field`, weighted aggregation,
+    `shape_net` / `channel_net` and the output activations (`aggregators/mlp.py:69-88,119-121`, `fields/mlp.py:38-72`,
+    `fields/field.py:126-141`) with forward AND backward in fused tcgen05 kernels.  Parameter order: see ``field_tc_bwd``."""
+
+    @staticmethod
+    def forward(ctx, kp_feat, nbr_idx, sample_pos, kp_pos, n_samples_dev, packed, *params):
+        assert len(params) == 24
+        capacity = nbr_idx.shape[0]
+        rgbs, stash, ws = field_tc_train_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, packed)
+        ctx.stash, ctx.ws, ctx.packed, ctx.feat_shape, ctx.n_dev = stash, ws, packed, kp_feat.shape, n_samples_dev
+        ctx.save_for_backward(rgbs)
+        return rgbs
+
+    @staticmethod
+    def backward(ctx, d_rgbs):
+        (rgbs,) = ctx.saved_tensors
+        shape = ctx.feat_shape
+        n_pts = 1
+        for d in shape[:-1]:
+            n_pts *= d
+        d_feat, grads = field_tc_bwd(d_rgbs, rgbs, ctx.stash, ctx.ws, ctx.n_dev, ctx.packed, n_pts)
+        ctx.stash = ctx.ws = None
+        return (d_feat.view(shape) if ctx.needs_input_grad[0] else None, None, None, None, None, None) + tuple(grads)
+
+
 class LinearTC(torch.autograd.Function):
     """y = lrelu_slope(x W^T + b) with forward, dgrad and wgrad on the tcgen05 GEMMs (`npcd_tc_gemm`, `npcd_tc_wgrad`); slope 1 =
     plain Linear.  Replaces the F.linear / LeakyReLU pairs of `npcd/utils/model.py:22-36` on the training path.  The operand image
     of x built for the forward is kept for the weight gradient, and the masked dy image serves dgrad (K-major), wgrad (MN-major)
     and the bias gradient (column sums), so each tensor is packed once."""
 
+    _wcache = {}
+
+    @staticmethod
+    def _packed_weight(weight, transpose: bool):
+        """operand image of a parameter, re-packed only when the parameter changes (optimizer step / load_state_dict)"""
+        key = (weight.data_ptr(), transpose)
+        hit = LinearTC._wcache.get(key)
+        if hit is None or hit[0] != weight._version or hit[1].rows != (weight.shape[1] if transpose else weight.shape[0]):
+            if len(LinearTC._wcache) > 256:
+                LinearTC._wcache.clear()
+            hit = (weight._version, tc_pack(weight.detach(), transpose=transpose))
+            LinearTC._wcache[key] = hit
+        return hit[1]
+
     @staticmethod
     def forward(ctx, x, weight, bias, slope: float):
         xi = tc_pack(x)
-        y = tc_gemm(xi, tc_pack(weight), bias, slope)
+        y = tc_gemm(xi, LinearTC._packed_weight(weight, False), bias, slope)
         ctx.save_for_backward(weight, y)
         ctx.xi = xi
         ctx.slope = slope
@@ -624,7 +757,7 @@ class LinearTC(torch.autograd.Function):
         dyi = tc_pack(dy, mask=y if slope != 1.0 else None, slope=slope)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = tc_gemm(dyi, tc_pack(weight, transpose=True))
+            dx = tc_gemm(dyi, LinearTC._packed_weight(weight, True))
         if ctx.needs_input_grad[1]:
             dw = tc_wgrad(dyi, xi)
         if ctx.has_bias and ctx.needs_input_grad[2]:

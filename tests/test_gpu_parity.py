@@ -261,6 +261,7 @@ def test_pair_backward_exact_given_stash(syn, model, torch_cuda):
         m = buf[lay.mask[l]:lay.mask[l] + rows * 32].view(np.uint32).reshape(rows, 8)
         masks.append(((m[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).reshape(rows, 256).astype(bool))
     X = [_decode_image(buf, lay.x[0], n_tiles, 2)] + [_decode_image(buf, lay.x[l], n_tiles, 4) for l in (1, 2, 3)]
+    X[0][:, 112:] = 0.0  # the first-layer input has 112 columns; the rest of its second K-block is never written nor read
     lf = [m for m in model.field.aggregator.local_field if hasattr(m, "weight")]
     W = [l.weight.detach().cpu().numpy().astype(np.float64) for l in lf[:4]]
     Bv = [l.bias.detach().cpu().numpy().astype(np.float64) for l in lf[:4]]
@@ -297,6 +298,89 @@ def test_pair_backward_exact_given_stash(syn, model, torch_cuda):
             dW = dW[:, [int(np.nonzero(perm == j)[0][0]) for j in range(95)]]
         check(dws[l], dW, f"dW{l}")
         check(dbs[l], dP[l].sum(0), f"db{l}")
+
+
+def test_field_backward_exact_given_stash(syn, model, torch_cuda):
+    """Whole fused field backward (npcd_heads_tc_bwd -> npcd_pair_tc_bwd -> weight / bias gradients) against float64 from the SAME
+    stash: heads part checked exactly here (the pair part is test_pair_backward_exact_given_stash)."""
+    torch = torch_cuda
+    from npcd_b200 import ops
+
+    g, coords, feats, extr, intr, res = load_case("view32", syn)
+    c, f, e, i = _t(torch, coords), _t(torch, feats), _t(torch, extr), _t(torch, intr)
+    with torch.no_grad():
+        out_ref = model.renderer(c, f, e, i, res, False, return_aux=True)
+    aux = out_ref["aux"]
+    nbr, pos = aux["neighbor_idx"], aux["sample_pos"]
+    S = nbr.shape[0]
+    prev = model.field.mlp_impl
+    model.field.mlp_impl = "tc"
+    try:
+        packed = model.field.packed_weights()
+        n_dev = torch.full((1,), S, dtype=torch.int64, device="cuda")
+        rgbs, stash, ws = ops.field_tc_train_fwd(nbr, pos, c, f, n_dev, S, packed)
+        assert (rgbs - aux["rgbs"]).abs().max().item() < 2e-5 * max(1.0, aux["rgbs"].abs().max().item())
+        d_rgbs = torch.randn(S, 4, generator=torch.Generator().manual_seed(9)).cuda() * 1e-3
+        d_feat, grads = ops.field_tc_bwd(d_rgbs, rgbs, stash, ws, n_dev, packed, coords.shape[0] * coords.shape[1])
+        torch.cuda.synchronize()
+        assert int(packed.error_flag.item()) == 0
+    finally:
+        model.field.mlp_impl = prev
+    lay = stash.layout
+    buf = stash.buf.cpu().numpy()
+    ht = lay.h_tiles
+    F_, C1, C2, C3, C4, H = [_decode_image(buf, lay.hx[j], ht, 4)[:S] for j in range(6)]
+    A0 = _decode_image(ws.cpu().numpy(), 0, ht, 4)[:S]
+    mH, m1, m2, m3, m4 = [((buf[lay.hmask[j]:lay.hmask[j] + ht * 128 * 32].view(np.uint32).reshape(-1, 8)[:S, :, None]
+                            >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).reshape(S, 256).astype(bool) for j in range(5)]
+    P64 = lambda m: (m.weight.detach().cpu().numpy().astype(np.float64), m.bias.detach().cpu().numpy().astype(np.float64))
+    lin = lambda seq: [m for m in seq if hasattr(m, "weight")]
+    (W4, b4) = P64(lin(model.field.aggregator.local_field)[4])
+    (Ws0, bs0), (Wso, bso) = [P64(m) for m in lin(model.field.shape_net)]
+    (Wc0, bc0), (Wc1, bc1), (Wc2, bc2), (Wc3, bc3), (Wco, bco) = [P64(m) for m in lin(model.field.channel_net)]
+    lrelu = lambda t: np.where(t > 0, t, 0.01 * t)
+    # forward stash
+    for got, want, m in ((F_, A0 @ W4.T + b4, None), (H, lrelu(F_ @ Ws0.T + bs0), mH), (C1, lrelu(F_ @ Wc0.T + bc0), m1),
+                         (C2, lrelu(C1 @ Wc1.T + bc1), m2), (C3, lrelu(C2 @ Wc2.T + bc2), m3), (C4, lrelu(C3 @ Wc3.T + bc3), m4)):
+        assert np.abs(got - want).max() < 2e-5 * max(1.0, np.abs(want).max())
+        if m is not None:
+            near = np.abs(want) > 1e-5
+            assert np.array_equal(m[near], (want > 0)[near])
+    o = rgbs.cpu().numpy().astype(np.float64)
+    d = d_rgbs.cpu().numpy().astype(np.float64)
+    gr = d[:, :3] * o[:, :3] * (1 - o[:, :3])
+    gs = d[:, 3] * (1 - np.exp(-o[:, 3]))
+    sel = lambda m: np.where(m, 1.0, 0.01)
+    dPc3 = (gr @ Wco) * sel(m4)
+    dPc2 = (dPc3 @ Wc3) * sel(m3)
+    dPc1 = (dPc2 @ Wc2) * sel(m2)
+    dPc0 = (dPc1 @ Wc1) * sel(m1)
+    dPs = (gs[:, None] * Wso) * sel(mH)
+    dF = dPc0 @ Wc0 + dPs @ Ws0
+    want_dagg = dF @ W4
+
+    def check(got, want, what, tol=2e-5):
+        got = got.cpu().numpy().astype(np.float64) if hasattr(got, "cpu") else got
+        err, scale = np.abs(got - want).max(), np.abs(want).max()
+        print(f"{what}: rel err {err / scale:.2e}")
+        assert err < tol * scale, (what, err, scale)
+
+    check(stash.f32(lay.d_agg, S, 256), want_dagg, "d_agg")
+    check(stash.f32(lay.g4, S, 4), np.concatenate([gr, gs[:, None]], 1), "g4")
+    names = ["l0w", "l0b", "l1w", "l1b", "l2w", "l2b", "l3w", "l3b", "l4w", "l4b", "s0w", "s0b", "sow", "sob",
+             "c0w", "c0b", "c1w", "c1b", "c2w", "c2b", "c3w", "c3b", "cow", "cob"]
+    G = dict(zip(names, grads))
+    want = {"l4w": dF.T @ A0, "l4b": dF.sum(0), "s0w": dPs.T @ F_, "s0b": dPs.sum(0), "sow": gs[None, :] @ H, "sob": gs.sum(keepdims=True),
+            "c0w": dPc0.T @ F_, "c0b": dPc0.sum(0), "c1w": dPc1.T @ C1, "c1b": dPc1.sum(0), "c2w": dPc2.T @ C2, "c2b": dPc2.sum(0),
+            "c3w": dPc3.T @ C3, "c3b": dPc3.sum(0), "cow": gr.T @ C4, "cob": gr.sum(0)}
+    for k, w in want.items():
+        assert tuple(G[k].shape) == w.shape, (k, G[k].shape, w.shape)
+        check(G[k], w, k)
+    # shapes of the pair part follow the parameters
+    own = dict(model.field.named_parameters())
+    for k, nm in (("l0w", "aggregator.local_field.0.weight"), ("l3b", "aggregator.local_field.6.bias")):
+        assert G[k].shape == own[nm].shape
+    assert d_feat.shape == (coords.shape[0] * coords.shape[1], 32) and torch.isfinite(d_feat).all()
 
 
 # ----------------------------------------------------------------------------------------------------------------------
