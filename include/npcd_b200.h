@@ -163,6 +163,27 @@ int npcd_tc_gemm(const void* a_image, const void* b_image, int M, int N, long lo
  * npcd_tc_image_colsum: out[j] (+)= *out_scale_dev * sum_rows X[row, col_perm ? col_perm[j] : j]  (bias gradients);
  *   workspace >= row_splits * 64 * ceil(cols / 64) floats.                                                                     */
 int npcd_tc_wgrad_workspace_bytes(int a_cols, int row_splits, size_t* bytes);
+/* Several weight-gradient problems (the layers of one backward) in ONE launch pair; each also yields its bias gradient
+ * bias_out[m] (+)= *bias_scale_dev * sum_rows A[row, m] (optional) from the same pass.  workspace >= the sum of
+ * npcd_tc_wgrad_workspace_bytes(a_cols, row_splits) over the problems.                                                        */
+#define NPCD_WGRAD_MAX_GROUPS 8
+typedef struct {
+  const void* a_image;
+  const void* b_image;
+  int a_cols, b_cols;
+  long long rows;
+  const long long* rows_dev; /* optional */
+  float* C;
+  long long ldc;
+  int n_out;
+  const int* col_perm;        /* optional */
+  const float* out_scale_dev; /* optional */
+  float* bias_out;            /* optional [a_cols] */
+  const float* bias_scale_dev; /* optional: bias_out uses this scale (the inverse of A's scale) instead of out_scale_dev */
+  int accumulate;
+} npcd_wgrad_problem;
+int npcd_tc_wgrad_grouped(const npcd_wgrad_problem* problems, int n_problems, int row_splits, void* workspace,
+                          size_t workspace_bytes, int flags, void* stream);
 int npcd_tc_wgrad(const void* a_image, int a_cols, const void* b_image, int b_cols, long long rows, const long long* rows_dev,
                   float* C, long long ldc, int n_out, const int* col_perm, const float* out_scale_dev, int accumulate,
                   int row_splits, void* workspace, size_t workspace_bytes, int flags, void* stream);

@@ -72,6 +72,14 @@ class PairStashLayout(C.Structure):
                 ("g4", C.c_size_t), ("d_agg", C.c_size_t), ("total", C.c_size_t)]
 
 
+class WgradProblem(C.Structure):
+    """mirror of ``npcd_wgrad_problem``"""
+
+    _fields_ = [("a_image", P), ("b_image", P), ("a_cols", C.c_int), ("b_cols", C.c_int), ("rows", C.c_longlong), ("rows_dev", P),
+                ("C", P), ("ldc", C.c_longlong), ("n_out", C.c_int), ("col_perm", P), ("out_scale_dev", P), ("bias_out", P),
+                ("bias_scale_dev", P), ("accumulate", C.c_int)]
+
+
 # name -> argtypes; every entry point declared in include/npcd_b200.h (tests check the header against this table)
 SIGNATURES = {
     "npcd_rays_generate": [P, P, I, I, P, I, F, P, P, P, P, P, P, P],
@@ -95,6 +103,7 @@ SIGNATURES = {
     "npcd_tc_gemm": [P, P, I, I, L, P, L, P, P, F, I, P, C.c_size_t, P],
     "npcd_tc_wgrad_workspace_bytes": [I, I, P],
     "npcd_tc_wgrad": [P, I, P, I, L, P, P, L, I, P, P, I, I, P, C.c_size_t, I, P],
+    "npcd_tc_wgrad_grouped": [P, I, I, P, C.c_size_t, I, P],
     "npcd_tc_image_colsum": [P, I, L, P, P, I, P, P, I, I, P, C.c_size_t, P],
     "npcd_pair_stash_layout_for": [L, P],
     "npcd_pair_tc_train_fwd": [P, P, P, P, P, L, P, P, C.c_size_t, P, P, C.c_size_t, P, I, P],

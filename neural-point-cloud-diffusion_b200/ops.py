@@ -488,6 +488,42 @@ def tc_wgrad(a: OperandImage, b: OperandImage, n_out: int = None, col_perm=None,
     return out
 
 
+def tc_wgrad_grouped(problems, row_splits: int = 0):
+    """One launch pair for several weight-gradient problems.  problems: dicts with a, b (OperandImage), out_scale (device [1]),
+    optional n_out, col_perm, rows_dev, want_bias.  Returns [(dW [a.k, n_out], db [a.k] or None), ...]."""
+    assert 1 <= len(problems) <= 8
+    dev = problems[0]["a"].data.device
+    if row_splits <= 0:
+        row_splits = max(1, sm_count(dev) // 2)
+    arr = (_lib.WgradProblem * len(problems))()
+    outs, total, keep = [], 0, []
+    for i, q in enumerate(problems):
+        a, b = q["a"], q["b"]
+        assert a.rows <= b.rows
+        n_out = q.get("n_out") or b.k
+        dw = torch.empty((a.k, n_out), device=dev)
+        db = torch.empty((a.k,), device=dev) if q.get("want_bias", True) else None
+        scale = q.get("out_scale")
+        bscale = None
+        if scale is None:
+            scale = (1.0 / (a.scale * b.scale)).contiguous()
+            bscale = (1.0 / a.scale).contiguous()
+        keep += [scale, bscale]
+        w = arr[i]
+        w.a_image, w.b_image, w.a_cols, w.b_cols, w.rows = ptr(a.data), ptr(b.data), a.k, b.k, a.rows
+        w.rows_dev = ptr(q.get("rows_dev"))
+        w.C, w.ldc, w.n_out, w.col_perm = ptr(dw), dw.stride(0), n_out, ptr(q.get("col_perm"))
+        w.out_scale_dev, w.bias_out, w.bias_scale_dev, w.accumulate = ptr(scale), ptr(db), ptr(bscale), 0
+        n = C.c_size_t()
+        call("npcd_tc_wgrad_workspace_bytes", a.k, row_splits, C.byref(n))
+        total += n.value
+        outs.append((dw, db))
+    ws = torch.empty(total, dtype=torch.uint8, device=dev)
+    call("npcd_tc_wgrad_grouped", arr, len(problems), row_splits, ptr(ws), total, 0, _stream())
+    _count(2)
+    return outs
+
+
 def tc_image_colsum(a: OperandImage, n_out: int = None, col_perm=None, out_scale=None, out=None, accumulate: bool = False,
                     rows_dev=None, row_splits: int = 0):
     """out[j] = sum_rows A[row, j] of an operand image (bias gradients), deterministic two-level sum."""
@@ -588,19 +624,18 @@ def pair_tc_bwd(d_agg, stash: PairStash, weights: "PackedTcWeights", n_points_to
     _count(1)
     inv_s = scale[1:2]
     rows_dev = stash.rows_dev
-    splits = max(1, sm_count(dev) // 2)
-    dws, dbs = [], []
+    res = []
 
     def grads():
+        probs = []
         for l in range(4):
-            dp = stash.image(lay.dp[l], 4, HIDDEN, None)
-            x = stash.image(lay.x[l], 2 if l == 0 else 4, 112 if l == 0 else HIDDEN, None)
-            dws.append(tc_wgrad(dp, x, n_out=95 if l == 0 else HIDDEN, col_perm=pair_ref_col_map(dev) if l == 0 else None,
-                                out_scale=inv_s, rows_dev=rows_dev, row_splits=splits))
-            dbs.append(tc_image_colsum(dp, out_scale=inv_s, rows_dev=rows_dev))
+            probs.append(dict(a=stash.image(lay.dp[l], 4, HIDDEN, None), b=stash.image(lay.x[l], 2 if l == 0 else 4, 112 if l == 0 else HIDDEN, None),
+                              n_out=95 if l == 0 else HIDDEN, col_perm=pair_ref_col_map(dev) if l == 0 else None, out_scale=inv_s,
+                              rows_dev=rows_dev))
+        res.extend(tc_wgrad_grouped(probs))
 
     _timed("pair_mlp_wgrad", grads)
-    return d_feat, dws, dbs
+    return d_feat, [r[0] for r in res], [r[1] for r in res]
 
 
 class PairFieldFn(torch.autograd.Function):
@@ -665,21 +700,22 @@ def field_tc_bwd(d_rgbs, rgbs, stash: PairStash, ws, n_samples_dev, weights: "Pa
     d_agg = stash.f32(lay.d_agg, S, HIDDEN)
     d_feat, dw_pair, db_pair = pair_tc_bwd(d_agg, stash, weights, n_points_total)
     inv_s = scale[1:2]
-    splits = max(1, sm_count(dev) // 2)
     res = {}
 
     def grads():
         agg_img = OperandImage(ws[:lay.h_tiles * 4 * 32768], None, lay.h_tiles * 128, HIDDEN)
         x_of = [stash.himage(lay.hx[3]), stash.himage(lay.hx[2]), stash.himage(lay.hx[1]), stash.himage(lay.hx[0]),
                 stash.himage(lay.hx[0]), agg_img]
-        for j, name in enumerate(("c3", "c2", "c1", "c0", "s0", "l4")):
-            dp = stash.himage(lay.hdp[j])
-            res[name] = (tc_wgrad(dp, x_of[j], out_scale=inv_s, row_splits=splits), tc_image_colsum(dp, out_scale=inv_s))
+        names = ("c3", "c2", "c1", "c0", "s0", "l4")
+        probs = [dict(a=stash.himage(lay.hdp[j]), b=x_of[j], out_scale=inv_s) for j in range(6)]
         g4i = tc_pack(stash.f32(lay.g4, S, 4))
         inv_g = (1.0 / g4i.scale).contiguous()
-        res["cout"] = tc_wgrad(g4i, stash.himage(lay.hx[4]), out_scale=inv_g, row_splits=splits)[:3]
-        res["sout"] = tc_wgrad(g4i, stash.himage(lay.hx[5]), out_scale=inv_g, row_splits=splits)[3:4]
-        res["bout"] = tc_image_colsum(g4i, out_scale=inv_g)
+        probs.append(dict(a=g4i, b=stash.himage(lay.hx[4]), out_scale=inv_g))                    # channel_net.8: rows 0..2
+        probs.append(dict(a=g4i, b=stash.himage(lay.hx[5]), out_scale=inv_g, want_bias=False))  # shape_net.2: row 3
+        outs = tc_wgrad_grouped(probs)
+        for j, name in enumerate(names):
+            res[name] = outs[j]
+        res["cout"], res["bout"], res["sout"] = outs[6][0][:3], outs[6][1], outs[7][0][3:4]
 
     _timed("heads_wgrad", grads)
     out = []
@@ -758,10 +794,9 @@ class LinearTC(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = tc_gemm(dyi, LinearTC._packed_weight(weight, True))
-        if ctx.needs_input_grad[1]:
-            dw = tc_wgrad(dyi, xi)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = tc_image_colsum(dyi)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = tc_wgrad_grouped([dict(a=dyi, b=xi, want_bias=ctx.has_bias)],
+                                      row_splits=max(1, min((dyi.rows + 63) // 64, sm_count(dy.device) // ((dyi.k + 127) // 128))))[0]
         return dx, dw, db, None
 
 

@@ -712,6 +712,13 @@ def test_tc_wgrad_vs_float64(rows, m, n, torch_cuda):
     cs = ops.tc_image_colsum(ia).cpu().double()
     wc = a.double().sum(0)
     assert (cs - wc).abs().max().item() < 1e-5 * max(wc.abs().max().item(), 1e-12)
+    # grouped launch: two problems at once, bias gradient (column sums of A) from the same pass via the ones-tile MMAs
+    (g0, b0), (g1, b1) = ops.tc_wgrad_grouped([dict(a=ia, b=ib), dict(a=ib, b=ia)])
+    assert torch.equal(g0.cpu().double(), got)
+    assert (g1.cpu().double() - want.t()).abs().max().item() < 1e-5 * scale
+    assert (b0.cpu().double() - wc).abs().max().item() < 1e-5 * max(wc.abs().max().item(), 1e-12)
+    wb = b.double().sum(0)
+    assert (b1.cpu().double() - wb).abs().max().item() < 1e-5 * max(wb.abs().max().item(), 1e-12)
     # deterministic: bit-identical run to run, and independent partial sums when accumulating into an existing tensor
     again = ops.tc_wgrad(ia, ib)
     assert torch.equal(again.cpu().double(), got)
