@@ -333,17 +333,125 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------------------- train ----
+def run_train(args):
+    """Secondary workload (BASELINE.json configs[2] / [3]): PointNeRF autodecoder training step, 8 objects x 50 views x 112 rays per
+    GPU, forward + backward through the drop-in module (fused tcgen05 forward/backward kernels), one NCCL all-reduce of the flat
+    MLP-gradient bucket when N > 1 (objects are sharded, so embedding rows never leave their rank).  Not the headline line."""
+    import torch
+    import torch.distributed as dist
+
+    import npcd_b200  # noqa: F401
+    from npcd_b200 import ops, parallel
+    from npcd_b200 import synthetic as syn
+    from npcd_b200.pointnerf import PointNeRF
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, T, n_sub = 8, 50, 112
+    model = PointNeRF(B, 32, 512, False).to(dev)
+    sd = model.state_dict()
+    with torch.no_grad():
+        for k, v in syn.make_weights(0).items():
+            sd[k].copy_(torch.from_numpy(v))
+        coords, feats = syn.make_clouds([rank * B + o for o in range(B)])  # object shard of this rank
+        model.set_all_coords(torch.from_numpy(coords).to(dev))
+        w = model.feats.get_emb().weight
+        w.zero_()
+        w.view(B, 512, 64)[:, :, :32] = torch.from_numpy(feats).to(dev)
+        w.view(B, 512, 64)[:, :, 32:] = -4.0  # log-variance (SURVEY.md section 8(d))
+    model.train()
+    poses, intr = syn.load_cameras()
+    views = np.arange(0, 250, 5)[:T]
+    extr = torch.from_numpy(np.broadcast_to(poses[views][None], (B, T, 4, 4)).copy()).to(dev)
+    K = torch.from_numpy(np.broadcast_to(intr[views][None], (B, T, 3, 3)).copy()).to(dev)
+    gt = torch.rand((B, T, RES * RES, 3), device=dev)
+    obj = torch.arange(B, device=dev)
+    bucket = parallel.GradBucket(parallel.mlp_parameters(model))
+    params = [p for p in model.parameters() if p.requires_grad]
+    stats = []
+
+    def step():
+        for p in params:
+            p.grad = None
+        pred, _ = model(obj, K, extr, True)
+        target = torch.gather(gt, 2, pred.ray_idx.expand(-1, -1, -1, 3))
+        loss = ((pred.channels - target) ** 2).mean()
+        loss.backward()
+        bucket.all_reduce_mean()
+        stats.append((int(model.renderer.last_stats["S"]), pred.channels.shape[2]))
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    stats.clear()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = ops.LAUNCHES
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        loss = step()
+    b.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    if rank == 0:
+        rays = world * B * T * n_sub * args.steps
+        line = {
+            "metric": "train_rays_per_sec", "value": rays / (ms_total * 1e-3), "unit": "rays/s (sampled rays marched)", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": model.field.compute_dtype(), "data": "synthetic",
+            "config": {"workload": "PointNeRF autodecoder training step, forward + backward (+ NCCL all-reduce of the MLP gradients when "
+                                   "N > 1), 8 objects x 50 views x 112 sampled rays per GPU (BASELINE.json configs[2]/[3])",
+                       "kept_samples_per_step_per_gpu": float(np.mean([s for s, _ in stats])),
+                       "rays_kept_per_view": float(np.mean([n for _, n in stats])), "optimizer": "none (gradients only)",
+                       "l2": "per-step stash (~1 GB) >> L2"},
+            "clocks": clocks, "gpu_launches": ops.LAUNCHES - launches0, "loss": float(loss.detach()),
+        }
+        print(json.dumps(line), flush=True)
+    if os.environ.get("NPCD_BENCH_PROFILE") and rank == 0:  # development aid: where does a step spend its time?
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            step()
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=30, max_name_column_width=60), file=sys.stderr)
+        print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=30, max_name_column_width=60), file=sys.stderr)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mlp", default=None, choices=[None, "simt", "tc"], help="field kernel family (default: best available)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="render", choices=["render", "train"],
+                    help="render: the headline line (configs[1]); train: the autodecoder training step (configs[2]/[3], secondary)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "train":
+        run_train(args)
     else:
         run_ours(args)
 

@@ -46,6 +46,26 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# Grow-only pool for the large per-step training buffers (stash ~8 KB per pair, workspace ~1 KB per sample): their sizes follow the
+# data-dependent sample count, and re-allocating a slightly larger block every step would send the caching allocator to cudaMalloc.
+_POOL = {}
+
+
+def _pool_acquire(tag: str, nbytes: int, dev):
+    free = _POOL.setdefault((tag, dev), [])
+    for i, b in enumerate(free):
+        if b.numel() >= nbytes:
+            return free.pop(i)
+    free.clear()  # every pooled block is too small: drop them, allocate with headroom
+    return torch.empty(int(nbytes * 1.3) + 4096, dtype=torch.uint8, device=dev)
+
+
+def _pool_release(tag: str, buf):
+    free = _POOL.setdefault((tag, buf.device), [])
+    if len(free) < 2:
+        free.append(buf)
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -518,8 +538,9 @@ def tc_wgrad_grouped(problems, row_splits: int = 0):
         call("npcd_tc_wgrad_workspace_bytes", a.k, row_splits, C.byref(n))
         total += n.value
         outs.append((dw, db))
-    ws = torch.empty(total, dtype=torch.uint8, device=dev)
+    ws = _pool_acquire("wgrad", total, dev)
     call("npcd_tc_wgrad_grouped", arr, len(problems), row_splits, ptr(ws), total, 0, _stream())
+    _pool_release("wgrad", ws)
     _count(2)
     return outs
 
@@ -670,9 +691,9 @@ def field_tc_train_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capa
     dev = sample_pos.device
     lay = _lib.PairStashLayout()
     call("npcd_pair_stash_layout_for", int(capacity), C.byref(lay))
-    stash = PairStash(lay, torch.empty(lay.total, dtype=torch.uint8, device=dev))
+    stash = PairStash(lay, _pool_acquire("stash", lay.total, dev))
     nbytes = tc_workspace_bytes(capacity)
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    ws = _pool_acquire("ws", nbytes, dev)
     rgbs = torch.empty((capacity, 4), device=dev)
     kp_pos = kp_pos.detach().contiguous().float()
     kp_feat = kp_feat.detach().contiguous().float()
@@ -751,6 +772,8 @@ class FieldFn(torch.autograd.Function):
         for d in shape[:-1]:
             n_pts *= d
         d_feat, grads = field_tc_bwd(d_rgbs, rgbs, ctx.stash, ctx.ws, ctx.n_dev, ctx.packed, n_pts)
+        _pool_release("stash", ctx.stash.buf)  # stream-ordered: the next forward's kernels run after this backward's
+        _pool_release("ws", ctx.ws)
         ctx.stash = ctx.ws = None
         return (d_feat.view(shape) if ctx.needs_input_grad[0] else None, None, None, None, None, None) + tuple(grads)
 
