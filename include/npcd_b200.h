@@ -260,6 +260,15 @@ int npcd_composite_bwd(const float* sample_pos, const float* rgbs, const long lo
                        const float* g_rgb, const float* g_mask, const float* g_depth, const float* out_mask,
                        const float* out_depth, const unsigned char* clamped, float* g_rgbs, void* stream);
 
+/* ---- TV loss of the neural point cloud: the second caller of the kNN boundary (npcd/losses/neural_point_cloud_tv_loss.py:28-83).
+ *   nbr_idx [n,8] = npcd_knn_points of every point against its own cloud (global indices, -1 padded);
+ *   tv_out[p] = weight * sum_n ||f_n - f_p||_1 / (||x_n - x_p||_2 + 1e-5);  backward: d_feat [n,F] += d tv / d feat * g_tv[p]
+ *   (fp32 atomics, like the reference's index_add_); no gradient to the positions (the loss detaches them, :39).              */
+int npcd_tv_loss_fwd(const float* kp_pos, const float* kp_feat, const int* nbr_idx, long long n_points_total, int feat_dim,
+                     float weight, float* tv_out, void* stream);
+int npcd_tv_loss_bwd(const float* kp_pos, const float* kp_feat, const int* nbr_idx, long long n_points_total, int feat_dim,
+                     float weight, const float* g_tv, float* d_feat, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -481,3 +481,33 @@ def render(kp_pos, kp_feat, extr, intr, resolution, sd, sample=False, rng=None, 
                           origins=o, dirs=d, start=start, end=end, t=t, ray_sample_mask=ray_sample_mask,
                           slot_depths=depths)
     return res
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# the TV loss's kNN self-query + weighted L1 total variation
+# (`npcd/losses/neural_point_cloud_tv_loss.py:28-83`).  TEST INFRASTRUCTURE ONLY, like everything in this file.
+def tv_loss(kp_pos: np.ndarray, kp_feat: np.ndarray, weight: float = 1.0, k: int = K_NEIGHBORS, r: float = RADIUS):
+    """kp_pos [B,P,3], kp_feat [B,P,F] -> (tv [B,P], grad of tv.mean() w.r.t. kp_feat [B,P,F]).
+
+    Each point queries its own cloud (`:41-44`); the neighbours are the <= k nearest points within r, the point itself included at
+    distance 0.  The reference then removes the point itself from its list when it has other neighbours (`:52-57`; the comparison
+    uses LOCAL indices against GLOBAL neighbour ids, so it only ever fires for batch element 0) -- which cannot change the value:
+    the self term is w * |f_p - f_p|_1 = 0.  tv_p = weight * sum_n ||f_n - f_p||_1 / (||x_n - x_p||_2 + 1e-5) (`:66-76`)."""
+    B, P, F = kp_feat.shape
+    tv = np.zeros((B, P), dtype=np.float64)
+    grad = np.zeros((B, P, F), dtype=np.float64)
+    for b in range(B):
+        idx, _ = knn_exact(kp_pos[b], kp_pos[b], k=k, r=r)
+        for j in range(idx.shape[1]):
+            n = idx[:, j]
+            ok = n >= 0
+            nn = np.where(ok, n, 0)
+            d = kp_pos[b][nn].astype(np.float32) - kp_pos[b]
+            dist = np.sqrt((d * d).sum(-1, dtype=np.float32))
+            w = np.where(ok, 1.0 / (dist.astype(np.float64) + 1e-5), 0.0)
+            diff = kp_feat[b][nn].astype(np.float64) - kp_feat[b]
+            tv[b] += w * np.abs(diff).sum(-1)
+            g = (w * weight / (B * P))[:, None] * np.sign(diff)
+            np.add.at(grad[b], nn, g)
+            grad[b] -= g
+    return (tv * weight).astype(np.float32), grad.astype(np.float32)

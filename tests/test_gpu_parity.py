@@ -584,6 +584,27 @@ def test_tv_loss_self_query(syn, model, torch_cuda):
 
 # ----------------------------------------------------------------------------------------------------------------------
 # Tensor-core (tcgen05) field kernels
+def test_tv_loss_module_vs_golden(syn, model, torch_cuda):
+    """`losses.NeuralPointCloudTVLoss` (kNN self-query + fused TV kernels, forward and backward) against the unmodified reference
+    loss (golden tv_b2) -- same call signature and dictionary keys as npcd/losses/neural_point_cloud_tv_loss.py."""
+    import os
+    import types
+
+    torch = torch_cuda
+    from npcd_b200.losses import NeuralPointCloudTVLoss
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "tv_b2.npz"))
+    coords, feats = syn.make_clouds([int(o) for o in g["objs"]])
+    f = _t(torch, feats).requires_grad_(True)
+    loss_fn = NeuralPointCloudTVLoss(types.SimpleNamespace(pointnerf=model), weight=float(g["weight"]), verbose=False)
+    total, sub, pw = loss_fn(None, None, {"feats": f, "coords": _t(torch, coords)}, 0)
+    assert set(sub) == set(pw) == {"00_neural_point_cloud_tv"}
+    np.testing.assert_allclose(pw["00_neural_point_cloud_tv"].detach().cpu().numpy(), g["tv"], rtol=3e-6, atol=0)
+    assert abs(total.item() - float(g["loss"])) < 2e-6 * float(g["loss"])
+    total.backward()
+    np.testing.assert_allclose(f.grad.cpu().numpy(), g["grad_feats"], atol=3e-6 * np.abs(g["grad_feats"]).max(), rtol=0)
+
+
 def test_tc_linear_probe(torch_cuda):
     """One 256x256 layer through the tcgen05 engine (fp16 hi/lo split, 3 products) against float64: error ~ fp32 level."""
     import os

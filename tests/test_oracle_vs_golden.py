@@ -92,3 +92,16 @@ def test_train_mode_backward(syn, weights):
         np.testing.assert_allclose(got.reshape(ref.shape), ref, atol=GRAD_TOL * max(np.abs(ref).max(), 1e-12), rtol=0, err_msg=k)
         nrm = float(np.sqrt((gr.astype(np.float64) ** 2).sum()))
         assert abs(nrm - float(g["gradnorm__" + k])) <= GRAD_TOL * float(g["gradnorm__" + k]) + 1e-12, k
+
+
+def test_tv_loss_self_query(syn):
+    """TV-loss kNN self-query + weighted L1 TV against the unmodified reference loss
+    (tests/golden/make_golden_tv.py)."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "tv_b2.npz"))
+    coords, feats = syn.make_clouds([int(o) for o in g["objs"]])
+    tv, grad = orc.tv_loss(coords, feats, float(g["weight"]))
+    np.testing.assert_allclose(tv, g["tv"], rtol=2e-6, atol=0)
+    assert abs(float(tv.mean()) - float(g["loss"])) < 1e-6 * float(g["loss"])
+    np.testing.assert_allclose(grad, g["grad_feats"], atol=2e-6 * np.abs(g["grad_feats"]).max(), rtol=0)
