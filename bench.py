@@ -289,9 +289,19 @@ def run_ours(args):
     pair_flops_per_launch = Np * FLOP_PER_PAIR * args.steps / n_launch
     avg_pair_s = (sum(pair_ms) / n_launch) * 1e-3 if pair_ms else float("nan")
     achieved_tf = pair_flops_per_launch / avg_pair_s / 1e12 if pair_ms else None
+    # DRAM bytes of one pair-kernel launch: measured once per kernel version with `ncu --set full` (profiles/ncu_traffic.json holds
+    # dram__bytes_read.sum + dram__bytes_write.sum of a full-size launch and the kept-sample count it processed); scaled by samples
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.isfile(tpath) and model.field.mlp_impl == "tc" and pair_ms:
+        tj = json.load(open(tpath))["pair_mlp_tc"]
+        traffic = tj["dram_bytes_per_launch"] / tj["samples_per_launch"] * S * args.steps / n_launch
     roofline = {
         "kernel": f"pair MLP ({model.field.mlp_impl})", "bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"],
-        "unit": "TFLOP/s", "frac": (achieved_tf / peaks["tf_sustained"]) if achieved_tf else None, "traffic": None,
+        "unit": "TFLOP/s", "frac": (achieved_tf / peaks["tf_sustained"]) if achieved_tf else None, "traffic": traffic,
+        "issued_mma_tflops": (3.0 * achieved_tf) if (achieved_tf and model.field.mlp_impl == "tc") else None,
+        "note": "achieved = algorithmic fp32 FLOPs; the tc kernels issue 3 fp16 tensor-core products per algorithmic product (fp32 "
+                "parity, DESIGN.md section 5), so frac tops out at 1/3",
         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']})",
         "algorithmic_flops_per_launch": pair_flops_per_launch, "launches_timed": len(pair_ms),
         "share_of_step": (sum(pair_ms) / ms_total) if pair_ms else None,

@@ -41,6 +41,7 @@ int npcd_rays_generate(const float* extr, const float* intr, int n_views, int re
  *   occ_bits [n_obj, words] uint32; `npcd_grid_dims` reports cells / words.                                                   */
 int npcd_grid_dims(int* cells, int* words);
 int npcd_grid_build(const float* kp_pos, int n_obj, int n_points, int* cell_start, float* sorted_pts, unsigned* occ_bits,
+                    float* aabb /* optional [n_obj,6]: box of the dilated occupied cells, +-inf where it meets the cube border */,
                     void* stream);
 
 /* ---- march + exact radius-kNN: replaces Aggregator.query_keypoints (fields/aggregators/aggregator.py:25-76) and
@@ -54,8 +55,9 @@ int npcd_grid_build(const float* kp_pos, int n_obj, int n_points, int* cell_star
  *           sample_ray [S] int32 (optional).                                                                                  */
 int npcd_march_count(const float* cam_centers, const float* dirs, const float* ray_start, const float* ray_end,
                      const float* jitter, long long n_rays, int rays_per_view, int views_per_obj, int n_points,
-                     const int* cell_start, const float* sorted_pts, const unsigned* occ_bits, float radius, int max_shading_pts,
-                     unsigned* valid_bits, int* ray_count, void* stream);
+                     const int* cell_start, const float* sorted_pts, const unsigned* occ_bits,
+                     const float* aabb /* optional, from npcd_grid_build: samples outside the box are skipped untested */,
+                     float radius, int max_shading_pts, unsigned* valid_bits, int* ray_count, void* stream);
 int npcd_scan_workspace_bytes(long long n, size_t* bytes);
 int npcd_scan_counts(const int* ray_count, const int* ray_ids, long long n, long long* ray_offset, void* workspace,
                      size_t workspace_bytes, void* stream);

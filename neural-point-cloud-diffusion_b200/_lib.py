@@ -84,8 +84,8 @@ class WgradProblem(C.Structure):
 SIGNATURES = {
     "npcd_rays_generate": [P, P, I, I, P, I, F, P, P, P, P, P, P, P],
     "npcd_grid_dims": [P, P],
-    "npcd_grid_build": [P, I, I, P, P, P, P],
-    "npcd_march_count": [P, P, P, P, P, L, I, I, I, P, P, P, F, I, P, P, P],
+    "npcd_grid_build": [P, I, I, P, P, P, P, P],
+    "npcd_march_count": [P, P, P, P, P, L, I, I, I, P, P, P, P, F, I, P, P, P],
     "npcd_scan_workspace_bytes": [L, P],
     "npcd_scan_counts": [P, P, L, P, P, C.c_size_t, P],
     "npcd_knn_fill": [P, P, P, P, P, P, L, P, P, I, I, I, P, P, F, L, P, P, P, P],

@@ -8,6 +8,9 @@
 //   cell_start [G^3 + 1] int32   CSR offsets into the sorted point list
 //   sorted_pts [P] float4        (x, y, z, original index as int bits), sorted by (cell, original index)
 //   occ_bits   [G^3 / 32] u32    bit c set iff any of the 27 cells around c holds a point ("dilated occupancy")
+//   aabb       [6] float         (optional) world-space bounding box of the cells with a set bit: (lo xyz, hi xyz), open-ended
+//                                (+-inf) on a side that touches the cube border (samples outside the cube are clamped into border
+//                                cells).  A sample outside this box cannot have a neighbour: the marcher skips it untested.
 // One CTA per object; the whole build lives in shared memory (histogram 55 KB + bits 1.7 KB).
 #include "common.cuh"
 #include "npcd_b200.h"
@@ -19,20 +22,25 @@ __device__ __forceinline__ int cell_of(float x, float y, float z) {
 }
 
 __global__ void __launch_bounds__(512) k_grid_build(const float* __restrict__ kp_pos, int P, int* __restrict__ cell_start,
-                                                    float4* __restrict__ sorted_pts, uint32_t* __restrict__ occ_bits) {
+                                                    float4* __restrict__ sorted_pts, uint32_t* __restrict__ occ_bits,
+                                                    float* __restrict__ aabb) {
   extern __shared__ int smem[];
   int* hist = smem;                                  // [kGridCells + 1]
   uint32_t* bits = (uint32_t*)(smem + kGridCells + 1);  // [kGridWords]
   __shared__ int chunk_sum[512];
+  __shared__ int box[6];
   const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const float* pts = kp_pos + (size_t)b * P * 3;
   for (int c = tid; c <= kGridCells; c += nt) hist[c] = 0;
   for (int c = tid; c < kGridWords; c += nt) bits[c] = 0u;
+  if (tid < 3) { box[tid] = kGrid; box[3 + tid] = -1; }
   __syncthreads();
   for (int p = tid; p < P; p += nt) {
     const float x = pts[p * 3], y = pts[p * 3 + 1], z = pts[p * 3 + 2];
     atomicAdd(&hist[cell_of(x, y, z)], 1);
     const int cx = grid_coord(x), cy = grid_coord(y), cz = grid_coord(z);
+    atomicMin(&box[0], cx); atomicMin(&box[1], cy); atomicMin(&box[2], cz);
+    atomicMax(&box[3], cx); atomicMax(&box[4], cy); atomicMax(&box[5], cz);
     for (int dz = -1; dz <= 1; ++dz)
       for (int dy = -1; dy <= 1; ++dy)
         for (int dx = -1; dx <= 1; ++dx) {
@@ -63,6 +71,11 @@ __global__ void __launch_bounds__(512) k_grid_build(const float* __restrict__ kp
   for (int c = tid; c <= kGridCells; c += nt) cs[c] = hist[c];
   uint32_t* ob = occ_bits + (size_t)b * kGridWords;
   for (int c = tid; c < kGridWords; c += nt) ob[c] = bits[c];
+  if (aabb && tid < 3) {  // dilated cell range [lo - 1, hi + 1] in world units, with a small margin for the cell-boundary rounding
+    const int lo_c = box[tid] - 1, hi_c = box[3 + tid] + 1;
+    aabb[b * 6 + tid] = lo_c <= 0 ? -INFINITY : (float)lo_c * (2.0f / kGrid) - 1.0f - 1e-4f;
+    aabb[b * 6 + 3 + tid] = hi_c >= kGrid - 1 ? INFINITY : (float)(hi_c + 1) * (2.0f / kGrid) - 1.0f + 1e-4f;
+  }
   // stable placement: rank within the cell = #points with the same cell and a lower index (deterministic, P is small)
   float4* sp = sorted_pts + (size_t)b * P;
   for (int p = tid; p < P; p += nt) {
@@ -77,14 +90,14 @@ __global__ void __launch_bounds__(512) k_grid_build(const float* __restrict__ kp
 }  // namespace npcd
 
 extern "C" int npcd_grid_build(const float* kp_pos, int n_obj, int n_points, int* cell_start, float* sorted_pts,
-                               unsigned* occ_bits, void* stream) {
+                               unsigned* occ_bits, float* aabb, void* stream) {
   using namespace npcd;
   NPCD_CHECK_ARG(kp_pos && cell_start && sorted_pts && occ_bits, "null pointer");
   NPCD_CHECK_ARG(n_obj >= 0 && n_points > 0 && n_points <= (1 << 20), "bad n_obj / n_points");
   if (n_obj == 0) return 0;
   const size_t smem = (size_t)(kGridCells + 1 + kGridWords) * sizeof(int);
   cudaFuncSetAttribute(k_grid_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_grid_build<<<n_obj, 512, smem, (cudaStream_t)stream>>>(kp_pos, n_points, cell_start, (float4*)sorted_pts, occ_bits);
+  k_grid_build<<<n_obj, 512, smem, (cudaStream_t)stream>>>(kp_pos, n_points, cell_start, (float4*)sorted_pts, occ_bits, aabb);
   return check_launch("npcd_grid_build");
 }
 

@@ -48,8 +48,9 @@ __global__ void __launch_bounds__(256) k_march_count(const float* __restrict__ c
                                                      const float* __restrict__ jitter, long long n_rays, int rays_per_view,
                                                      int views_per_obj, int P, const int* __restrict__ cell_start,
                                                      const float4* __restrict__ sorted_pts,
-                                                     const uint32_t* __restrict__ occ_bits, float radius, int max_shading,
-                                                     uint32_t* __restrict__ valid_bits, int* __restrict__ ray_count) {
+                                                     const uint32_t* __restrict__ occ_bits, const float* __restrict__ aabb,
+                                                     float radius, int max_shading, uint32_t* __restrict__ valid_bits,
+                                                     int* __restrict__ ray_count) {
   const int lane = threadIdx.x & 31;
   const long long ray = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (ray >= n_rays) return;
@@ -60,16 +61,52 @@ __global__ void __launch_bounds__(256) k_march_count(const float* __restrict__ c
   const float dx = dirs[ray * 3], dy = dirs[ray * 3 + 1], dz = dirs[ray * 3 + 2];
   const float t0 = start[ray], t1 = end[ray];
   const float* jit = jitter ? jitter + ray * kDepthRes : nullptr;
+  // Empty-space skipping: only the depth samples inside the object's dilated-occupancy box can have a neighbour.  The sample-index
+  // range is conservative (+-2 samples absorb the rounding of the slab test and the train-mode jitter of < 1 step); every sample
+  // inside it still takes the exact test below, so the result is bit-identical to testing all 128.
+  int i_lo = 0, i_hi = kDepthRes - 1;
+  if (aabb) {
+    const float* bx = aabb + (size_t)obj * 6;
+    float tmin = -INFINITY, tmax = INFINITY;
+    bool miss = false;
+    const float o3[3] = {ox, oy, oz}, d3[3] = {dx, dy, dz};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float lo = __ldg(bx + a), hi = __ldg(bx + 3 + a);
+      if (fabsf(d3[a]) < 1e-12f) {
+        miss |= (o3[a] < lo || o3[a] > hi);
+      } else {
+        const float inv = 1.0f / d3[a];
+        const float ta = (lo - o3[a]) * inv, tb = (hi - o3[a]) * inv;  // +-inf bounds give +-inf (o is finite)
+        tmin = fmaxf(tmin, fminf(ta, tb));
+        tmax = fminf(tmax, fmaxf(ta, tb));
+      }
+    }
+    const float span = t1 - t0;
+    if (miss || tmin > tmax || !(span > 0.f)) {
+      if (miss || tmin > tmax) i_hi = -1;  // the ray never enters the box (a degenerate span keeps the full range)
+    } else {
+      const float s = (float)(kDepthRes - 1) / span;
+      const float flo = (tmin - t0) * s - 2.0f, fhi = (tmax - t0) * s + 2.0f;
+      i_lo = flo <= 0.f ? 0 : (flo >= (float)kDepthRes ? kDepthRes : (int)flo);
+      i_hi = fhi >= (float)(kDepthRes - 1) ? kDepthRes - 1 : (fhi < 0.f ? -1 : (int)fhi + 1);
+      i_hi = min(i_hi, kDepthRes - 1);
+    }
+  }
   int total = 0;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
+    if (j * 32 > i_hi || j * 32 + 31 < i_lo) {  // warp-uniform: no sample of this word can be valid
+      if (lane == j) valid_bits[ray * 4 + j] = 0u;
+      continue;
+    }
     const int i = j * 32 + lane;
     const float t = sample_depth(t0, t1, i, jit);
     const float x = axpy_rn(ox, t, dx), y = axpy_rn(oy, t, dy), z = axpy_rn(oz, t, dz);
     bool hit = false;
     // samples outside the cube cannot be within r of a cell we index (points are clamped into border cells, so test anyway)
     const int c = (grid_coord(z) * kGrid + grid_coord(y)) * kGrid + grid_coord(x);
-    if ((__ldg(g.occ_bits + (c >> 5)) >> (c & 31)) & 1u) {
+    if (i >= i_lo && i <= i_hi && ((__ldg(g.occ_bits + (c >> 5)) >> (c & 31)) & 1u)) {
       visit_neighbourhood(g, x, y, z, [&](float px, float py, float pz, int) {
         hit = dist_rn(x, y, z, px, py, pz) < radius;
         return hit;
@@ -179,8 +216,8 @@ __global__ void __launch_bounds__(128) k_knn_fill(const float* __restrict__ cam,
 
 extern "C" int npcd_march_count(const float* cam_centers, const float* dirs, const float* ray_start, const float* ray_end,
                                 const float* jitter, long long n_rays, int rays_per_view, int views_per_obj, int n_points,
-                                const int* cell_start, const float* sorted_pts, const unsigned* occ_bits, float radius,
-                                int max_shading_pts, unsigned* valid_bits, int* ray_count, void* stream) {
+                                const int* cell_start, const float* sorted_pts, const unsigned* occ_bits, const float* aabb,
+                                float radius, int max_shading_pts, unsigned* valid_bits, int* ray_count, void* stream) {
   using namespace npcd;
   NPCD_CHECK_ARG(cam_centers && dirs && ray_start && ray_end && cell_start && sorted_pts && occ_bits && valid_bits && ray_count,
                  "null pointer");
@@ -192,7 +229,7 @@ extern "C" int npcd_march_count(const float* cam_centers, const float* dirs, con
   const unsigned grid = (unsigned)((n_rays + wpb - 1) / wpb);
   k_march_count<<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(cam_centers, dirs, ray_start, ray_end, jitter, n_rays, rays_per_view,
                                                              views_per_obj, n_points, cell_start, (const float4*)sorted_pts,
-                                                             occ_bits, radius, max_shading_pts, valid_bits, ray_count);
+                                                             occ_bits, aabb, radius, max_shading_pts, valid_bits, ray_count);
   return check_launch("npcd_march_count");
 }
 

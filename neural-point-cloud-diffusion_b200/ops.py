@@ -112,6 +112,7 @@ class Grid:
     occ_bits: torch.Tensor  # [B, words] int32 (bit pattern)
     n_obj: int
     n_points: int
+    aabb: Optional[torch.Tensor] = None  # [B, 6] world box of the dilated occupied cells (empty-space skipping in the marcher)
 
 
 _GRID_DIMS = None
@@ -134,8 +135,8 @@ def grid_build(kp_pos) -> Grid:
     cells, words = grid_dims()
     dev = kp_pos.device
     g = Grid(torch.empty((B, cells + 1), dtype=torch.int32, device=dev), torch.empty((B, P, 4), device=dev),
-             torch.empty((B, words), dtype=torch.int32, device=dev), B, P)
-    call("npcd_grid_build", ptr(kp_pos), B, P, ptr(g.cell_start), ptr(g.sorted_pts), ptr(g.occ_bits), _stream())
+             torch.empty((B, words), dtype=torch.int32, device=dev), B, P, torch.empty((B, 6), device=dev))
+    call("npcd_grid_build", ptr(kp_pos), B, P, ptr(g.cell_start), ptr(g.sorted_pts), ptr(g.occ_bits), ptr(g.aabb), _stream())
     _count(1)
     return g
 
@@ -151,7 +152,7 @@ def march_count(rays: Rays, grid: Grid, views_per_obj: int, radius: float, max_s
         jitter = jitter.contiguous().float()
         assert jitter.numel() == n_rays * DEPTH_RES
     call("npcd_march_count", ptr(rays.cam), ptr(rays.dirs), ptr(rays.start), ptr(rays.end), ptr(jitter), n_rays, R, views_per_obj,
-         grid.n_points, ptr(grid.cell_start), ptr(grid.sorted_pts), ptr(grid.occ_bits), float(radius), int(max_shading_pts),
+         grid.n_points, ptr(grid.cell_start), ptr(grid.sorted_pts), ptr(grid.occ_bits), ptr(grid.aabb), float(radius), int(max_shading_pts),
          ptr(valid_bits), ptr(ray_count), _stream())
     _count(1)
     return valid_bits, ray_count

@@ -65,7 +65,7 @@ def test_abi_version_and_error_string(lib):
 def test_argument_errors_are_reported_without_a_gpu(lib):
     """Argument validation happens before any CUDA call: null pointers -> rc 1 and a message."""
     lib.npcd_grid_build.restype = ctypes.c_int
-    rc = lib.npcd_grid_build(None, 1, 512, None, None, None, None)
+    rc = lib.npcd_grid_build(None, 1, 512, None, None, None, None, None)
     assert rc == 1
     lib.npcd_last_error.restype = ctypes.c_char_p
     assert b"null pointer" in lib.npcd_last_error()
