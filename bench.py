@@ -447,6 +447,87 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------------------------------- decode ----
+def run_decode(args):
+    """Secondary workload (BASELINE.json configs[4]): diffusion-sample decoding -- 64 generated neural point clouds x 8 views at
+    128x128, the (object, view) grid sharded over the ranks in contiguous blocks (`parallel.shard_work_items`), no collective."""
+    import torch
+    import torch.distributed as dist
+
+    import npcd_b200  # noqa: F401
+    from npcd_b200 import ops, parallel
+    from npcd_b200 import synthetic as syn
+    from npcd_b200.pointnerf import PointNeRF
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_obj, n_views = 64, 8
+    model = PointNeRF(1, 32, 512, False).eval().to(dev)
+    sd = model.state_dict()
+    with torch.no_grad():
+        for k, v in syn.make_weights(0).items():
+            sd[k].copy_(torch.from_numpy(v))
+    poses, intr = syn.load_cameras()
+    view_ids = np.arange(0, 8 * 31, 31)  # v = 0, 31, ... (SURVEY.md section 8(d) config 5)
+    runs = parallel.shard_work_items(n_obj, n_views, rank, world)
+    # group this rank's runs into one batched render per distinct view range (whole objects render as one [B, 8] batch)
+    full = [o for o, lo, hi in runs if (lo, hi) == (0, n_views)]
+    part = [(o, lo, hi) for o, lo, hi in runs if (lo, hi) != (0, n_views)]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    batches = []
+    if full:
+        c, f = syn.make_clouds(full)
+        batches.append((t(c), t(f), t(np.broadcast_to(poses[view_ids][None], (len(full), n_views, 4, 4)).copy()),
+                        t(np.broadcast_to(intr[view_ids][None], (len(full), n_views, 3, 3)).copy())))
+    for o, lo, hi in part:
+        c, f = syn.make_clouds([o])
+        batches.append((t(c), t(f), t(poses[view_ids[lo:hi]][None]), t(intr[view_ids[lo:hi]][None])))
+    my_rays = sum(b[2].shape[0] * b[2].shape[1] for b in batches) * RES * RES
+
+    def step():
+        with torch.no_grad():
+            return [model.render(c, f, e, i, resolution=RES) for c, f, e, i in batches]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches0 = ops.LAUNCHES
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        step()
+    b.record()
+    barrier()
+    tt = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total = float(tt.item())
+    if rank == 0:
+        rays = n_obj * n_views * RES * RES * args.steps
+        print(json.dumps({
+            "metric": "rays_per_sec", "value": rays / (ms_total * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": model.field.compute_dtype(), "data": "synthetic",
+            "config": {"workload": "diffusion-sample decode: 64 random-init neural point clouds x 8 views at 128x128, (object, view) "
+                                   "grid sharded over the ranks (BASELINE.json configs[4])",
+                       "views_per_sec": rays / (ms_total * 1e-3) / (RES * RES), "rays_on_rank0": my_rays},
+            "gpu_launches": ops.LAUNCHES - launches0}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -455,13 +536,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mlp", default=None, choices=[None, "simt", "tc"], help="field kernel family (default: best available)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="render", choices=["render", "train"],
-                    help="render: the headline line (configs[1]); train: the autodecoder training step (configs[2]/[3], secondary)")
+    ap.add_argument("--workload", default="render", choices=["render", "train", "decode"],
+                    help="render: the headline line (configs[1]); train: the autodecoder training step (configs[2]/[3]); "
+                         "decode: 64 clouds x 8 views sharded over the ranks (configs[4]); the last two are secondary lines")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "train":
         run_train(args)
+    elif args.workload == "decode":
+        run_decode(args)
     else:
         run_ours(args)
 

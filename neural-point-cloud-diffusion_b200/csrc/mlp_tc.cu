@@ -1042,13 +1042,11 @@ extern "C" int npcd_tc_linear_probe(const void* image, const long long* n_rows_d
 // ---- training forward of the pair stage: same kernel, plus the stash the fused backward needs ------------------------------
 extern "C" int npcd_pair_stash_layout_for(long long capacity, npcd_pair_stash_layout* out) {
   NPCD_CHECK_ARG(out && capacity >= 0 && capacity < (1ll << 27), "bad arguments");
-  TcWorkspace ws;
-  int rc = tc_workspace_layout(capacity, &ws);
-  if (rc) return rc;
-  const size_t tiles = (size_t)ws.max_tiles;
+  const long long max_tiles = capacity * kK / tc::kPackRows + 2;  // as in tc_workspace_layout (host arithmetic only: no device needed)
+  const size_t tiles = (size_t)max_tiles;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align256(off + bytes); return o; };
-  out->max_tiles = ws.max_tiles;
+  out->max_tiles = max_tiles;
   out->x[0] = take(tiles * 2 * (2 * tc::kTileBytesA));
   for (int l = 1; l < 4; ++l) out->x[l] = take(tiles * 4 * (2 * tc::kTileBytesA));
   for (int l = 0; l < 4; ++l) out->dp[l] = take(tiles * 4 * (2 * tc::kTileBytesA));

@@ -768,6 +768,9 @@ class FieldFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_rgbs):
         (rgbs,) = ctx.saved_tensors
+        if ctx.stash is None:
+            raise RuntimeError("FieldFn: the training stash was released by the first backward pass (retain_graph / double backward "
+                               "are not supported on the fused path)")
         shape = ctx.feat_shape
         n_pts = 1
         for d in shape[:-1]:

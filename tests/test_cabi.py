@@ -89,3 +89,47 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, os.path.join(dp, f)
+
+
+def test_training_stash_layout_is_consistent(lib):
+    """npcd_pair_stash_layout_for runs on the host: regions are 256-byte aligned, disjoint, ordered and sized from the capacity."""
+    import npcd_b200  # noqa: F401
+    from npcd_b200 import _lib
+
+    prev_total = 0
+    for cap in (1, 127, 128, 129, 5000, 1 << 20):
+        lay = _lib.PairStashLayout()
+        fn = lib.npcd_pair_stash_layout_for
+        fn.restype = ctypes.c_int
+        fn.argtypes = [ctypes.c_longlong, ctypes.c_void_p]
+        assert fn(cap, ctypes.byref(lay)) == 0
+        assert lay.max_tiles == cap * 8 // 121 + 2 and lay.h_tiles == (cap + 127) // 128
+        offs = list(lay.x) + list(lay.dp) + list(lay.mask) + [lay.wn, lay.idx, lay.samp, lay.rows_dev] + list(lay.hx) + list(lay.hdp) \
+            + list(lay.hmask) + [lay.g4, lay.d_agg, lay.total]
+        assert all(o % 256 == 0 for o in offs) and offs == sorted(offs) and len(set(offs)) == len(offs)
+        assert lay.x[1] - lay.x[0] == lay.max_tiles * 2 * 32768 and lay.dp[1] - lay.dp[0] == lay.max_tiles * 4 * 32768
+        assert lay.total - lay.d_agg >= lay.h_tiles * 128 * 256 * 4
+        assert lay.total >= prev_total
+        prev_total = lay.total
+    lay = _lib.PairStashLayout()
+    assert fn(-1, ctypes.byref(lay)) == 1  # argument error, reported through npcd_last_error
+
+
+def test_wgrad_argument_errors_without_a_gpu(lib):
+    import npcd_b200  # noqa: F401
+    from npcd_b200 import _lib
+
+    lib.npcd_last_error.restype = ctypes.c_char_p
+    fn = lib.npcd_tc_wgrad_grouped
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+    arr = (_lib.WgradProblem * 1)()
+    assert fn(arr, 0, 1, None, 0, 0, None) == 1           # null workspace / no problems
+    assert fn(arr, 9, 1, ctypes.c_void_p(8), 0, 0, None) == 1  # more than NPCD_WGRAD_MAX_GROUPS problems
+    assert b"npcd_tc_wgrad_grouped" in lib.npcd_last_error()
+    n = ctypes.c_size_t()
+    ws = lib.npcd_tc_wgrad_workspace_bytes
+    ws.restype = ctypes.c_int
+    ws.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    assert ws(256, 74, ctypes.byref(n)) == 0 and n.value == 74 * 2 * 128 * 260 * 4
+    assert ws(3, 5, ctypes.byref(n)) == 0 and n.value == 5 * 1 * 128 * 260 * 4
