@@ -271,6 +271,11 @@ int npcd_tv_loss_fwd(const float* kp_pos, const float* kp_feat, const int* nbr_i
 int npcd_tv_loss_bwd(const float* kp_pos, const float* kp_feat, const int* nbr_idx, long long n_points_total, int feat_dim,
                      float weight, const float* g_tv, float* d_feat, void* stream);
 
+/* ---- decode post-processing of eval_diffusion (npcd/eval/diffusion_evaluation.py:169-173): channels [n_views, res*res, 3] ->
+ * images [n_views, 3, res, res] (npcd/utils/util.py:199-203 unflatten_pred), optionally clipped to [0,1] and quantised to
+ * round(x * 255) / 255 (round-half-to-even, as numpy).                                                                         */
+int npcd_channels_to_images(const float* channels, long long n_views, int resolution, int quantize, float* images, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

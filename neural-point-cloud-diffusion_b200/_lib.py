@@ -113,6 +113,7 @@ SIGNATURES = {
     "npcd_pair_tc_bwd": [P, P, P, P, P, P, P, P, I, P],
     "npcd_tv_loss_fwd": [P, P, P, L, I, F, P, P],
     "npcd_tv_loss_bwd": [P, P, P, L, I, F, P, P, P],
+    "npcd_channels_to_images": [P, L, I, I, P, P],
     "npcd_composite_fwd": [P, P, P, P, P, L, I, P, P, P, P, I, P],
     "npcd_clamp_depth": [P, L, P, P, P],
     "npcd_composite_bwd": [P, P, P, L, I, P, P, P, P, P, P, P, P],

@@ -227,3 +227,38 @@ extern "C" int npcd_composite_bwd(const float* sample_pos, const float* rgbs, co
       clamped, (float4*)g_rgbs);
   return check_launch("npcd_composite_bwd");
 }
+
+
+// ---- decode post-processing of `eval_diffusion` (npcd/eval/diffusion_evaluation.py:169-173):
+// unflatten_pred (npcd/utils/util.py:199-203: [n, R, 3] -> [n, 3, H, W]) fused with np.clip(., 0, 1) and np.round(. * 255) / 255
+// (round-half-to-even, like numpy), so the images feed the Inception network without a host round trip.
+namespace npcd {
+__global__ void k_channels_to_images(const float* __restrict__ channels, long long n_views, int n_pix, int quantize,
+                                     float* __restrict__ images) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (view, pixel)
+  if (i >= n_views * n_pix) return;
+  const long long v = i / n_pix;
+  const int p = (int)(i - v * n_pix);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float x = __ldg(channels + i * 3 + c);
+    if (quantize) {
+      if (x == x) x = fminf(fmaxf(x, 0.f), 1.f);  // np.clip keeps NaN; fminf/fmaxf would silently turn it into a bound
+      x = __fdiv_rn(rintf(__fmul_rn(x, 255.f)), 255.f);
+    }
+    images[(v * 3 + c) * n_pix + p] = x;
+  }
+}
+}  // namespace npcd
+
+extern "C" int npcd_channels_to_images(const float* channels, long long n_views, int resolution, int quantize, float* images,
+                                       void* stream) {
+  using namespace npcd;
+  NPCD_CHECK_ARG(n_views >= 0 && resolution > 0, "bad sizes");
+  if (n_views == 0) return 0;
+  NPCD_CHECK_ARG(channels && images, "null pointer");
+  const long long n = n_views * resolution * resolution;
+  k_channels_to_images<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(channels, n_views, resolution * resolution, quantize,
+                                                                                     images);
+  return check_launch("npcd_channels_to_images");
+}

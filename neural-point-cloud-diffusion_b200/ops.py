@@ -912,3 +912,19 @@ def composite_bwd(sample_pos, rgbs, ray_offset, white_back, g_rgb, g_mask, g_dep
          ptr(cont(g_depth)), ptr(out_mask), ptr(out_depth), ptr(clamped), ptr(g), _stream())
     _count(1 if n else 0)
     return g
+
+
+def channels_to_images(channels, resolution: int, quantize: bool = True):
+    """channels [..., res*res, 3] -> images [..., 3, res, res] (`unflatten_pred`), with the clip + 8-bit rounding of
+    `npcd/eval/diffusion_evaluation.py:171-172` fused in (quantize=True)."""
+    _need_cuda(channels)
+    c = channels.contiguous().float()
+    lead = c.shape[:-2]
+    assert c.shape[-2] == resolution * resolution and c.shape[-1] == 3
+    n = 1
+    for d in lead:
+        n *= d
+    out = torch.empty((*lead, 3, resolution, resolution), device=c.device)
+    call("npcd_channels_to_images", ptr(c), n, resolution, int(quantize), ptr(out), _stream())
+    _count(1 if n else 0)
+    return out

@@ -94,3 +94,10 @@ class PointNeRF(nn.Module):
             return self.renderer(coords, feats, extrinsics, intrinsics, resolution, sample_rays)
         finally:
             agg.max_shading_pts = prev
+
+    def render_images(self, coords, feats, extrinsics, intrinsics, resolution=128, quantize=True):
+        """`render` + the decode post-processing of `npcd/eval/diffusion_evaluation.py:169-173` on the device:
+        images [B,T,3,res,res], clipped to [0,1] and rounded to 8 bits when ``quantize``."""
+        from . import ops
+
+        return ops.channels_to_images(self.render(coords, feats, extrinsics, intrinsics, resolution).channels, resolution, quantize)

@@ -584,6 +584,31 @@ def test_tv_loss_self_query(syn, model, torch_cuda):
 
 # ----------------------------------------------------------------------------------------------------------------------
 # Tensor-core (tcgen05) field kernels
+def test_decode_postprocessing_matches_numpy(syn, model, torch_cuda):
+    """`PointNeRF.render_images` = render + unflatten_pred + np.clip + np.round(x * 255) / 255 (eval/diffusion_evaluation.py:169-173)."""
+    torch = torch_cuda
+    from npcd_b200 import ops
+
+    poses, intr = syn.load_cameras()
+    coords, feats = syn.make_clouds([2])
+    c, f = _t(torch, coords), _t(torch, feats)
+    e, i = _t(torch, poses[[0, 100]][None]), _t(torch, syn.scale_intrinsics(intr[[0, 100]], 32)[None])
+    with torch.no_grad():
+        ch = model.render(c, f, e, i, resolution=32).channels
+        img = model.render_images(c, f, e, i, resolution=32)
+    x = ch.cpu().numpy()
+    want = np.swapaxes(x, -1, -2).reshape(1, 2, 3, 32, 32)
+    want = np.round(np.clip(want, 0, 1.0) * 255) / 255
+    np.testing.assert_array_equal(img.cpu().numpy(), want.astype(np.float32))
+    # ties and out-of-range values
+    t = torch.tensor([[[0.5 / 255, 1.5 / 255, 2.5 / 255], [-0.3, 1.7, 0.49999]]], device="cuda").repeat(1, 2, 1)  # [1, 4, 3]
+    got = ops.channels_to_images(t, 2).cpu().numpy()
+    w = np.swapaxes(t.cpu().numpy(), -1, -2).reshape(1, 3, 2, 2)
+    np.testing.assert_array_equal(got, (np.round(np.clip(w, 0, 1.0) * 255) / 255).astype(np.float32))
+    raw = ops.channels_to_images(t, 2, quantize=False).cpu().numpy()
+    np.testing.assert_array_equal(raw, w)
+
+
 def test_tv_loss_module_vs_golden(syn, model, torch_cuda):
     """`losses.NeuralPointCloudTVLoss` (kNN self-query + fused TV kernels, forward and backward) against the unmodified reference
     loss (golden tv_b2) -- same call signature and dictionary keys as npcd/losses/neural_point_cloud_tv_loss.py."""
