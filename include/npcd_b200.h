@@ -271,6 +271,32 @@ int npcd_tv_loss_fwd(const float* kp_pos, const float* kp_feat, const int* nbr_i
 int npcd_tv_loss_bwd(const float* kp_pos, const float* kp_feat, const int* nbr_idx, long long n_points_total, int feat_dim,
                      float weight, const float* g_tv, float* d_feat, void* stream);
 
+/* ---- embedding-side training step ---------------------------------------------------------------
+ * npcd_embed_fwd / _bwd: VariationalEmbedding.forward + get_mean_log_var_std (npcd/models/pointnerf/embeddings/
+ *   variational_embedding.py:36-70) fused: table [n_obj, P*2F] rows obj_idx [n_slots] int64 -> feats = mean + exp(0.5 lv) * eps
+ *   (eps NULL: feats = mean, the eval path), mean, log_var, std, each [n_slots,P,F] (any output may be NULL).  Backward writes the
+ *   COMPACT row gradient d_rows [n_slots, P*2F] (duplicated objects are summed by the optimiser kernel, like nn.Embedding's
+ *   backward would) from g_feats / g_mean / g_log_var / g_std (any may be NULL).
+ * npcd_kl_fwd / _bwd: NeuralPointCloudKLLoss (npcd/losses/neural_point_cloud_kl_loss.py:36-37):
+ *   kld [n] = -0.5 * weight * sum_f (1 + lv - mean^2 - exp(lv)).
+ * npcd_embed_adam_rows: torch.optim.Adam as the reference trainer runs it over the table (npcd/train/pointnerf_training.py:101-102,
+ *   152; defaults: no weight decay, no amsgrad), applied to the rows obj_idx [n_slots] only yet EQUAL to the dense optimiser:
+ *   row_step [n_obj] int32 holds the step each row was last brought up to (0 = never touched, exp_avg = exp_avg_sq = 0) and the
+ *   missed zero-gradient steps are replayed before `step` (1-based) is applied with d_rows.  obj_idx == NULL and d_rows == NULL:
+ *   bring rows 0..n_slots-1 up to date with `step` (before reading the table for evaluation or a checkpoint).                  */
+int npcd_embed_fwd(const float* table, const long long* obj_idx, int n_slots, int n_points, int feat_dim, const float* eps,
+                   float* feats, float* mean, float* log_var, float* std, void* stream);
+int npcd_embed_bwd(const float* table, const long long* obj_idx, int n_slots, int n_points, int feat_dim, const float* eps,
+                   const float* g_feats, const float* g_mean, const float* g_log_var, const float* g_std, float* d_rows,
+                   void* stream);
+int npcd_kl_fwd(const float* mean, const float* log_var, long long n_points_total, int feat_dim, float weight, float* kld,
+                void* stream);
+int npcd_kl_bwd(const float* mean, const float* log_var, long long n_points_total, int feat_dim, float weight, const float* g_kld,
+                float* d_mean, float* d_log_var, void* stream);
+int npcd_embed_adam_rows(float* table, float* exp_avg, float* exp_avg_sq, int* row_step, const long long* obj_idx, int n_slots,
+                         long long row_len, const float* d_rows, int step, double lr, double beta1, double beta2, double adam_eps,
+                         void* stream);
+
 /* ---- decode post-processing of eval_diffusion (npcd/eval/diffusion_evaluation.py:169-173): channels [n_views, res*res, 3] ->
  * images [n_views, 3, res, res] (npcd/utils/util.py:199-203 unflatten_pred), optionally clipped to [0,1] and quantised to
  * round(x * 255) / 255 (round-half-to-even, as numpy).                                                                         */

@@ -19,6 +19,7 @@ P = C.c_void_p
 I = C.c_int
 L = C.c_longlong
 F = C.c_float
+D = C.c_double
 
 
 class SimtWeights(C.Structure):
@@ -114,6 +115,11 @@ SIGNATURES = {
     "npcd_tv_loss_fwd": [P, P, P, L, I, F, P, P],
     "npcd_tv_loss_bwd": [P, P, P, L, I, F, P, P, P],
     "npcd_channels_to_images": [P, L, I, I, P, P],
+    "npcd_embed_fwd": [P, P, I, I, I, P, P, P, P, P, P],
+    "npcd_embed_bwd": [P, P, I, I, I, P, P, P, P, P, P, P],
+    "npcd_kl_fwd": [P, P, L, I, F, P, P],
+    "npcd_kl_bwd": [P, P, L, I, F, P, P, P, P],
+    "npcd_embed_adam_rows": [P, P, P, P, P, I, L, P, I, D, D, D, D, P],
     "npcd_composite_fwd": [P, P, P, P, P, L, I, P, P, P, P, I, P],
     "npcd_clamp_depth": [P, L, P, P, P],
     "npcd_composite_bwd": [P, P, P, L, I, P, P, P, P, P, P, P, P],

@@ -1,7 +1,12 @@
 """Per-object latent tables (`npcd/models/pointnerf/embeddings/{embedding,variational_embedding}.py`,
-`npcd/utils/flex_embedding.py`).  OUT OF SCOPE of the accelerated path (plain ``nn.Embedding`` lookups producing the
-``[B,512,3]`` / ``[B,512,32]`` inputs); mirrored only so ``PointNeRF`` keeps the reference's interface and checkpoint
-layout (weights travel as ``_extra_state``; SURVEY.md §5 checkpoint row)."""
+`npcd/utils/flex_embedding.py`): same classes, constructor arguments and checkpoint layout (weights travel as ``_extra_state``;
+SURVEY.md §5 checkpoint row).
+
+SURVEY.md section 8(f) N2: on CUDA the variational lookup + reparameterised sampling (+ mean / log-var / std for the losses) is ONE
+kernel (`npcd_embed_fwd`) with a hand-written backward (`npcd_embed_bwd`) into a COMPACT ``[B, P*2F]`` row gradient.  With
+``row_sparse_grad = False`` (default, what an unchanged `torch.optim.Adam(model.parameters())` loop needs) that gradient is scattered
+into the dense ``weight.grad`` like `nn.Embedding`'s backward; with ``row_sparse_grad = True`` (set by `optim.PointNeRFAdam`) it is
+left on ``weight.row_grads`` for the lazy row optimiser and the 308 MB dense gradient is never formed."""
 from __future__ import annotations
 
 import warnings
@@ -69,6 +74,45 @@ class Embedding(torch.nn.Module):
             e.eval()
 
 
+class _VarEmbedFn(torch.autograd.Function):
+    """(table, obj_idx, eps) -> feats, mean, log_var, std  [B,P,F] each; `variational_embedding.py:36-70` in one kernel."""
+
+    @staticmethod
+    def forward(ctx, table, idx, eps, P, F, sparse):
+        from .. import ops
+        from .._lib import call, ptr
+
+        B = idx.numel()
+        idx = idx.contiguous().long()
+        outs = [torch.empty((B, P, F), device=table.device) for _ in range(4)]
+        call("npcd_embed_fwd", ptr(table), ptr(idx), B, P, F, ptr(eps), *(ptr(o) for o in outs), ops._stream())
+        ops._count(1)
+        ctx.save_for_backward(idx, eps)
+        ctx.table, ctx.dims, ctx.sparse = table, (B, P, F), sparse
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g_feats, g_mean, g_lv, g_std):
+        from .. import ops
+        from .._lib import call, ptr
+
+        idx, eps = ctx.saved_tensors
+        table, (B, P, F) = ctx.table, ctx.dims
+        c = lambda g: None if g is None else g.contiguous().float()
+        d_rows = torch.empty((B, P * 2 * F), device=table.device)
+        call("npcd_embed_bwd", ptr(table.detach()), ptr(idx), B, P, F, ptr(eps), ptr(c(g_feats)), ptr(c(g_mean)), ptr(c(g_lv)),
+             ptr(c(g_std)), ptr(d_rows), ops._stream())
+        ops._count(1)
+        if ctx.sparse:
+            if getattr(table, "row_grads", None) is None:
+                table.row_grads = []
+            table.row_grads.append((idx, d_rows))
+            return None, None, None, None, None, None
+        dense = torch.zeros_like(table)
+        dense.index_add_(0, idx, d_rows)  # nn.Embedding backward: duplicates accumulate
+        return dense, None, None, None, None, None
+
+
 class VariationalEmbedding(Embedding):
     """mean || log-var table with reparameterised sampling in train mode (variational_embedding.py:36-58)."""
 
@@ -77,6 +121,20 @@ class VariationalEmbedding(Embedding):
     def __init__(self, n_kp: int, out_dim: int, n_obj: int, gpu: bool = True) -> None:
         super().__init__(n_kp, out_dim, n_obj, gpu)
         self.sample_embedding = True
+        self.row_sparse_grad = False
+
+    def fused(self, idx: Tensor, eps: Tensor = None):
+        """One launch for everything `PointNeRF.forward` needs: (feats, mean, log_var, std).  ``eps``: injected N(0,1) tensor
+        [B,P,F] (parity tests); drawn on the device in train mode otherwise; eval mode returns feats = mean."""
+        w = self.get_emb().weight
+        if not (self.gpu and w.is_cuda):
+            raise RuntimeError("the fused embedding step needs the table on the GPU (gpu=True, model.cuda())")
+        if self.sample_embedding and eps is None:
+            eps = torch.randn((idx.numel(), self.n_kp, self.out_dim), device=w.device)
+        if not self.sample_embedding:
+            eps = None
+        return _VarEmbedFn.apply(w, idx, None if eps is None else eps.contiguous().float(), self.n_kp, self.out_dim,
+                                 self.row_sparse_grad)
 
     def train(self, mode=True):
         super().train(mode)

@@ -71,14 +71,19 @@ class PointNeRF(nn.Module):
             return w.reshape(w.shape[0], self.opt.model.kp.num, 2 * f)[:, :, :f]
         return w.reshape(w.shape[0], self.opt.model.kp.num, f)
 
-    def forward(self, obj_idx: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor, sample_rays: bool):
-        feats = self.feats(idx=obj_idx)
+    def forward(self, obj_idx: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor, sample_rays: bool, feats_eps=None):
         coords = self.coords(idx=obj_idx)
         self.voxel_grid.set_pointset(coords.detach(), None)
-        if hasattr(self.feats, "get_mean_log_var_std"):
+        if hasattr(self.feats, "fused") and self.feats.get_emb().weight.is_cuda:
+            # lookup + sampling + mean/log-var/std in one kernel (pointnerf.py:57-66 does three lookups)
+            feats, mean, log_var, std = self.feats.fused(obj_idx, eps=feats_eps)
+            aux = {"coords": coords, "feats": mean, "feats_mean": mean, "feats_log_var": log_var, "feats_std": std}
+        elif hasattr(self.feats, "get_mean_log_var_std"):
+            feats = self.feats(idx=obj_idx)
             mean, log_var, std = self.feats.get_mean_log_var_std(idx=obj_idx)
             aux = {"coords": coords, "feats": mean, "feats_mean": mean, "feats_log_var": log_var, "feats_std": std}
         else:
+            feats = self.feats(idx=obj_idx)
             aux = {"coords": coords, "feats": feats}
         pred = self.renderer(coords, feats, extrinsics, intrinsics, resolution=self.opt.sizes.default_resolution,
                              sample=sample_rays, return_channels=True)

@@ -105,3 +105,28 @@ def test_tv_loss_self_query(syn):
     np.testing.assert_allclose(tv, g["tv"], rtol=2e-6, atol=0)
     assert abs(float(tv.mean()) - float(g["loss"])) < 1e-6 * float(g["loss"])
     np.testing.assert_allclose(grad, g["grad_feats"], atol=2e-6 * np.abs(g["grad_feats"]).max(), rtol=0)
+
+
+def test_embedding_step_oracle(syn):
+    """Embedding-side step: variational sampling, KL term, embedding-row gradient and DENSE Adam against the
+    unmodified reference modules + torch.optim.Adam (tests/golden/make_golden_embed.py)."""
+    import os
+
+    from oracle import embedding_oracle as eo
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "embed_adam.npz"))
+    n_obj, P, F = (int(x) for x in g["dims"])
+    lr, kw = float(g["lr"]), float(g["kl_weight"])
+    w = g["table0"].copy()
+    m, v = np.zeros_like(w), np.zeros_like(w)
+    for t, batch in enumerate(g["batches"]):
+        B = len(batch)
+        np.testing.assert_allclose(eo.variational_forward(w, batch, P, F, g[f"eps{t}"]), g[f"feats{t}"], atol=1e-6, rtol=0)
+        np.testing.assert_allclose(eo.kl_pointwise(w, batch, P, F, kw), g[f"kld{t}"], rtol=2e-6, atol=1e-7)
+        # loss = sum(feats * c) + mean(kld)  (make_golden_embed.py)
+        grad = eo.dense_row_grad(w, batch, P, F, g[f"eps{t}"], g[f"c{t}"], np.full((B, P), 1.0 / (B * P)), kw, n_obj)
+        np.testing.assert_allclose(grad, g[f"grad{t}"], atol=2e-6 * np.abs(g[f"grad{t}"]).max(), rtol=0)
+        eo.adam_dense_step(w, m, v, g[f"grad{t}"], t + 1, lr)
+        np.testing.assert_allclose(w, g[f"table{t + 1}"], atol=2e-7, rtol=0)
+    np.testing.assert_allclose(m, g["exp_avg"], atol=1e-7 * np.abs(g["exp_avg"]).max(), rtol=1e-6)
+    np.testing.assert_allclose(v, g["exp_avg_sq"], atol=1e-7 * np.abs(g["exp_avg_sq"]).max(), rtol=1e-6)
