@@ -312,10 +312,24 @@ def run_ours(args):
             "peak_gbs": peaks["hbm"],
         },
     }
-    if roofline["hbm_path"]["non_mlp_ms_per_step"]:
-        gbs = roofline["hbm_path"]["algorithmic_bytes_per_step"] / (roofline["hbm_path"]["non_mlp_ms_per_step"] * 1e-3) / 1e9
-        roofline["hbm_path"]["achieved_gbs"] = gbs
-        roofline["hbm_path"]["frac"] = gbs / peaks["hbm"]
+    # per-stage device times of the HBM-side kernels (CUDA events around each C-ABI call, same stream), SURVEY.md section 8(d):
+    # hbm_fraction = sum of algorithmic bytes / sum of the times of THOSE kernels / HBM peak
+    stage = {}
+    for (a, b, tag) in prof:
+        if tag not in ("pair_mlp", "heads"):
+            stage[tag] = stage.get(tag, 0.0) + a.elapsed_time(b) / args.steps
+    hp = roofline["hbm_path"]
+    hp["stage_ms_per_step"] = stage
+    kern_ms = sum(stage.values())
+    if kern_ms > 0:
+        query_ms = stage.get("march", 0.0) + stage.get("scan", 0.0) + stage.get("knn", 0.0)
+        hp["kernels_ms_per_step"] = kern_ms
+        hp["host_gap_ms_per_step"] = hp["non_mlp_ms_per_step"] - kern_ms if hp["non_mlp_ms_per_step"] else None
+        hp["achieved_gbs"] = hp["algorithmic_bytes_per_step"] / (kern_ms * 1e-3) / 1e9
+        hp["frac"] = hp["achieved_gbs"] / peaks["hbm"]
+        hp["query_gbs"] = (44.0 * S) / (query_ms * 1e-3) / 1e9 if query_ms > 0 else None  # march + scan + kNN: 44 B per kept sample out
+        cm = stage.get("composite", 0.0)
+        hp["composite_gbs"] = (20.0 * S + BYTES_PER_RAY * n_rays) / (cm * 1e-3) / 1e9 if cm > 0 else None
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -366,36 +380,47 @@ def run_train(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, T, n_sub = 8, 50, 112
-    model = PointNeRF(B, 32, 512, False).to(dev)
+    N_OBJ = 2347  # SRN-cars training set (configs/npcd_srncars.yaml:4): the latent table is 2347 x 512 x 64 floats = 308 MB
+    model = PointNeRF(N_OBJ, 32, 512, False).to(dev)
     sd = model.state_dict()
+    my_objs = [rank * B + o for o in range(B)]  # object shard of this rank
     with torch.no_grad():
         for k, v in syn.make_weights(0).items():
             sd[k].copy_(torch.from_numpy(v))
-        coords, feats = syn.make_clouds([rank * B + o for o in range(B)])  # object shard of this rank
-        model.set_all_coords(torch.from_numpy(coords).to(dev))
+        coords, feats = syn.make_clouds(my_objs)
+        model.coords.get_emb().weight.view(N_OBJ, 512, 3)[my_objs] = torch.from_numpy(coords).to(dev)
         w = model.feats.get_emb().weight
         w.zero_()
-        w.view(B, 512, 64)[:, :, :32] = torch.from_numpy(feats).to(dev)
-        w.view(B, 512, 64)[:, :, 32:] = -4.0  # log-variance
+        w.view(N_OBJ, 512, 64)[:, :, 32:] = -4.0  # log-variance
+        w.view(N_OBJ, 512, 64)[my_objs, :, :32] = torch.from_numpy(feats).to(dev)
     model.train()
     poses, intr = syn.load_cameras()
     views = np.arange(0, 250, 5)[:T]
     extr = torch.from_numpy(np.broadcast_to(poses[views][None], (B, T, 4, 4)).copy()).to(dev)
     K = torch.from_numpy(np.broadcast_to(intr[views][None], (B, T, 3, 3)).copy()).to(dev)
     gt = torch.rand((B, T, RES * RES, 3), device=dev)
-    obj = torch.arange(B, device=dev)
+    obj = torch.tensor(my_objs, device=dev)
+    import types
+
+    from npcd_b200.losses import NeuralPointCloudKLLoss, NeuralPointCloudTVLoss
+    from npcd_b200.optim import PointNeRFAdam
+
     bucket = parallel.GradBucket(parallel.mlp_parameters(model))
-    params = [p for p in model.parameters() if p.requires_grad]
+    # the full autodecoder step of the reference trainer (npcd/train/pointnerf_training.py:139-152): image + KL + TV losses
+    # (npcd/losses/pointnerf_loss.py:40-47), backward, Adam (lazy dense-equivalent rows on the latent table)
+    opt = PointNeRFAdam(model, lr=1e-3)
+    holder = types.SimpleNamespace(pointnerf=model)
+    kl_loss, tv_loss = NeuralPointCloudKLLoss(holder, 1e-3, False), NeuralPointCloudTVLoss(holder, 1e-3, False)
     stats = []
 
     def step():
-        for p in params:
-            p.grad = None
-        pred, _ = model(obj, K, extr, True)
+        opt.zero_grad()
+        pred, aux = model(obj, K, extr, True)
         target = torch.gather(gt, 2, pred.ray_idx.expand(-1, -1, -1, 3))
-        loss = ((pred.channels - target) ** 2).mean()
+        loss = ((pred.channels - target) ** 2).mean() + kl_loss(None, pred, aux, 0)[0] + tv_loss(None, pred, aux, 0)[0]
         loss.backward()
         bucket.all_reduce_mean()
+        opt.step()
         stats.append((int(model.renderer.last_stats["S"]), pred.channels.shape[2]))
         return loss
 
@@ -427,10 +452,10 @@ def run_train(args):
             "metric": "train_rays_per_sec", "value": rays / (ms_total * 1e-3), "unit": "rays/s (sampled rays marched)", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": model.field.compute_dtype(), "data": "synthetic",
-            "config": {"workload": "PointNeRF autodecoder training step, forward + backward (+ NCCL all-reduce of the MLP gradients when "
-                                   "N > 1), 8 objects x 50 views x 112 sampled rays per GPU (BASELINE.json configs[2]/[3])",
+            "config": {"workload": "PointNeRF autodecoder training step: forward, image + KL + TV losses, backward, (NCCL all-reduce of the MLP "
+                                   "gradients when N > 1), Adam step; 8 objects x 50 views x 112 sampled rays per GPU (BASELINE.json configs[2]/[3])",
                        "kept_samples_per_step_per_gpu": float(np.mean([s for s, _ in stats])),
-                       "rays_kept_per_view": float(np.mean([n for _, n in stats])), "optimizer": "none (gradients only)",
+                       "rays_kept_per_view": float(np.mean([n for _, n in stats])), "optimizer": "Adam: lazy dense-equivalent rows on the latent table + torch Adam on the 24 MLP tensors",
                        "l2": "per-step stash (~1 GB) >> L2"},
             "clocks": clocks, "gpu_launches": ops.LAUNCHES - launches0, "loss": float(loss.detach()),
         }

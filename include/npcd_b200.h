@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define NPCD_B200_ABI_VERSION 1
+#define NPCD_B200_ABI_VERSION 2
 
 const char* npcd_last_error(void);
 int npcd_abi_version(void);
@@ -43,6 +43,10 @@ int npcd_grid_dims(int* cells, int* words);
 int npcd_grid_build(const float* kp_pos, int n_obj, int n_points, int* cell_start, float* sorted_pts, unsigned* occ_bits,
                     float* aabb /* optional [n_obj,6]: box of the dilated occupied cells, +-inf where it meets the cube border */,
                     void* stream);
+/* Sub-cell masks for the marcher (optional): masks [n_obj, cells, 2] uint64 = (sure, maybe) per grid cell, one bit per 1/48-edge
+ * sub-cell: a depth sample in a `sure` sub-cell has a point within `radius` for certain, one outside every `maybe` sub-cell has
+ * none; only the shell in between takes the exact test, so results are unchanged.  Must be built with the radius later queried.  */
+int npcd_grid_build_masks(const float* kp_pos, int n_obj, int n_points, float radius, void* masks, void* stream);
 
 /* ---- march + exact radius-kNN: replaces Aggregator.query_keypoints (fields/aggregators/aggregator.py:25-76) and
  * torch_knnquery.VoxelGrid.query (call site aggregator.py:63), with the depth sampling that feeds them
@@ -57,7 +61,9 @@ int npcd_march_count(const float* cam_centers, const float* dirs, const float* r
                      const float* jitter, long long n_rays, int rays_per_view, int views_per_obj, int n_points,
                      const int* cell_start, const float* sorted_pts, const unsigned* occ_bits,
                      const float* aabb /* optional, from npcd_grid_build: samples outside the box are skipped untested */,
-                     float radius, int max_shading_pts, unsigned* valid_bits, int* ray_count, void* stream);
+                     const void* fine_masks /* optional, from npcd_grid_build_masks (same radius) */,
+                     float radius, int max_shading_pts, unsigned* valid_bits, int* ray_count,
+                     int impl /* 0 auto; 1 generic global-memory kernels; 2 shared-memory kernels (n_points <= 2048) */, void* stream);
 int npcd_scan_workspace_bytes(long long n, size_t* bytes);
 int npcd_scan_counts(const int* ray_count, const int* ray_ids, long long n, long long* ray_offset, void* workspace,
                      size_t workspace_bytes, void* stream);
@@ -68,7 +74,8 @@ int npcd_knn_points(const float* x, const int* query_obj, long long n, int queri
 int npcd_knn_fill(const float* cam_centers, const float* dirs, const float* ray_start, const float* ray_end, const float* jitter,
                   const int* ray_ids, long long n_sel, const long long* ray_offset, const unsigned* valid_bits, int rays_per_view,
                   int views_per_obj, int n_points, const int* cell_start, const float* sorted_pts, float radius,
-                  long long capacity, int* nbr_idx, float* sample_pos, int* sample_ray, void* stream);
+                  long long capacity, int* nbr_idx, float* sample_pos, int* sample_ray, int impl /* as npcd_march_count */,
+                  void* stream);
 
 /* ---- field: gather + posenc + pair MLP + aggregation + density/colour heads -------------------------------------------------
  * Replaces aggregators.MLP.get_local_feat / aggregate_local_feat (fields/aggregators/mlp.py:36-125), Aggregator.get_keypoint_data

@@ -10,7 +10,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnpcd_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _lock = threading.Lock()
 _lib = None
@@ -86,10 +86,11 @@ SIGNATURES = {
     "npcd_rays_generate": [P, P, I, I, P, I, F, P, P, P, P, P, P, P],
     "npcd_grid_dims": [P, P],
     "npcd_grid_build": [P, I, I, P, P, P, P, P],
-    "npcd_march_count": [P, P, P, P, P, L, I, I, I, P, P, P, P, F, I, P, P, P],
+    "npcd_grid_build_masks": [P, I, I, F, P, P],
+    "npcd_march_count": [P, P, P, P, P, L, I, I, I, P, P, P, P, P, F, I, P, P, I, P],
     "npcd_scan_workspace_bytes": [L, P],
     "npcd_scan_counts": [P, P, L, P, P, C.c_size_t, P],
-    "npcd_knn_fill": [P, P, P, P, P, P, L, P, P, I, I, I, P, P, F, L, P, P, P, P],
+    "npcd_knn_fill": [P, P, P, P, P, P, L, P, P, I, I, I, P, P, F, L, P, P, P, I, P],
     "npcd_knn_points": [P, P, L, I, I, P, P, F, P, P],
     "npcd_field_simt_fwd": [P, P, P, P, P, L, P, P, P, P, I, I, P],
     "npcd_tc_pack_weights": [P, I, P, I, F, P, P],

@@ -87,7 +87,74 @@ __global__ void __launch_bounds__(512) k_grid_build(const float* __restrict__ kp
   }
 }
 
+// Sub-cell classification for the marcher: every grid cell is split into 4^3 sub-cells of edge 1/48 and gets two 64-bit masks
+// (bit (sz*4+sy)*4+sx):
+//   sure  : some point is closer than r - margin to EVERY position of the sub-cell  -> a sample in it is valid, no exact test needed
+//   maybe : some point is closer than r + margin to SOME position of the sub-cell   -> a sample outside every maybe sub-cell is invalid
+// Only samples in maybe-but-not-sure sub-cells (a shell of ~0.036 around the surface of the union of r-balls) take the exact test,
+// so the classification never changes a result (the margin, 2e-5, is 100x the rounding of the fp32 distance and of the sub-cell
+// assignment).  Masks are zeroed by the host wrapper (memset) before the kernel ORs into them.
+constexpr int kFine = kGrid * 4;
+constexpr int kMaskLayers = 12;  // fine z layers a point can reach: 2 (r + margin) * 48 + 3 <= 12 for r <= 1/12
+
+// one thread per (point, fine z layer): tests the <= 12 x 12 sub-cells of that layer, ORs one mask pair per touched grid cell
+__global__ void __launch_bounds__(128) k_grid_masks(const float* __restrict__ kp_pos, int P, float radius,
+                                                    unsigned long long* __restrict__ masks /* [n_obj, cells, 2] = (sure, maybe) */) {
+  const int b = blockIdx.y;
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= P * kMaskLayers) return;
+  const int p = item / kMaskLayers, layer = item % kMaskLayers;
+  const float* pts = kp_pos + (size_t)b * P * 3;
+  unsigned long long* m = masks + (size_t)b * kGridCells * 2;
+  const float margin = 2e-5f;
+  const float r_maybe = radius + margin, r_sure = radius - margin;
+  const float r2_maybe = r_maybe * r_maybe, r2_sure = r_sure > 0.f ? r_sure * r_sure : 0.f;
+  const float h = 2.0f / kFine;
+  const float c3[3] = {pts[p * 3], pts[p * 3 + 1], pts[p * 3 + 2]};
+  int lo[3], hi[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = min(max((int)floorf((c3[a] - r_maybe + 1.0f) * (0.5f * kFine)) - 1, 0), kFine - 1);
+    hi[a] = min(max((int)floorf((c3[a] + r_maybe + 1.0f) * (0.5f * kFine)) + 1, 0), kFine - 1);
+  }
+  const int fz = lo[2] + layer;
+  if (fz > hi[2]) return;
+  const int cz = fz >> 2;
+  const float zl = (float)fz * h - 1.0f, zh = (float)(fz + 1) * h - 1.0f;
+  const float zn = fmaxf(fmaxf(zl - c3[2], c3[2] - zh), 0.f), zx = fmaxf(c3[2] - zl, zh - c3[2]);
+  for (int cy = lo[1] >> 2; cy <= hi[1] >> 2; ++cy)
+    for (int cx = lo[0] >> 2; cx <= hi[0] >> 2; ++cx) {
+      unsigned long long sure = 0ull, maybe = 0ull;
+      for (int fy = max(lo[1], cy * 4); fy <= min(hi[1], cy * 4 + 3); ++fy) {
+        const float yl = (float)fy * h - 1.0f, yh = (float)(fy + 1) * h - 1.0f;
+        const float yn = fmaxf(fmaxf(yl - c3[1], c3[1] - yh), 0.f), yx = fmaxf(c3[1] - yl, yh - c3[1]);
+        for (int fx = max(lo[0], cx * 4); fx <= min(hi[0], cx * 4 + 3); ++fx) {
+          const float xl = (float)fx * h - 1.0f, xh = (float)(fx + 1) * h - 1.0f;
+          const float xn = fmaxf(fmaxf(xl - c3[0], c3[0] - xh), 0.f), xx = fmaxf(c3[0] - xl, xh - c3[0]);
+          const int bit = ((fz & 3) * 4 + (fy & 3)) * 4 + (fx & 3);
+          if (xn * xn + yn * yn + zn * zn < r2_maybe) maybe |= 1ull << bit;
+          if (xx * xx + yx * yx + zx * zx < r2_sure) sure |= 1ull << bit;
+        }
+      }
+      const int c = (cz * kGrid + cy) * kGrid + cx;
+      if (sure) atomicOr(m + 2 * c, sure);
+      if (maybe) atomicOr(m + 2 * c + 1, maybe);
+    }
+}
+
 }  // namespace npcd
+
+extern "C" int npcd_grid_build_masks(const float* kp_pos, int n_obj, int n_points, float radius, void* masks, void* stream) {
+  using namespace npcd;
+  NPCD_CHECK_ARG(kp_pos && masks, "null pointer");
+  NPCD_CHECK_ARG(n_obj >= 0 && n_points > 0, "bad n_obj / n_points");
+  NPCD_CHECK_ARG(radius > 0.f && radius <= 2.0f / kGrid, "radius must be in (0, 1/12] (grid cell edge)");
+  if (n_obj == 0) return 0;
+  cudaMemsetAsync(masks, 0, (size_t)n_obj * kGridCells * 2 * sizeof(unsigned long long), (cudaStream_t)stream);
+  k_grid_masks<<<dim3((n_points * kMaskLayers + 127) / 128, n_obj), 128, 0, (cudaStream_t)stream>>>(kp_pos, n_points, radius,
+                                                                                                      (unsigned long long*)masks);
+  return check_launch("npcd_grid_build_masks");
+}
 
 extern "C" int npcd_grid_build(const float* kp_pos, int n_obj, int n_points, int* cell_start, float* sorted_pts,
                                unsigned* occ_bits, float* aabb, void* stream) {

@@ -212,12 +212,403 @@ __global__ void __launch_bounds__(128) k_knn_fill(const float* __restrict__ cam,
   if (sample_ray) sample_ray[s] = (int)sel;
 }
 
+
+// =====================================================================================================================================
+// Shared-memory fast path (n_points <= kSmemMaxPoints; the reference uses 512).  Same results bit for bit as the kernels above, which
+// stay as the generic path and as the cross-check in the tests.
+//   * a CTA owns a chunk of rays of ONE object and first copies that object's grid into shared memory: sorted points (16 B each),
+//     CSR offsets narrowed to u16, dilated-occupancy bits -- 37 KB at P = 512; every lookup of the scans below is an LDS;
+//   * the 9 row ranges of a neighbourhood scan are fetched up front (18 independent LDS), the radius test compares the squared
+//     distance with the largest float T whose correctly rounded root is < r  (sqrt_rn(d2) < r  <=>  d2 <= T), so the square root is
+//     only taken for accepted neighbours (it orders them);
+//   * k_march_count_s: pass 1, warp per ray: sub-cell masks (grid.cu) classify each depth sample as valid / invalid / uncertain;
+//     uncertain samples of the whole CTA go to a shared queue (warp-aggregated append).  Pass 2: all threads drain the queue, one
+//     exact early-exit scan per item at full lane utilisation, hits OR-ed into the shared validity words.  Pass 3: coalesced store.
+//   * k_knn_fill_s: thread per kept sample of the chunk (its ray found by a binary search over the chunk's offsets in shared memory).
+constexpr int kSmemMaxPoints = 2048;
+constexpr int kChunk = 256;       // rays per CTA
+constexpr int kQueue = 4096;      // uncertain samples queued per CTA (overflow: tested in line by the owning lane)
+constexpr int kFineRes = kGrid * 4;
+
+struct SGrid {
+  const float4* pts;     // [P]
+  const uint16_t* cs;    // [kGridCells + 1]
+  const uint32_t* occ;   // [kGridWords]
+};
+
+__host__ __device__ inline size_t sgrid_bytes(int P) {
+  return (size_t)P * 16 + (((size_t)(kGridCells + 1) * 2 + 15) / 16) * 16 + (size_t)kGridWords * 4;
+}
+
+__device__ __forceinline__ SGrid sgrid_load(uint8_t* smem, int P, const int* __restrict__ cell_start, const float4* __restrict__ sorted_pts,
+                                            const uint32_t* __restrict__ occ_bits) {
+  float4* pts = reinterpret_cast<float4*>(smem);
+  uint16_t* cs = reinterpret_cast<uint16_t*>(smem + (size_t)P * 16);
+  uint32_t* occ = reinterpret_cast<uint32_t*>(smem + (size_t)P * 16 + (((size_t)(kGridCells + 1) * 2 + 15) / 16) * 16);
+  for (int i = threadIdx.x; i < P; i += blockDim.x) pts[i] = __ldg(sorted_pts + i);
+  for (int i = threadIdx.x; i <= kGridCells; i += blockDim.x) cs[i] = (uint16_t)__ldg(cell_start + i);
+  if (occ_bits)
+    for (int i = threadIdx.x; i < kGridWords; i += blockDim.x) occ[i] = __ldg(occ_bits + i);
+  return SGrid{pts, cs, occ};
+}
+
+// f(d2, original index) for every point with d2 <= T in the 27 cells around (x,y,z); f returns true to stop.
+template <typename F>
+__device__ __forceinline__ void scan_smem(const SGrid& g, float x, float y, float z, float T, F&& f) {
+  const int cx = grid_coord(x), cy = grid_coord(y), cz = grid_coord(z);
+  const int x0 = max(cx - 1, 0), x1 = min(cx + 1, kGrid - 1) + 1;
+  int rs[9], re[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const int qz = cz + k / 3 - 1, qy = cy + k % 3 - 1;
+    const bool ok = qz >= 0 && qz < kGrid && qy >= 0 && qy < kGrid;
+    const int base = ok ? (qz * kGrid + qy) * kGrid : 0;
+    rs[k] = ok ? (int)g.cs[base + x0] : 0;
+    re[k] = ok ? (int)g.cs[base + x1] : 0;
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    for (int i = rs[k]; i < re[k]; ++i) {
+      const float4 p = g.pts[i];
+      const float dx = __fsub_rn(x, p.x), dy = __fsub_rn(y, p.y), dz = __fsub_rn(z, p.z);
+      const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      if (d2 <= T)
+        if (f(d2, __float_as_int(p.w))) return;
+    }
+  }
+}
+
+__device__ __forceinline__ bool any_within(const SGrid& g, float x, float y, float z, float T) {
+  bool hit = false;
+  scan_smem(g, x, y, z, T, [&](float, int) { hit = true; return true; });
+  return hit;
+}
+
+__device__ __forceinline__ int fine_coord(float v) {
+  int c = (int)floorf((v + 1.0f) * (0.5f * kFineRes));
+  return min(max(c, 0), kFineRes - 1);
+}
+
+__global__ void __launch_bounds__(kChunk) k_march_count_s(const float* __restrict__ cam, const float* __restrict__ dirs,
+                                                          const float* __restrict__ start, const float* __restrict__ end,
+                                                          const float* __restrict__ jitter, int rays_per_view, int views_per_obj,
+                                                          int chunks_per_obj, int P, const int* __restrict__ cell_start,
+                                                          const float4* __restrict__ sorted_pts, const uint32_t* __restrict__ occ_bits,
+                                                          const float* __restrict__ aabb, const ulonglong2* __restrict__ masks,
+                                                          float T, int max_shading, uint32_t* __restrict__ valid_bits,
+                                                          int* __restrict__ ray_count, int rays_per_cta) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ uint32_t valid_s[kChunk * 4];
+  __shared__ uint16_t queue[kQueue];
+  __shared__ int q_count, q_valid;
+  const int obj = blockIdx.x / chunks_per_obj, chunk = blockIdx.x % chunks_per_obj;
+  const long long rays_per_obj = (long long)rays_per_view * views_per_obj;
+  const long long ray0 = obj * rays_per_obj + (long long)chunk * rays_per_cta;
+  const int n_local = (int)min((long long)rays_per_cta, rays_per_obj - (long long)chunk * rays_per_cta);
+  const SGrid g = sgrid_load(smem_raw, P, cell_start + (size_t)obj * (kGridCells + 1), sorted_pts + (size_t)obj * P,
+                             occ_bits + (size_t)obj * kGridWords);
+  const ulonglong2* mk = masks ? masks + (size_t)obj * kGridCells : nullptr;
+  for (int i = threadIdx.x; i < kChunk * 4; i += blockDim.x) valid_s[i] = 0u;
+  if (threadIdx.x == 0) { q_count = 0; q_valid = kQueue; }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  // position of depth sample i of local ray r (bit-exact restatement shared by all passes)
+  auto sample_xyz = [&](long long ray, int i, float& x, float& y, float& z) {
+    const int view = (int)(ray / rays_per_view);
+    const float ox = __ldg(cam + view * 3), oy = __ldg(cam + view * 3 + 1), oz = __ldg(cam + view * 3 + 2);
+    const float t = sample_depth(__ldg(start + ray), __ldg(end + ray), i, jitter ? jitter + ray * kDepthRes : nullptr);
+    x = axpy_rn(ox, t, __ldg(dirs + ray * 3));
+    y = axpy_rn(oy, t, __ldg(dirs + ray * 3 + 1));
+    z = axpy_rn(oz, t, __ldg(dirs + ray * 3 + 2));
+  };
+
+  // ---- pass 1: classify ----
+  for (int r = warp; r < n_local; r += n_warps) {
+    const long long ray = ray0 + r;
+    const int view = (int)(ray / rays_per_view);
+    const float ox = __ldg(cam + view * 3), oy = __ldg(cam + view * 3 + 1), oz = __ldg(cam + view * 3 + 2);
+    const float dx = __ldg(dirs + ray * 3), dy = __ldg(dirs + ray * 3 + 1), dz = __ldg(dirs + ray * 3 + 2);
+    const float t0 = __ldg(start + ray), t1 = __ldg(end + ray);
+    const float* jit = jitter ? jitter + ray * kDepthRes : nullptr;
+    int i_lo = 0, i_hi = kDepthRes - 1;  // conservative sample range inside the object's box (see k_march_count)
+    if (aabb) {
+      const float* bx = aabb + (size_t)obj * 6;
+      float tmin = -INFINITY, tmax = INFINITY;
+      bool miss = false;
+      const float o3[3] = {ox, oy, oz}, d3[3] = {dx, dy, dz};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float lo = __ldg(bx + a), hi = __ldg(bx + 3 + a);
+        if (fabsf(d3[a]) < 1e-12f) {
+          miss |= (o3[a] < lo || o3[a] > hi);
+        } else {
+          const float inv = 1.0f / d3[a];
+          const float ta = (lo - o3[a]) * inv, tb = (hi - o3[a]) * inv;
+          tmin = fmaxf(tmin, fminf(ta, tb));
+          tmax = fminf(tmax, fmaxf(ta, tb));
+        }
+      }
+      const float span = t1 - t0;
+      if (miss || tmin > tmax || !(span > 0.f)) {
+        if (miss || tmin > tmax) i_hi = -1;
+      } else {
+        const float sc = (float)(kDepthRes - 1) / span;
+        const float flo = (tmin - t0) * sc - 2.0f, fhi = (tmax - t0) * sc + 2.0f;
+        i_lo = flo <= 0.f ? 0 : (flo >= (float)kDepthRes ? kDepthRes : (int)flo);
+        i_hi = fhi >= (float)(kDepthRes - 1) ? kDepthRes - 1 : (fhi < 0.f ? -1 : (int)fhi + 1);
+        i_hi = min(i_hi, kDepthRes - 1);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j * 32 > i_hi || j * 32 + 31 < i_lo) continue;  // warp-uniform
+      const int i = j * 32 + lane;
+      const float t = sample_depth(t0, t1, i, jit);
+      const float x = axpy_rn(ox, t, dx), y = axpy_rn(oy, t, dy), z = axpy_rn(oz, t, dz);
+      bool sure = false, unc = false;
+      if (i >= i_lo && i <= i_hi) {
+        const int fx = fine_coord(x), fy = fine_coord(y), fz = fine_coord(z);
+        const int c = ((fz >> 2) * kGrid + (fy >> 2)) * kGrid + (fx >> 2);  // == grid_coord cell: scaling by 4 commutes with rounding
+        if ((g.occ[c >> 5] >> (c & 31)) & 1u) {
+          // samples pushed outside the cube (jitter, rounding) are clamped into border sub-cells they do not lie in: exact test
+          const bool border = fx == 0 || fy == 0 || fz == 0 || fx == kFineRes - 1 || fy == kFineRes - 1 || fz == kFineRes - 1;
+          if (mk && !border) {
+            const ulonglong2 m = __ldg(mk + c);
+            const int bit = ((fz & 3) * 4 + (fy & 3)) * 4 + (fx & 3);
+            sure = (m.x >> bit) & 1ull;
+            unc = !sure && ((m.y >> bit) & 1ull);
+          } else {
+            unc = true;
+          }
+        }
+      }
+      const uint32_t w_sure = __ballot_sync(0xffffffffu, sure);
+      const uint32_t w_unc = __ballot_sync(0xffffffffu, unc);
+      if (lane == 0 && w_sure) valid_s[r * 4 + j] = w_sure;
+      __syncwarp();  // the plain store is ordered before the atomicOr of the overflow path below
+      if (w_unc) {
+        const int n = __popc(w_unc);
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&q_count, n);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base + n <= kQueue) {
+          if (unc) queue[base + __popc(w_unc & ((1u << lane) - 1u))] = (uint16_t)((r << 7) | i);
+        } else {
+          if (lane == 0) atomicMin(&q_valid, base);
+          if (unc && any_within(g, x, y, z, T)) atomicOr(&valid_s[r * 4 + j], 1u << lane);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- pass 2: exact test of the queued samples, one per thread ----
+  const int n_items = min(q_count, q_valid);
+  for (int q = threadIdx.x; q < n_items; q += blockDim.x) {
+    const int item = queue[q];
+    const int r = item >> 7, i = item & 127;
+    float x, y, z;
+    sample_xyz(ray0 + r, i, x, y, z);
+    if (any_within(g, x, y, z, T)) atomicOr(&valid_s[r * 4 + (i >> 5)], 1u << (i & 31));
+  }
+  __syncthreads();
+  // ---- pass 3: store ----
+  for (int i = threadIdx.x; i < n_local * 4; i += blockDim.x) valid_bits[ray0 * 4 + i] = valid_s[i];
+  for (int r = threadIdx.x; r < n_local; r += blockDim.x) {
+    const int total = __popc(valid_s[r * 4]) + __popc(valid_s[r * 4 + 1]) + __popc(valid_s[r * 4 + 2]) + __popc(valid_s[r * 4 + 3]);
+    ray_count[ray0 + r] = min(total, max_shading);
+  }
+}
+
+// <= 8 nearest points within r, ascending (dist, index), built from what ncu showed on the first versions of this kernel:
+//   * a direct 8-deep sorted insertion inside the scan makes the whole warp execute it on nearly every iteration (some lane accepts
+//     a point almost every time): the scan only APPENDS accepted points (squared distance, index) to a per-thread column of shared
+//     memory; selection runs afterwards, converged: a 19-comparator sorting network over the first 8 entries (the square root that
+//     orders neighbours is taken here), sorted insertion of the rest;
+//   * 40 % of the samples of a surface-like cloud have >= 10 points within r: the column holds kCand = 24; beyond that (never seen
+//     on the benchmark clouds) the sample is redone by the out-of-line generic scan;
+//   * looping row range by row range leaves 12 of 32 lanes active (trip counts differ per lane and range): the 9 (start, end) pairs go
+//     to a per-thread shared-memory column and ONE flattened loop walks them, every active lane testing one point per iteration;
+//   * the selection code must exist once: 9 inlined copies thrashed the instruction cache (23 warps stalled on no_instruction).
+constexpr int kCand = 24;
+
+// out-of-line generic scan: rays whose object is not the one held in shared memory, and candidate-column overflow
+__device__ __noinline__ void select_and_store_foreign(const int* cell_start, const float4* sorted_pts, float x, float y, float z,
+                                                      float radius, int base, int* out) {
+  GridView gv{cell_start, sorted_pts, nullptr};
+  select_and_store(gv, x, y, z, radius, base, out);
+}
+
+#define NPCD_CE(a, b)                                     \
+  {                                                       \
+    const unsigned long long lo_ = min(best[a], best[b]); \
+    best[b] = max(best[a], best[b]);                      \
+    best[a] = lo_;                                        \
+  }
+
+// returns false when more than kCand points lie within r (caller falls back to the generic scan)
+__device__ __forceinline__ bool select_and_store_s(const float4* __restrict__ pts_s, const int* __restrict__ cs, float x, float y, float z,
+                                                   float T, int base, int* __restrict__ out, float* __restrict__ cand_d2,
+                                                   uint16_t* __restrict__ cand_idx, uint32_t* __restrict__ range_s) {
+  const int cx = grid_coord(x), cy = grid_coord(y), cz = grid_coord(z);
+  const int x0 = max(cx - 1, 0), x1 = min(cx + 1, kGrid - 1) + 1;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {  // 18 independent loads (L1-resident CSR offsets), packed (start | end << 16)
+    const int qz = cz + k / 3 - 1, qy = cy + k % 3 - 1;
+    const bool ok = qz >= 0 && qz < kGrid && qy >= 0 && qy < kGrid;
+    const int rb = ok ? (qz * kGrid + qy) * kGrid : 0;
+    const uint32_t st = ok ? (uint32_t)__ldg(cs + rb + x0) : 0u, en = ok ? (uint32_t)__ldg(cs + rb + x1) : 0u;
+    range_s[k * kChunk] = st | (en << 16);
+  }
+  int cnt = 0, k = 0;
+  uint32_t r0 = range_s[0];
+  int i = (int)(r0 & 0xffffu), e = (int)(r0 >> 16);
+#pragma unroll 1
+  while (true) {
+    while (i >= e && k < 8) {  // next non-empty range
+      ++k;
+      r0 = range_s[k * kChunk];
+      i = (int)(r0 & 0xffffu);
+      e = (int)(r0 >> 16);
+    }
+    if (i >= e) break;
+    const float4 p = pts_s[i];
+    ++i;
+    const float dx = __fsub_rn(x, p.x), dy = __fsub_rn(y, p.y), dz = __fsub_rn(z, p.z);
+    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    if (d2 <= T) {
+      if (cnt < kCand) {
+        cand_d2[cnt * kChunk] = d2;
+        cand_idx[cnt * kChunk] = (uint16_t)__float_as_int(p.w);
+      }
+      ++cnt;
+    }
+  }
+  if (cnt > kCand) return false;
+  unsigned long long best[kK];
+  auto key_of = [&](int en) {
+    return ((unsigned long long)__float_as_uint(__fsqrt_rn(cand_d2[en * kChunk])) << 32) | (unsigned)cand_idx[en * kChunk];
+  };
+#pragma unroll
+  for (int j = 0; j < kK; ++j) best[j] = j < cnt ? key_of(j) : ~0ull;
+  NPCD_CE(0, 2) NPCD_CE(1, 3) NPCD_CE(4, 6) NPCD_CE(5, 7)
+  NPCD_CE(0, 4) NPCD_CE(1, 5) NPCD_CE(2, 6) NPCD_CE(3, 7)
+  NPCD_CE(0, 1) NPCD_CE(2, 3) NPCD_CE(4, 5) NPCD_CE(6, 7)
+  NPCD_CE(2, 4) NPCD_CE(3, 5)
+  NPCD_CE(1, 4) NPCD_CE(3, 6)
+  NPCD_CE(1, 2) NPCD_CE(3, 4) NPCD_CE(5, 6)
+#pragma unroll 1
+  for (int en = kK; en < cnt; ++en) {
+    unsigned long long cur = key_of(en);
+    if (cur < best[kK - 1]) {
+#pragma unroll
+      for (int j = 0; j < kK; ++j) {
+        const unsigned long long bj = best[j];
+        const bool sw = cur < bj;
+        best[j] = sw ? cur : bj;
+        cur = sw ? bj : cur;
+      }
+    }
+  }
+  int tmp[kK];
+#pragma unroll
+  for (int j = 0; j < kK; ++j) tmp[j] = best[j] == ~0ull ? -1 : base + (int)(best[j] & 0xffffffffu);
+  reinterpret_cast<int4*>(out)[0] = make_int4(tmp[0], tmp[1], tmp[2], tmp[3]);
+  reinterpret_cast<int4*>(out)[1] = make_int4(tmp[4], tmp[5], tmp[6], tmp[7]);
+  return true;
+}
+#undef NPCD_CE
+
+__global__ void __launch_bounds__(kChunk) k_knn_fill_s(const float* __restrict__ cam, const float* __restrict__ dirs,
+                                                       const float* __restrict__ start, const float* __restrict__ end,
+                                                       const float* __restrict__ jitter, const int* __restrict__ ray_ids, long long n_sel,
+                                                       const long long* __restrict__ ray_offset, const uint32_t* __restrict__ valid_bits,
+                                                       int rays_per_view, int views_per_obj, int P, const int* __restrict__ cell_start,
+                                                       const float4* __restrict__ sorted_pts, float radius, float T, long long capacity,
+                                                       int* __restrict__ nbr_idx, float4* __restrict__ sample_pos,
+                                                       int* __restrict__ sample_ray, int rays_per_cta) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];  // [sorted points of the chunk's object: P float4][cand_d2][range][cand_idx]
+  __shared__ int off_s[kChunk + 1];
+  float4* pts_s = reinterpret_cast<float4*>(smem_raw);
+  float* cand_d2 = reinterpret_cast<float*>(smem_raw + (size_t)P * 16);           // [entry][thread]: conflict-free columns
+  uint32_t* range_s = reinterpret_cast<uint32_t*>(cand_d2 + kCand * kChunk);       // [9][thread]
+  uint16_t* cand_idx = reinterpret_cast<uint16_t*>(range_s + 9 * kChunk);          // [entry][thread]
+  const long long sel0 = (long long)blockIdx.x * rays_per_cta;
+  const int n_local = (int)min((long long)rays_per_cta, n_sel - sel0);
+  const long long S = min(__ldg(ray_offset + n_sel), capacity);
+  const long long s0 = min(__ldg(ray_offset + sel0), S), s1 = min(__ldg(ray_offset + sel0 + n_local), S);
+  if (s1 <= s0) return;  // no kept sample in this chunk (uniform for the CTA)
+  const long long rays_per_obj = (long long)rays_per_view * views_per_obj;
+  const long long first_ray = ray_ids ? (long long)ray_ids[sel0] : sel0;
+  const int obj0 = (int)(first_ray / rays_per_obj);
+  const int* cs0 = cell_start + (size_t)obj0 * (kGridCells + 1);
+  for (int i = threadIdx.x; i < P; i += blockDim.x) pts_s[i] = __ldg(sorted_pts + (size_t)obj0 * P + i);
+  for (int i = threadIdx.x; i <= n_local; i += blockDim.x) off_s[i] = (int)(min(__ldg(ray_offset + sel0 + i), S) - s0);
+  __syncthreads();
+  const int n_samples = (int)(s1 - s0);
+  for (int sl = threadIdx.x; sl < n_samples; sl += blockDim.x) {
+    int lo = 0, hi = n_local;  // upper_bound(off_s, sl) - 1
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (off_s[mid] <= sl) lo = mid; else hi = mid;
+    }
+    const long long sel = sel0 + lo;
+    const long long ray = ray_ids ? (long long)ray_ids[sel] : sel;
+    int rank = sl - off_s[lo];
+    int i = 0;
+    const uint4 vb = __ldg(reinterpret_cast<const uint4*>(valid_bits + ray * 4));
+    const uint32_t w4[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int pc = __popc(w4[j]);
+      if (rank >= 0 && rank < pc) { i = j * 32 + nth_set_bit(w4[j], rank); rank = -1; }
+      else if (rank >= 0) rank -= pc;
+    }
+    const int view = (int)(ray / rays_per_view);
+    const int obj = view / views_per_obj;
+    const float ox = __ldg(cam + view * 3), oy = __ldg(cam + view * 3 + 1), oz = __ldg(cam + view * 3 + 2);
+    const float dx = __ldg(dirs + ray * 3), dy = __ldg(dirs + ray * 3 + 1), dz = __ldg(dirs + ray * 3 + 2);
+    const float t = sample_depth(__ldg(start + ray), __ldg(end + ray), i, jitter ? jitter + ray * kDepthRes : nullptr);
+    const float x = axpy_rn(ox, t, dx), y = axpy_rn(oy, t, dy), z = axpy_rn(oz, t, dz);
+    const long long s = s0 + sl;
+    // generic global-memory scan when the chunk straddles two objects (or ray_ids is not ascending) or the column overflowed
+    if (obj != obj0 || !select_and_store_s(pts_s, cs0, x, y, z, T, obj * P, nbr_idx + s * kK, cand_d2 + threadIdx.x,
+                                           cand_idx + threadIdx.x, range_s + threadIdx.x)) {
+      select_and_store_foreign(cell_start + (size_t)obj * (kGridCells + 1), sorted_pts + (size_t)obj * P, x, y, z, radius, obj * P,
+                               nbr_idx + s * kK);
+    }
+    const float q0 = __fdiv_rn(__fsub_rn(x, ox), dx), q1 = __fdiv_rn(__fsub_rn(y, oy), dy), q2 = __fdiv_rn(__fsub_rn(z, oz), dz);
+    float sum = 0.f, cnt = 0.f;
+    if (q0 == q0) { sum = __fadd_rn(sum, q0); cnt += 1.f; }
+    if (q1 == q1) { sum = __fadd_rn(sum, q1); cnt += 1.f; }
+    if (q2 == q2) { sum = __fadd_rn(sum, q2); cnt += 1.f; }
+    sample_pos[s] = make_float4(x, y, z, __fdiv_rn(sum, cnt));
+    if (sample_ray) sample_ray[s] = (int)sel;
+  }
+}
+
+// rays per CTA: kChunk for big launches; small launches (training: a few thousand rays) are split finer so every SM gets work
+static int rays_per_cta_for(long long n) {
+  long long r = (n + 148 * 8 - 1) / (148 * 8);
+  r = (r + 7) / 8 * 8;
+  return (int)(r < 16 ? 16 : (r > kChunk ? kChunk : r));
+}
+
+// largest float T with sqrt_rn(T) < r:  sqrt_rn(d2) < r  <=>  d2 <= T  (sqrt_rn is monotone; host sqrtf is correctly rounded)
+static float radius_threshold(float r) {
+  float T = r * r;
+  while (sqrtf(T) >= r) T = nextafterf(T, 0.f);
+  while (sqrtf(nextafterf(T, INFINITY)) < r) T = nextafterf(T, INFINITY);
+  return T;
+}
+
 }  // namespace npcd
 
 extern "C" int npcd_march_count(const float* cam_centers, const float* dirs, const float* ray_start, const float* ray_end,
                                 const float* jitter, long long n_rays, int rays_per_view, int views_per_obj, int n_points,
                                 const int* cell_start, const float* sorted_pts, const unsigned* occ_bits, const float* aabb,
-                                float radius, int max_shading_pts, unsigned* valid_bits, int* ray_count, void* stream) {
+                                const void* fine_masks, float radius, int max_shading_pts, unsigned* valid_bits, int* ray_count,
+                                int impl, void* stream) {
   using namespace npcd;
   NPCD_CHECK_ARG(cam_centers && dirs && ray_start && ray_end && cell_start && sorted_pts && occ_bits && valid_bits && ray_count,
                  "null pointer");
@@ -225,6 +616,21 @@ extern "C" int npcd_march_count(const float* cam_centers, const float* dirs, con
   NPCD_CHECK_ARG(max_shading_pts > 0 && max_shading_pts <= kDepthRes, "max_shading_pts must be in [1,128]");
   NPCD_CHECK_ARG(radius > 0.f && radius <= 2.0f / kGrid, "radius must be in (0, 1/12] (grid cell edge)");
   if (n_rays == 0) return 0;
+  NPCD_CHECK_ARG(impl >= 0 && impl <= 2, "impl must be 0 (auto), 1 (global-memory kernels) or 2 (shared-memory kernels)");
+  const long long rays_per_obj = (long long)rays_per_view * views_per_obj;
+  if (impl == 2) NPCD_CHECK_ARG(n_points <= kSmemMaxPoints && n_rays % rays_per_obj == 0, "shared-memory kernels: n_points <= 2048, whole objects");
+  if (impl != 1 && n_points <= kSmemMaxPoints && n_rays % rays_per_obj == 0) {
+    const int rpc = rays_per_cta_for(n_rays);
+    const int chunks_per_obj = (int)((rays_per_obj + rpc - 1) / rpc);
+    const long long n_obj = n_rays / rays_per_obj;
+    const size_t smem = sgrid_bytes(n_points);
+    cudaFuncSetAttribute(k_march_count_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_march_count_s<<<(unsigned)(n_obj * chunks_per_obj), kChunk, smem, (cudaStream_t)stream>>>(
+        cam_centers, dirs, ray_start, ray_end, jitter, rays_per_view, views_per_obj, chunks_per_obj, n_points, cell_start,
+        (const float4*)sorted_pts, occ_bits, aabb, (const ulonglong2*)fine_masks, radius_threshold(radius), max_shading_pts, valid_bits,
+        ray_count, rpc);
+    return check_launch("npcd_march_count");
+  }
   const int wpb = 8;
   const unsigned grid = (unsigned)((n_rays + wpb - 1) / wpb);
   k_march_count<<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(cam_centers, dirs, ray_start, ray_end, jitter, n_rays, rays_per_view,
@@ -237,12 +643,24 @@ extern "C" int npcd_knn_fill(const float* cam_centers, const float* dirs, const 
                              const float* jitter, const int* ray_ids, long long n_sel, const long long* ray_offset,
                              const unsigned* valid_bits, int rays_per_view, int views_per_obj, int n_points,
                              const int* cell_start, const float* sorted_pts, float radius, long long capacity, int* nbr_idx,
-                             float* sample_pos, int* sample_ray, void* stream) {
+                             float* sample_pos, int* sample_ray, int impl, void* stream) {
   using namespace npcd;
   NPCD_CHECK_ARG(cam_centers && dirs && ray_start && ray_end && ray_offset && valid_bits && cell_start && sorted_pts, "null pointer");
   NPCD_CHECK_ARG(capacity == 0 || (nbr_idx && sample_pos), "null output with capacity > 0");
   NPCD_CHECK_ARG(n_sel >= 0 && capacity >= 0, "bad sizes");
   if (n_sel == 0 || capacity == 0) return 0;
+  NPCD_CHECK_ARG(impl >= 0 && impl <= 2, "impl must be 0 (auto), 1 (global-memory kernels) or 2 (shared-memory kernels)");
+  NPCD_CHECK_ARG(radius > 0.f && radius <= 2.0f / kGrid, "radius must be in (0, 1/12] (grid cell edge)");
+  if (impl == 2) NPCD_CHECK_ARG(n_points <= kSmemMaxPoints, "shared-memory kernels: n_points <= 2048");
+  if (impl != 1 && n_points <= kSmemMaxPoints) {
+    const size_t smem = (size_t)n_points * 16 + (size_t)kChunk * (kCand * 6 + 9 * 4);
+    cudaFuncSetAttribute(k_knn_fill_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int rpc = rays_per_cta_for(n_sel);
+    k_knn_fill_s<<<(unsigned)((n_sel + rpc - 1) / rpc), kChunk, smem, (cudaStream_t)stream>>>(
+        cam_centers, dirs, ray_start, ray_end, jitter, ray_ids, n_sel, ray_offset, valid_bits, rays_per_view, views_per_obj, n_points,
+        cell_start, (const float4*)sorted_pts, radius, radius_threshold(radius), capacity, nbr_idx, (float4*)sample_pos, sample_ray, rpc);
+    return check_launch("npcd_knn_fill");
+  }
   const int bs = 128;
   const unsigned grid = (unsigned)((capacity + bs - 1) / bs);
   k_knn_fill<<<grid, bs, 0, (cudaStream_t)stream>>>(cam_centers, dirs, ray_start, ray_end, jitter, ray_ids, n_sel, ray_offset,

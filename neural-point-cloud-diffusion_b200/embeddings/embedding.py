@@ -52,6 +52,9 @@ class Embedding(torch.nn.Module):
     def _lookup(self, idx: Tensor) -> Tensor:
         dev = idx.device
         emb = self.get_emb()
+        lazy = getattr(emb.weight, "lazy_opt", None)
+        if lazy is not None:
+            lazy.catch_up(idx.to(emb.weight.device))
         if not self.gpu:
             idx = idx.cpu()
         return emb(idx).to(device=dev).view(-1, self.n_kp, self.out_dim * self._mult)
@@ -129,6 +132,9 @@ class VariationalEmbedding(Embedding):
         w = self.get_emb().weight
         if not (self.gpu and w.is_cuda):
             raise RuntimeError("the fused embedding step needs the table on the GPU (gpu=True, model.cuda())")
+        lazy = getattr(w, "lazy_opt", None)
+        if lazy is not None:
+            lazy.catch_up(idx)  # rows idle since their last step: replay the dense optimiser's momentum moves before reading
         if self.sample_embedding and eps is None:
             eps = torch.randn((idx.numel(), self.n_kp, self.out_dim), device=w.device)
         if not self.sample_embedding:

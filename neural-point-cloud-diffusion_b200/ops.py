@@ -99,8 +99,8 @@ def rays_generate(extr, intr, resolution: int, ray_subset=None, cube_scale: floa
     end = torch.empty((N, R), device=dev)
     origins = torch.empty((N, R, 3), device=dev) if want_origins else None
     scratch = torch.empty(2, dtype=torch.int32, device=dev)
-    call("npcd_rays_generate", ptr(extr), ptr(intr), N, resolution, ptr(ray_subset), 0 if ray_subset is None else R,
-         float(cube_scale), ptr(cam), ptr(origins), ptr(dirs), ptr(start), ptr(end), ptr(scratch), _stream())
+    _timed("rays", lambda: call("npcd_rays_generate", ptr(extr), ptr(intr), N, resolution, ptr(ray_subset), 0 if ray_subset is None else R,
+                                float(cube_scale), ptr(cam), ptr(origins), ptr(dirs), ptr(start), ptr(end), ptr(scratch), _stream()))
     _count(3)
     return Rays(cam, dirs, start, end, origins)
 
@@ -113,6 +113,9 @@ class Grid:
     n_obj: int
     n_points: int
     aabb: Optional[torch.Tensor] = None  # [B, 6] world box of the dilated occupied cells (empty-space skipping in the marcher)
+    masks: Optional[torch.Tensor] = None  # [B, cells, 2] int64 (sure, maybe) sub-cell masks, built lazily for one radius
+    mask_radius: Optional[float] = None
+    kp_pos: Optional[torch.Tensor] = None  # the (detached, contiguous) points the grid was built from
 
 
 _GRID_DIMS = None
@@ -136,9 +139,31 @@ def grid_build(kp_pos) -> Grid:
     dev = kp_pos.device
     g = Grid(torch.empty((B, cells + 1), dtype=torch.int32, device=dev), torch.empty((B, P, 4), device=dev),
              torch.empty((B, words), dtype=torch.int32, device=dev), B, P, torch.empty((B, 6), device=dev))
-    call("npcd_grid_build", ptr(kp_pos), B, P, ptr(g.cell_start), ptr(g.sorted_pts), ptr(g.occ_bits), ptr(g.aabb), _stream())
+    _timed("grid", lambda: call("npcd_grid_build", ptr(kp_pos), B, P, ptr(g.cell_start), ptr(g.sorted_pts), ptr(g.occ_bits), ptr(g.aabb),
+                                _stream()))
     _count(1)
+    g.kp_pos = kp_pos
     return g
+
+
+# 0 = auto (shared-memory kernels when n_points <= 2048), 1 = generic global-memory kernels, 2 = shared-memory kernels; tests flip
+# this to cross-check the two implementations bit for bit
+QUERY_IMPL = 0
+USE_FINE_MASKS = True
+
+
+def grid_masks(grid: Grid, radius: float):
+    """Sub-cell (sure, maybe) masks of the marcher for ``radius`` (built once per grid and radius)."""
+    if not USE_FINE_MASKS or QUERY_IMPL == 1 or grid.n_points > 2048:
+        return None
+    if grid.masks is None or grid.mask_radius != float(radius):
+        cells, _ = grid_dims()
+        grid.masks = torch.empty((grid.n_obj, cells, 2), dtype=torch.int64, device=grid.cell_start.device)
+        _timed("grid", lambda: call("npcd_grid_build_masks", ptr(grid.kp_pos), grid.n_obj, grid.n_points, float(radius), ptr(grid.masks),
+                                    _stream()))
+        _count(2)
+        grid.mask_radius = float(radius)
+    return grid.masks
 
 
 def march_count(rays: Rays, grid: Grid, views_per_obj: int, radius: float, max_shading_pts: int, jitter=None):
@@ -151,9 +176,11 @@ def march_count(rays: Rays, grid: Grid, views_per_obj: int, radius: float, max_s
     if jitter is not None:
         jitter = jitter.contiguous().float()
         assert jitter.numel() == n_rays * DEPTH_RES
-    call("npcd_march_count", ptr(rays.cam), ptr(rays.dirs), ptr(rays.start), ptr(rays.end), ptr(jitter), n_rays, R, views_per_obj,
-         grid.n_points, ptr(grid.cell_start), ptr(grid.sorted_pts), ptr(grid.occ_bits), ptr(grid.aabb), float(radius), int(max_shading_pts),
-         ptr(valid_bits), ptr(ray_count), _stream())
+    masks = grid_masks(grid, radius)
+    _timed("march", lambda: call(
+        "npcd_march_count", ptr(rays.cam), ptr(rays.dirs), ptr(rays.start), ptr(rays.end), ptr(jitter), n_rays, R, views_per_obj,
+        grid.n_points, ptr(grid.cell_start), ptr(grid.sorted_pts), ptr(grid.occ_bits), ptr(grid.aabb), ptr(masks), float(radius),
+        int(max_shading_pts), ptr(valid_bits), ptr(ray_count), int(QUERY_IMPL), _stream()))
     _count(1)
     return valid_bits, ray_count
 
@@ -172,7 +199,7 @@ def scan_counts(ray_count, ray_ids=None):
     ws = _SCAN_WS.get(key)
     if ws is None:
         ws = _SCAN_WS[key] = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
-    call("npcd_scan_counts", ptr(ray_count), ptr(ray_ids), n, ptr(out), ptr(ws), nbytes.value, _stream())
+    _timed("scan", lambda: call("npcd_scan_counts", ptr(ray_count), ptr(ray_ids), n, ptr(out), ptr(ws), nbytes.value, _stream()))
     _count(2)
     return out
 
@@ -188,9 +215,10 @@ def knn_fill(rays: Rays, grid: Grid, views_per_obj: int, radius: float, valid_bi
     sray = torch.empty((capacity,), dtype=torch.int32, device=dev) if want_sample_ray else None
     if jitter is not None:
         jitter = jitter.contiguous().float()
-    call("npcd_knn_fill", ptr(rays.cam), ptr(rays.dirs), ptr(rays.start), ptr(rays.end), ptr(jitter), ptr(ray_ids), n_sel,
-         ptr(ray_offset), ptr(valid_bits), R, views_per_obj, grid.n_points, ptr(grid.cell_start), ptr(grid.sorted_pts),
-         float(radius), capacity, ptr(nbr), ptr(pos), ptr(sray), _stream())
+    _timed("knn", lambda: call(
+        "npcd_knn_fill", ptr(rays.cam), ptr(rays.dirs), ptr(rays.start), ptr(rays.end), ptr(jitter), ptr(ray_ids), n_sel,
+        ptr(ray_offset), ptr(valid_bits), R, views_per_obj, grid.n_points, ptr(grid.cell_start), ptr(grid.sorted_pts),
+        float(radius), capacity, ptr(nbr), ptr(pos), ptr(sray), int(QUERY_IMPL), _stream()))
     _count(1 if capacity and n_sel else 0)
     return nbr, pos, sray
 
@@ -889,8 +917,8 @@ def composite_fwd(sample_pos, rgbs, ray_offset, ray_end, ray_ids=None, white_bac
         assert mask.numel() == n and depth.numel() == n and rgb.numel() == 3 * n
     if range_scratch is None:
         range_scratch = torch.empty(2, dtype=torch.int32, device=dev)
-    call("npcd_composite_fwd", ptr(sample_pos), ptr(rgbs), ptr(ray_offset), ptr(ray_ids), ptr(ray_end), n, int(white_back),
-         ptr(mask), ptr(depth), ptr(rgb), ptr(range_scratch), int(init_range), _stream())
+    _timed("composite", lambda: call("npcd_composite_fwd", ptr(sample_pos), ptr(rgbs), ptr(ray_offset), ptr(ray_ids), ptr(ray_end), n,
+                                     int(white_back), ptr(mask), ptr(depth), ptr(rgb), ptr(range_scratch), int(init_range), _stream()))
     _count((1 if init_range else 0) + (1 if n else 0))
     return mask, depth, rgb, range_scratch
 
@@ -898,7 +926,7 @@ def composite_fwd(sample_pos, rgbs, ray_offset, ray_end, ray_ids=None, white_bac
 def clamp_depth(depth, range_scratch, want_clamped: bool = False):
     n = depth.numel()
     clamped = torch.empty((n,), dtype=torch.uint8, device=depth.device) if want_clamped else None
-    call("npcd_clamp_depth", ptr(depth), n, ptr(range_scratch), ptr(clamped), _stream())
+    _timed("composite", lambda: call("npcd_clamp_depth", ptr(depth), n, ptr(range_scratch), ptr(clamped), _stream()))
     _count(1 if n else 0)
     return clamped
 

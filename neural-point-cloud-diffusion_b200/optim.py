@@ -5,8 +5,9 @@ DENSE Adam pass per step over the per-object latent table (2347 x 512 x 64 float
 written) although a step only touches the ``batch_size`` (8) rows of its objects -- and dense Adam semantics make the untouched rows
 move too (their momentum keeps decaying into the weights).  ``LazyRowAdam`` keeps those semantics EXACTLY at the cost of the touched
 rows: every row remembers the step it was last brought up to and `npcd_embed_adam_rows` replays the missed zero-gradient steps in
-registers before applying the current gradient.  ``flush()`` brings the whole table up to date (call before evaluating or
-checkpointing; `state_dict()` does it).
+registers -- when the embedding lookup is about to READ the row (``catch_up``, so the forward pass sees what the dense optimiser
+would have produced) and again, as a no-op safety net, before the current gradient is applied.  ``flush()`` brings the whole table
+up to date (call before evaluating or checkpointing; `state_dict()` does it).
 
 ``PointNeRFAdam`` is the drop-in for the trainer's optimiser: ``LazyRowAdam`` for the embedding tables (switching their modules
 to compact row gradients) and ``torch.optim.Adam`` -- the reference's own optimiser -- for the 24 small MLP tensors (2.47 MB).
@@ -37,6 +38,14 @@ class LazyRowAdam:
         self.row_step = torch.zeros(table.shape[0], dtype=torch.int32, device=table.device)
         self.step_count = 0
         table.row_grads = None
+        table.lazy_opt = self  # the embedding lookup calls catch_up() on the rows it is about to read
+
+    @torch.no_grad()
+    def catch_up(self, idx):
+        """Brings the rows ``idx`` up to the last completed step BEFORE they are read: the dense optimiser has already moved them
+        through their momentum on every step since they were last touched, and the forward pass (sampling, KL, TV) must see that."""
+        if self.step_count > 0 and idx.numel() > 0:
+            self._launch(idx.contiguous().long(), idx.numel(), None)
 
     def zero_grad(self):
         self.table.row_grads = None

@@ -57,7 +57,7 @@ def test_ctypes_binding_matches_header(lib):
 
 def test_abi_version_and_error_string(lib):
     lib.npcd_abi_version.restype = ctypes.c_int
-    assert lib.npcd_abi_version() == 1
+    assert lib.npcd_abi_version() == 2
     lib.npcd_last_error.restype = ctypes.c_char_p
     assert isinstance(lib.npcd_last_error(), bytes)
 

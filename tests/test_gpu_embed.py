@@ -9,6 +9,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+TABLE_TOL = 1e-6  # 2 ulp of the largest table entries (|log-var| ~ 5); one Adam update moves an entry by ~1e-3
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "embed_adam.npz")
 
 
@@ -81,13 +82,13 @@ def test_lazy_row_adam_equals_reference_dense_adam(flush_at):
         assert w.grad is None  # the dense 308 MB-style gradient is never formed
         opt.step()
         rows = sorted(set(int(b) for b in batch))
-        np.testing.assert_allclose(w.detach().cpu().numpy()[rows], g[f"table{t + 1}"][rows], atol=3e-7, rtol=0)
+        np.testing.assert_allclose(w.detach().cpu().numpy()[rows], g[f"table{t + 1}"][rows], atol=TABLE_TOL, rtol=0)
         if flush_at == t + 1:
             opt.flush()
-            np.testing.assert_allclose(w.detach().cpu().numpy(), g[f"table{t + 1}"], atol=3e-7, rtol=0)
+            np.testing.assert_allclose(w.detach().cpu().numpy(), g[f"table{t + 1}"], atol=TABLE_TOL, rtol=0)
     # row 6 is never touched, rows 1 and 3 have been idle since steps 2 and 4: lazily behind until the flush
     opt.flush()
-    np.testing.assert_allclose(w.detach().cpu().numpy(), g["table6"], atol=3e-7, rtol=0)
+    np.testing.assert_allclose(w.detach().cpu().numpy(), g["table6"], atol=TABLE_TOL, rtol=0)
     np.testing.assert_allclose(opt.exp_avg.cpu().numpy(), g["exp_avg"], atol=2e-7 * np.abs(g["exp_avg"]).max(), rtol=2e-6)
     np.testing.assert_allclose(opt.exp_avg_sq.cpu().numpy(), g["exp_avg_sq"], atol=2e-7 * np.abs(g["exp_avg_sq"]).max(), rtol=2e-6)
     np.testing.assert_array_equal(opt.row_step.cpu().numpy(), np.full(n_obj, 6, np.int32))

@@ -930,3 +930,68 @@ def test_tc_matches_simt_full_size(syn, model, cameras, torch_cuda):
     for k in ("mask", "depth", "channels"):
         assert torch.equal(b[k], c[k]), k
         np.testing.assert_allclose(a[k].cpu().numpy(), b[k].cpu().numpy(), atol=2e-5, rtol=0, err_msg=k)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,train", [("ellipsoid", False), ("box", False), ("ellipsoid", True)])
+def test_query_kernel_variants_agree_bit_for_bit(kind, train, syn, cameras, torch_cuda):
+    """The shared-memory march / kNN kernels (sub-cell masks, queued exact tests, squared-distance threshold) against the generic
+    global-memory kernels, with and without the masks: validity words, counts, neighbour lists and sample positions identical at
+    full size (3 objects x 6 views x 128^2 rays; train mode adds depth jitter and a ray subset that straddles objects)."""
+    torch = torch_cuda
+    from npcd_b200 import ops
+
+    poses, intr = cameras
+    B, views = 3, [0, 40, 80, 120, 160, 200]
+    T = len(views)
+    coords, _ = syn.make_clouds([5, 6, 7], kind=kind)
+    extr = _t(torch, np.broadcast_to(poses[views][None], (B, T, 4, 4)).copy()).reshape(B * T, 4, 4)
+    K = _t(torch, np.broadcast_to(intr[views][None], (B, T, 3, 3)).copy()).reshape(B * T, 3, 3)
+    rays = ops.rays_generate(extr, K, 128)
+    N, R = rays.start.shape
+    jitter = torch.rand((N, R, 128), device="cuda", generator=torch.Generator(device="cuda").manual_seed(1)) if train else None
+    results = {}
+    try:
+        for tag, impl, masks in (("generic", 1, False), ("smem", 2, False), ("smem+masks", 2, True)):
+            ops.QUERY_IMPL, ops.USE_FINE_MASKS = impl, masks
+            grid = ops.grid_build(_t(torch, coords))
+            vb, cnt = ops.march_count(rays, grid, T, 0.08, 50, jitter)
+            assert (grid.masks is not None) == masks
+            ids = None
+            if train:  # every 7th ray with a kept sample: ascending, chunks straddle views and objects
+                ids = torch.nonzero(cnt > 0).flatten()[::7].to(torch.int32).contiguous()
+            off = ops.scan_counts(cnt, ids)
+            S = int(off[-1].item())
+            nbr, pos, sray = ops.knn_fill(rays, grid, T, 0.08, vb, off, S, ids, jitter, want_sample_ray=True)
+            results[tag] = (vb, cnt, off, nbr, pos, sray)
+    finally:
+        ops.QUERY_IMPL, ops.USE_FINE_MASKS = 0, True
+    ref = results["generic"]
+    assert int(ref[2][-1].item()) > 100_000 or train
+    assert int(ref[1].max()) == (50 if kind == "box" else int(ref[1].max()))
+    for tag in ("smem", "smem+masks"):
+        for name, a, b in zip(("valid_bits", "ray_count", "ray_offset", "nbr_idx", "sample_pos", "sample_ray"), ref, results[tag]):
+            assert torch.equal(a, b), (tag, name)
+
+
+def test_fine_masks_are_conservative(syn, torch_cuda):
+    """Sub-cell masks against brute force on random positions: `sure` implies a point within r, not `maybe` implies none."""
+    torch = torch_cuda
+    from npcd_b200 import ops
+
+    coords, _ = syn.make_clouds([9])
+    grid = ops.grid_build(_t(torch, coords))
+    masks = ops.grid_masks(grid, 0.08).cpu().numpy().astype(np.uint64)[0]  # [cells, 2]
+    rng = np.random.default_rng(3)
+    x = (coords[0][rng.integers(0, 512, 200_000)] + rng.normal(0, 0.06, (200_000, 3))).astype(np.float32)
+    x = np.clip(x, -0.999, 0.999)
+    fine = np.clip(np.floor((x + np.float32(1)) * np.float32(48)).astype(np.int64), 0, 95)
+    cell = ((fine[:, 2] >> 2) * 24 + (fine[:, 1] >> 2)) * 24 + (fine[:, 0] >> 2)
+    bit = (((fine[:, 2] & 3) * 4 + (fine[:, 1] & 3)) * 4 + (fine[:, 0] & 3)).astype(np.uint64)
+    sure = (masks[cell, 0] >> bit) & np.uint64(1)
+    maybe = (masks[cell, 1] >> bit) & np.uint64(1)
+    d = np.sqrt(((x[:, None, :].astype(np.float64) - coords[0][None].astype(np.float64)) ** 2).sum(-1)).min(1)
+    assert np.all(d[sure == 1] < 0.08) and np.all(d[maybe == 0] >= 0.08)
+    assert np.all(maybe[sure == 1] == 1)
+    # the masks do prune: most samples within r are `sure`, most samples outside are not `maybe`
+    assert (sure[d < 0.08] == 1).mean() > 0.4 and (maybe[d >= 0.08] == 0).mean() > 0.3
