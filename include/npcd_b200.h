@@ -137,7 +137,8 @@ int npcd_field_tc_workspace_bytes(long long capacity, size_t* bytes);
 int npcd_field_tc_fwd(const int* nbr_idx, const float* sample_pos, const float* kp_pos, const float* kp_feat,
                       const long long* n_samples_dev, long long capacity, const npcd_mlp_tc_weights* weights, void* workspace,
                       size_t workspace_bytes, float* rgbs, float* feat_out,
-                      int stages /* bit0: dense packing + pair MLP + aggregation -> workspace, bit1: heads -> rgbs */,
+                      int stages /* bit0: dense packing + pair MLP + aggregation -> workspace, bit1: heads -> rgbs, bit2: heads with
+                                    local_field.8 folded into W->shape / W->chan[0] by the caller (W' = W W_8, b' = W b_8 + b; W->agg unused) */,
                       int* error_flag /* device int, optional */, int num_sms, void* stream);
 /* fp32 rows [n,256] <-> the pre-split operand image the tensor-core kernels exchange: per 128-row tile 4 K-blocks x
  * (fp16 hi 16 KB, fp16 lo 16 KB) in the SWIZZLE_128B layout; ceil(n / 128) * 128 KB.                                           */

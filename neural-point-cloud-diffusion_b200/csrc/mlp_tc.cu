@@ -77,6 +77,7 @@ struct Params {
   float shape_out_b;
   float chan_out_b[3];
   int n_layers;
+  int layer_ofs;  // heads: 1 when local_field.8 is folded into shape_net.0 / channel_net.0 (layers[0] = shape_net.0'), else 0
   // pair
   const int* nbr_idx;
   const float4* sample_pos;
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(kMode == MODE_HEADS_TRAIN ? kThreadsTcTrainHea
         const int ksteps = P.layers[l].ksteps;
         const int nkb = (ksteps + 3) >> 2;
         // heads layer 2 (channel_net.0) reads the same operand (feat) as layer 1 (shape_net.0): nothing new to wait for
-        const bool fresh_a = !(kHeads && l == 2);
+        const bool fresh_a = !(kHeads && l + P.layer_ofs == 2);
         for (int kb = 0; kb < nkb; ++kb) {
           if (!kPair && l == 0) {
             mbar_wait(bar(kBarA0Rdy + kb), (ph_a0 >> kb) & 1u);
@@ -721,18 +722,21 @@ __global__ void __launch_bounds__(kMode == MODE_HEADS_TRAIN ? kThreadsTcTrainHea
         float* feat_row = (P.feat_out && s < S) ? P.feat_out + s * kHidden : nullptr;
         float sigma = 0.f;
         float res[3];
+        // logical layer ll = l + layer_ofs (layer_ofs = 1: local_field.8 folded into the two layers that consume it, the tile's
+        // input image then feeds shape_net.0' and channel_net.0' directly)
 #pragma unroll 1
-        for (int l = 0; l < 6; ++l) {
-          if (l == 1 || l == 5) {
-            // l = 1: shape_net.0 + LeakyReLU, shape_net.2;  l = 5: channel_net.6 + LeakyReLU, channel_net.8
-            epilogue_dot(l, l == 1 ? 1 : 3, res);
-            if (l == 1 && half == 0) {
+        for (int l = 0; l < n_layers; ++l) {
+          const int ll = l + P.layer_ofs;
+          if (ll == 1 || ll == 5) {
+            // ll = 1: shape_net.0 + LeakyReLU, shape_net.2;  ll = 5: channel_net.6 + LeakyReLU, channel_net.8
+            epilogue_dot(l, ll == 1 ? 1 : 3, res);
+            if (ll == 1 && half == 0) {
               const float xs = res[0] + P.shape_out_b - 1.0f;
               sigma = xs > 20.f ? xs : log1pf(expf(xs));
             }
           } else {
-            // l = 0: local_field.8 (linear) -> feat;  l = 2..4: channel_net.0,2,4 (layer 2 reads feat and overwrites it in place)
-            epilogue_store(l, l == 0 ? 1.0f : 0.01f, l == 0 ? feat_row : nullptr);
+            // ll = 0: local_field.8 (linear) -> feat;  ll = 2..4: channel_net.0,2,4 (layer 2 reads feat and overwrites it in place)
+            epilogue_store(l, ll == 0 ? 1.0f : 0.01f, ll == 0 ? feat_row : nullptr);
           }
         }
         if (half == 0 && s < S) {
@@ -964,14 +968,17 @@ int pair_stage(const int* nbr_idx, const float* sample_pos, const float* kp_pos,
 namespace {
 template <int kMode>
 int heads_stage(const npcd_mlp_tc_weights* W, uint8_t* img, float* rgbs, float* feat_out, const long long* n_samples_dev,
-                long long capacity, const npcd_pair_stash_layout* layout, uint8_t* stash, int* error_flag, int num_sms, cudaStream_t st) {
+                long long capacity, const npcd_pair_stash_layout* layout, uint8_t* stash, int* error_flag, int num_sms, cudaStream_t st,
+                bool folded = false) {
   static thread_local tc::Params P;
   memset(&P, 0, sizeof(P));
-  fill_layer(P, 0, W->agg, tc::EPI_LINEAR);
-  fill_layer(P, 1, W->shape, tc::EPI_DOT1);
-  for (int i = 0; i < 3; ++i) fill_layer(P, 2 + i, W->chan[i], tc::EPI_ACT);
-  fill_layer(P, 5, W->chan[3], tc::EPI_DOT3);
-  P.n_layers = 6;
+  const int o = folded ? 1 : 0;  // folded: W->shape / W->chan[0] already contain local_field.8 (W' = W W_8, b' = W b_8 + b)
+  if (!folded) fill_layer(P, 0, W->agg, tc::EPI_LINEAR);
+  fill_layer(P, 1 - o, W->shape, tc::EPI_DOT1);
+  for (int i = 0; i < 3; ++i) fill_layer(P, 2 + i - o, W->chan[i], tc::EPI_ACT);
+  fill_layer(P, 5 - o, W->chan[3], tc::EPI_DOT3);
+  P.n_layers = 6 - o;
+  P.layer_ofs = o;
   P.img = img; P.rgbs = (float4*)rgbs; P.feat_out = feat_out;
   memcpy(P.shape_out_w, W->shape_out_w, sizeof(float) * 256);
   memcpy(P.chan_out_w, W->chan_out_w, sizeof(float) * 3 * 256);
@@ -1019,7 +1026,10 @@ extern "C" int npcd_field_tc_fwd(const int* nbr_idx, const float* sample_pos, co
                                    error_flag, num_sms, st);
     if (rc) return rc;
   }
-  if (stages & 2) rc = heads_stage<tc::MODE_HEADS>(W, img, rgbs, feat_out, n_samples_dev, capacity, nullptr, nullptr, error_flag, num_sms, st);
+  NPCD_CHECK_ARG(!(stages & 4) || !feat_out, "the folded heads stage has no local_field.8 output to return");
+  if (stages & 6)
+    rc = heads_stage<tc::MODE_HEADS>(W, img, rgbs, feat_out, n_samples_dev, capacity, nullptr, nullptr, error_flag, num_sms, st,
+                                     (stages & 4) != 0);
   return rc;
 }
 

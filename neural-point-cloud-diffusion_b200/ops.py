@@ -303,12 +303,18 @@ class PackedTcWeights:
         perm0 = torch.tensor(pair_input_perm(), dtype=torch.int32, device=dev)
         self.keep.append(perm0)
         layers = [lf[0], lf[1], lf[2], lf[3], lf[4], sn[0], cn[0], cn[1], cn[2], cn[3]]
+        # inference folds local_field.8 (linear, no activation, `fields/aggregators/mlp.py:84`) into the two layers that consume its
+        # output: W' = W W_8, b' = W b_8 + b (float64 product, rounded once) -- one 256x256 GEMM less per shading sample
+        w8, b8 = lf[4].weight.detach().double(), lf[4].bias.detach().double()
+        folded = [((l.weight.detach().double() @ w8).float().contiguous(), (l.weight.detach().double() @ b8 + l.bias.detach().double()).float())
+                  for l in (sn[0], cn[0])]
         # one device->host transfer for everything the host needs: per-layer max|w| (scales), biases, narrow output layers
-        small = torch.cat([torch.stack([l.weight.detach().float().abs().max() for l in layers])]
+        small = torch.cat([torch.stack([l.weight.detach().float().abs().max() for l in layers] + [w.abs().max() for w, _ in folded])]
                           + [l.bias.detach().float().reshape(-1) for l in layers]
                           + [sn[1].weight.detach().float().reshape(-1), sn[1].bias.detach().float().reshape(-1),
-                             cn[4].weight.detach().float().reshape(-1), cn[4].bias.detach().float().reshape(-1)]).cpu().numpy()
-        maxabs, off = small[:10], 10
+                             cn[4].weight.detach().float().reshape(-1), cn[4].bias.detach().float().reshape(-1)]
+                          + [b.reshape(-1) for _, b in folded]).cpu().numpy()
+        maxabs, fold_maxabs, off = small[:10], small[10:12], 12
         self.maxabs = maxabs
         self.pair_linears = lf[:4]
         self.head_linears = [cn[3], cn[2], cn[1], cn[0], sn[0], lf[4]]  # order of use in npcd_heads_tc_bwd
@@ -344,6 +350,17 @@ class PackedTcWeights:
         s.shape_out_w, s.shape_out_b = host(HIDDEN), host(1)
         s.chan_out_w, s.chan_out_b = host(3 * HIDDEN), host(3)
         self.struct = s
+        # second view of the same weights for the folded heads stage (stages bit 2): shape / chan[0] replaced, agg unused
+        f = _lib.TcWeights()
+        C.memmove(C.byref(f), C.byref(s), C.sizeof(_lib.TcWeights))
+        for dst, (w, _), m in ((f.shape, folded[0], fold_maxabs[0]), (f.chan[0], folded[1], fold_maxabs[1])):
+            scale = 2.0 ** math.floor(math.log2(4.0 / float(m))) if m > 0 else 1.0
+            out = torch.zeros(4 * 2 * 32768, dtype=torch.uint8, device=dev)
+            call("npcd_tc_pack_weights", ptr(w), HIDDEN, None, HIDDEN, float(scale), ptr(out), _stream())
+            _count(1)
+            self.keep += [w, out]
+            dst.packed_w, dst.bias, dst.inv_scale, dst.k_pad = out.data_ptr(), host(HIDDEN), 1.0 / scale, HIDDEN
+        self.struct_folded = f
         self.error_flag = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def dgrad_pack(self):
@@ -384,6 +401,10 @@ class PackedTcWeights:
         return self._hdgrad
 
 
+# inference: fold local_field.8 into the layers that consume it (tests flip this to compare both heads stages)
+FOLD_HEADS = True
+
+
 def tc_workspace_bytes(capacity: int) -> int:
     n = C.c_size_t()
     call("npcd_field_tc_workspace_bytes", int(capacity), C.byref(n))
@@ -406,7 +427,11 @@ def field_tc_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity: 
     args = (ptr(nbr_idx), ptr(sample_pos), ptr(kp_pos), ptr(kp_feat), ptr(n_samples_dev), capacity, C.byref(weights.struct),
             ptr(ws), nbytes, ptr(rgbs), ptr(feat))
     _timed("pair_mlp", lambda: call("npcd_field_tc_fwd", *args, 1, ptr(weights.error_flag), sm_count(dev), _stream()))
-    _timed("heads", lambda: call("npcd_field_tc_fwd", *args, 2, ptr(weights.error_flag), sm_count(dev), _stream()))
+    if FOLD_HEADS and not want_feat:  # local_field.8 folded into shape_net.0 / channel_net.0: 5 GEMMs per sample instead of 6
+        fargs = args[:6] + (C.byref(weights.struct_folded),) + args[7:]
+        _timed("heads", lambda: call("npcd_field_tc_fwd", *fargs, 4, ptr(weights.error_flag), sm_count(dev), _stream()))
+    else:
+        _timed("heads", lambda: call("npcd_field_tc_fwd", *args, 2, ptr(weights.error_flag), sm_count(dev), _stream()))
     _count(6)  # pair-offset scan (3 launches) + tile starts + pair kernel + heads kernel
     if want_agg:
         agg = torch.empty((capacity, HIDDEN), device=dev)

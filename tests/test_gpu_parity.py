@@ -995,3 +995,31 @@ def test_fine_masks_are_conservative(syn, torch_cuda):
     assert np.all(maybe[sure == 1] == 1)
     # the masks do prune: most samples within r are `sure`, most samples outside are not `maybe`
     assert (sure[d < 0.08] == 1).mean() > 0.4 and (maybe[d >= 0.08] == 0).mean() > 0.3
+
+
+def test_folded_heads_stage_matches_unfolded(syn, model, cameras, torch_cuda):
+    """Inference folds local_field.8 into shape_net.0 / channel_net.0 (one GEMM less per sample): images and per-sample (rgb, sigma)
+    against the six-GEMM heads stage, and against the golden full view of the unmodified reference."""
+    torch = torch_cuda
+    from npcd_b200 import ops
+
+    poses, intr = cameras
+    coords, feats = syn.make_clouds([0])
+    c, f = _t(torch, coords), _t(torch, feats)
+    e, i = _t(torch, poses[[0, 90, 180]][None]), _t(torch, intr[[0, 90, 180]][None])
+    out = {}
+    try:
+        for fold in (True, False):
+            ops.FOLD_HEADS = fold
+            with torch.no_grad():
+                out[fold] = model.renderer(c, f, e, i, 128, False)
+    finally:
+        ops.FOLD_HEADS = True
+    for k in ("mask", "depth", "channels"):
+        np.testing.assert_allclose(out[True][k].cpu().numpy(), out[False][k].cpu().numpy(), atol=2e-6, rtol=0, err_msg=k)
+    assert not torch.equal(out[True]["channels"], out[False]["channels"])  # the two stages really are different code paths
+    g, coords, feats, extr, intrn, res = load_case("view128", syn)
+    with torch.no_grad():
+        r = model.renderer(_t(torch, coords), _t(torch, feats), _t(torch, extr), _t(torch, intrn), res, False)
+    for k in ("mask", "depth", "channels"):
+        np.testing.assert_allclose(r[k].cpu().numpy(), g[k], atol=IMG_TOL, rtol=0, err_msg=k)
