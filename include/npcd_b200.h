@@ -77,6 +77,15 @@ int npcd_knn_fill(const float* cam_centers, const float* dirs, const float* ray_
                   long long capacity, int* nbr_idx, float* sample_pos, int* sample_ray, int impl /* as npcd_march_count */,
                   void* stream);
 
+/* ---- Q3: train-mode valid-ray subsampling, replaces Aggregator.subsample_valid_rays (fields/aggregators/aggregator.py:78-119) ------
+ *   npcd_count_valid_rays: n_valid [n_views] = #rays of the view with ray_count > 0, min_valid [1] = their minimum (the host reads it:
+ *     n = min(min_valid, ray_subsamples) sizes every output, aggregator.py:102-103).
+ *   npcd_subsample_valid_rays: per view a uniform random n_keep-subset of its valid rays (counter-based generator on `seed`), written
+ *     as global ray ids view * rays_per_view + ray in ascending order: ray_ids [n_views, n_keep] int32 (n_keep <= every n_valid).   */
+int npcd_count_valid_rays(const int* ray_count, long long n_views, int rays_per_view, int* n_valid, int* min_valid, void* stream);
+int npcd_subsample_valid_rays(const int* ray_count, long long n_views, int rays_per_view, int n_keep, unsigned long long seed,
+                              int* ray_ids, void* stream);
+
 /* ---- field: gather + posenc + pair MLP + aggregation + density/colour heads -------------------------------------------------
  * Replaces aggregators.MLP.get_local_feat / aggregate_local_feat (fields/aggregators/mlp.py:36-125), Aggregator.get_keypoint_data
  * (aggregator.py:121-144), fields.MLP.get_shape / get_channels (fields/mlp.py:38-72) and the activations of Field.forward

@@ -91,6 +91,8 @@ SIGNATURES = {
     "npcd_scan_workspace_bytes": [L, P],
     "npcd_scan_counts": [P, P, L, P, P, C.c_size_t, P],
     "npcd_knn_fill": [P, P, P, P, P, P, L, P, P, I, I, I, P, P, F, L, P, P, P, I, P],
+    "npcd_count_valid_rays": [P, L, I, P, P, P],
+    "npcd_subsample_valid_rays": [P, L, I, I, C.c_ulonglong, P, P],
     "npcd_knn_points": [P, P, L, I, I, P, P, F, P, P],
     "npcd_field_simt_fwd": [P, P, P, P, P, L, P, P, P, P, I, I, P],
     "npcd_tc_pack_weights": [P, I, P, I, F, P, P],

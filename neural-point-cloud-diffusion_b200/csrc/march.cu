@@ -301,6 +301,7 @@ __global__ void __launch_bounds__(kChunk) k_march_count_s(const float* __restric
   __shared__ uint32_t valid_s[kChunk * 4];
   __shared__ uint16_t queue[kQueue];
   __shared__ int q_count, q_valid;
+  __shared__ float step_tab[kDepthRes];  // i / 127 rounded once (math_utils.py:106-115): saves an IEEE division per depth sample
   const int obj = blockIdx.x / chunks_per_obj, chunk = blockIdx.x % chunks_per_obj;
   const long long rays_per_obj = (long long)rays_per_view * views_per_obj;
   const long long ray0 = obj * rays_per_obj + (long long)chunk * rays_per_cta;
@@ -309,15 +310,23 @@ __global__ void __launch_bounds__(kChunk) k_march_count_s(const float* __restric
                              occ_bits + (size_t)obj * kGridWords);
   const ulonglong2* mk = masks ? masks + (size_t)obj * kGridCells : nullptr;
   for (int i = threadIdx.x; i < kChunk * 4; i += blockDim.x) valid_s[i] = 0u;
+  for (int i = threadIdx.x; i < kDepthRes; i += blockDim.x) step_tab[i] = __fdiv_rn((float)i, (float)(kDepthRes - 1));
   if (threadIdx.x == 0) { q_count = 0; q_valid = kQueue; }
   __syncthreads();
+  // sample_depth() of common.cuh with the division looked up
+  auto depth_of = [&](float t0, float t1, int i, const float* jit) {
+    const float span = __fsub_rn(t1, t0);
+    float t = __fadd_rn(t0, __fmul_rn(step_tab[i], span));
+    if (jit) t = __fadd_rn(t, __fmul_rn(jit[i], __fdiv_rn(span, (float)(kDepthRes - 1))));
+    return t;
+  };
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   // position of depth sample i of local ray r (bit-exact restatement shared by all passes)
   auto sample_xyz = [&](long long ray, int i, float& x, float& y, float& z) {
     const int view = (int)(ray / rays_per_view);
     const float ox = __ldg(cam + view * 3), oy = __ldg(cam + view * 3 + 1), oz = __ldg(cam + view * 3 + 2);
-    const float t = sample_depth(__ldg(start + ray), __ldg(end + ray), i, jitter ? jitter + ray * kDepthRes : nullptr);
+    const float t = depth_of(__ldg(start + ray), __ldg(end + ray), i, jitter ? jitter + ray * kDepthRes : nullptr);
     x = axpy_rn(ox, t, __ldg(dirs + ray * 3));
     y = axpy_rn(oy, t, __ldg(dirs + ray * 3 + 1));
     z = axpy_rn(oz, t, __ldg(dirs + ray * 3 + 2));
@@ -364,7 +373,7 @@ __global__ void __launch_bounds__(kChunk) k_march_count_s(const float* __restric
     for (int j = 0; j < 4; ++j) {
       if (j * 32 > i_hi || j * 32 + 31 < i_lo) continue;  // warp-uniform
       const int i = j * 32 + lane;
-      const float t = sample_depth(t0, t1, i, jit);
+      const float t = depth_of(t0, t1, i, jit);
       const float x = axpy_rn(ox, t, dx), y = axpy_rn(oy, t, dy), z = axpy_rn(oz, t, dz);
       bool sure = false, unc = false;
       if (i >= i_lo && i <= i_hi) {

@@ -223,6 +223,22 @@ def knn_fill(rays: Rays, grid: Grid, views_per_obj: int, radius: float, valid_bi
     return nbr, pos, sray
 
 
+def subsample_valid_rays(ray_count, n_views: int, rays_per_view: int, max_keep: int, seed: int):
+    """Q3 (`aggregator.py:78-119`): (ray_ids [n_views*n] int32 ascending per view, n) with n = min(min #valid rays, max_keep).
+    One host sync (n sizes the output)."""
+    dev = ray_count.device
+    n_valid = torch.empty((n_views,), dtype=torch.int32, device=dev)
+    min_valid = torch.empty((1,), dtype=torch.int32, device=dev)
+    call("npcd_count_valid_rays", ptr(ray_count), n_views, rays_per_view, ptr(n_valid), ptr(min_valid), _stream())
+    _count(2)
+    n = min(int(min_valid.item()), int(max_keep)) if n_views > 0 else 0
+    ray_ids = torch.empty((n_views * n,), dtype=torch.int32, device=dev)
+    if n > 0:
+        call("npcd_subsample_valid_rays", ptr(ray_count), n_views, rays_per_view, n, int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(ray_ids), _stream())
+        _count(1)
+    return ray_ids, n
+
+
 def knn_points(x, grid: Grid, radius: float, queries_per_obj: int = 0, query_obj=None):
     """Exact radius-kNN of explicit positions x [n,3] -> [n,8] int32 (global index, canonical order, -1 padded)."""
     _need_cuda(x)

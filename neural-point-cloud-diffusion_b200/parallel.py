@@ -62,6 +62,10 @@ class GradBucket:
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
 
     def pack(self):
+        """One concatenation kernel (``torch.cat(..., out=flat)``) instead of one copy per tensor."""
+        if all(p.grad is not None for p in self.params):
+            torch.cat([p.grad.reshape(-1) for p in self.params], out=self.flat)
+            return self.flat
         o = 0
         for p in self.params:
             n = p.numel()
@@ -73,23 +77,26 @@ class GradBucket:
         return self.flat
 
     def unpack(self):
-        o = 0
+        views, o = [], 0
         for p in self.params:
             n = p.numel()
-            g = self.flat[o:o + n].view_as(p)
+            views.append(self.flat[o:o + n].view_as(p))
+            o += n
+        if all(p.grad is not None for p in self.params):
+            torch._foreach_copy_([p.grad for p in self.params], views)  # multi-tensor copy: one or two launches
+            return
+        for p, g in zip(self.params, views):
             if p.grad is None:
                 p.grad = g.clone()
             else:
                 p.grad.copy_(g)
-            o += n
 
     def all_reduce_mean(self, group: Optional[dist.ProcessGroup] = None, async_op: bool = False):
         """Sum across ranks, then divide by the world size.  With ``async_op`` returns the work handle; call
         ``finish(handle)`` after overlapping the embedding-row update."""
-        self.pack()
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-            self.unpack()
-            return None
+            return None  # single process: the local gradients already are the mean over the (one-rank) world
+        self.pack()
         work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
         if async_op:
             return work

@@ -62,6 +62,11 @@ class VolumeRenderer(nn.Module):
     def _subsample_valid_rays(self, ray_count: Tensor, rng):
         """ray_count [N,R] -> (ray_ids [N*n] int32 ascending per view, n)."""
         N, R = ray_count.shape
+        if rng is None:
+            # fused path: count + select kernels, one host sync; the seed comes from torch's CPU generator (torch.manual_seed applies)
+            seed = int(torch.empty((), dtype=torch.int64).random_().item())
+            return ops.subsample_valid_rays(ray_count.contiguous(), N, R, self.field.aggregator.ray_subsamples, seed)
+        # injected permutation (parity tests against the reference's own randperm): the reference's op sequence in torch
         valid = ray_count > 0
         nvalid = valid.sum(-1)
         n = int(min(int(nvalid.min().item()), self.field.aggregator.ray_subsamples)) if N > 0 else 0

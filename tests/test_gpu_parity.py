@@ -1023,3 +1023,45 @@ def test_folded_heads_stage_matches_unfolded(syn, model, cameras, torch_cuda):
         r = model.renderer(_t(torch, coords), _t(torch, feats), _t(torch, extr), _t(torch, intrn), res, False)
     for k in ("mask", "depth", "channels"):
         np.testing.assert_allclose(r[k].cpu().numpy(), g[k], atol=IMG_TOL, rtol=0, err_msg=k)
+
+
+def test_fused_valid_ray_subsampling(torch_cuda):
+    """Q3 (`aggregator.py:78-119`) on the device: n = min(min #valid, cap); per view a sorted, distinct subset of its valid rays;
+    reproducible per seed; every valid ray equally likely."""
+    torch = torch_cuda
+    from npcd_b200 import ops
+
+    gen = torch.Generator().manual_seed(11)
+    N, R = 37, 300
+    count = (torch.rand((N, R), generator=gen) < 0.35).to(torch.int32) * torch.randint(1, 50, (N, R), generator=gen, dtype=torch.int32)
+    count[5] = 0
+    count[5, [3, 17, 250, 299, 100, 101, 102, 7, 8, 9, 10, 11]] = 4  # the view with the fewest valid rays: 12
+    rc = count.cuda().contiguous()
+    nvalid = (count > 0).sum(1)
+    ids, n = ops.subsample_valid_rays(rc, N, R, 128, seed=123)
+    assert n == int(nvalid.min()) == 12
+    sel = ids.view(N, n).cpu().long()
+    assert torch.equal(sel // R, torch.arange(N)[:, None].expand(N, n))  # right view
+    local = sel % R
+    assert bool((local[:, 1:] > local[:, :-1]).all())  # ascending, distinct
+    assert bool(torch.gather(count, 1, local).gt(0).all())  # only valid rays
+    assert torch.equal(torch.sort(local[5]).values, torch.tensor(sorted([3, 17, 250, 299, 100, 101, 102, 7, 8, 9, 10, 11])))
+    ids2, _ = ops.subsample_valid_rays(rc, N, R, 128, seed=123)
+    ids3, _ = ops.subsample_valid_rays(rc, N, R, 128, seed=124)
+    assert torch.equal(ids, ids2) and not torch.equal(ids, ids3)
+    capped, n_c = ops.subsample_valid_rays(rc, N, R, 5, seed=1)
+    assert n_c == 5 and capped.numel() == N * 5
+    # uniformity: view 0 over 4000 seeds, every valid ray picked with probability n / nvalid
+    one = rc[:1].contiguous()
+    hits = torch.zeros(R)
+    trials = 4000
+    for s in range(trials):
+        i0, n0 = ops.subsample_valid_rays(one, 1, R, 10, seed=s)
+        hits[i0.cpu().long()] += 1
+    v0 = count[0] > 0
+    p = 10.0 / float(v0.sum())
+    assert float(hits[~v0].sum()) == 0
+    sigma = (trials * p * (1 - p)) ** 0.5
+    assert float((hits[v0] - trials * p).abs().max()) < 5 * sigma
+    empty, n_e = ops.subsample_valid_rays(torch.zeros((3, 64), dtype=torch.int32, device="cuda"), 3, 64, 128, seed=0)
+    assert n_e == 0 and empty.numel() == 0
