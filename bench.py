@@ -436,12 +436,16 @@ def run_train(args):
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = ops.LAUNCHES
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     a.record()
-    for _ in range(args.steps):
+    marks[0].record()
+    for i in range(args.steps):
         loss = step()
+        marks[i + 1].record()
     b.record()
     barrier()
     clocks = sampler.stop() if sampler else None
+    per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))
     t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -458,6 +462,7 @@ def run_train(args):
                        "rays_kept_per_view": float(np.mean([n for _, n in stats])), "optimizer": "Adam: lazy dense-equivalent rows on the latent table + torch Adam on the 24 MLP tensors",
                        "l2": "per-step stash (~1 GB) >> L2"},
             "clocks": clocks, "gpu_launches": ops.LAUNCHES - launches0, "loss": float(loss.detach()),
+            "ms_per_step_rank0": {"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1]},
         }
         print(json.dumps(line), flush=True)
     if os.environ.get("NPCD_BENCH_PROFILE") and rank == 0:  # development aid: where does a step spend its time?

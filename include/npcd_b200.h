@@ -140,6 +140,17 @@ typedef struct {
 
 int npcd_tc_pack_weights(const float* w /* [256,k_in] */, int k_in, const int* perm, int k_pad, float scale, void* out,
                          void* stream);
+/* All weight matrices of one step in one launch (<= 24 jobs): packed element (n, k) = scale * (transpose ? w[k*ld + n] : w[n*ld + k])
+ * for n < n_rows and k < k_in (through perm when given), zero elsewhere; same output image as npcd_tc_pack_weights.              */
+typedef struct {
+  const float* w;
+  long long ld;
+  int n_rows, k_in, k_pad, transpose;
+  const int* perm;
+  float scale;
+  void* out;
+} npcd_tc_pack_job;
+int npcd_tc_pack_weights_batched(const npcd_tc_pack_job* jobs, int n_jobs, void* stream);
 /* workspace (device bytes) for `capacity` kept samples (< 2^27 per launch): the pre-split [S,256] aggregate image that links the
  * pair stage to the heads stage, the dense pair packing (pair offsets, tile starts) and scan scratch.                          */
 int npcd_field_tc_workspace_bytes(long long capacity, size_t* bytes);

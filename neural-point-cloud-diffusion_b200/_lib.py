@@ -64,6 +64,13 @@ class TcWeights(C.Structure):
     ]
 
 
+class PackJob(C.Structure):
+    """mirror of ``npcd_tc_pack_job``"""
+
+    _fields_ = [("w", P), ("ld", C.c_longlong), ("n_rows", C.c_int), ("k_in", C.c_int), ("k_pad", C.c_int), ("transpose", C.c_int),
+                ("perm", P), ("scale", C.c_float), ("out", P)]
+
+
 class PairStashLayout(C.Structure):
     """mirror of ``npcd_pair_stash_layout``"""
 
@@ -96,6 +103,7 @@ SIGNATURES = {
     "npcd_knn_points": [P, P, L, I, I, P, P, F, P, P],
     "npcd_field_simt_fwd": [P, P, P, P, P, L, P, P, P, P, I, I, P],
     "npcd_tc_pack_weights": [P, I, P, I, F, P, P],
+    "npcd_tc_pack_weights_batched": [P, I, P],
     "npcd_field_tc_workspace_bytes": [L, P],
     "npcd_field_tc_fwd": [P, P, P, P, P, L, P, P, C.c_size_t, P, P, I, P, I, P],
     "npcd_tc_rows_to_image": [P, L, P, P],

@@ -774,6 +774,28 @@ __global__ void k_pack_weights(const float* __restrict__ w, int k_in, const int*
   *reinterpret_cast<__half*>(tile + kTileBytesW + off) = lo;
 }
 
+// Batched variant: every weight matrix of a training step (10 forward layers, 4 + 6 transposed dgrad operands) in ONE launch;
+// a job may read its source transposed and keep only the first n_rows packed rows (layer 0 of the dgrad chain: 32 feature rows).
+struct PackJobs {
+  npcd_tc_pack_job j[24];
+};
+__global__ void __launch_bounds__(256) k_pack_weights_batched(const __grid_constant__ PackJobs J) {
+  const npcd_tc_pack_job& job = J.j[blockIdx.y];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (n, k') pairs
+  if (idx >= 256 * job.k_pad) return;
+  const int n = idx / job.k_pad, kp = idx % job.k_pad;
+  const int src = job.perm ? job.perm[kp] : (kp < job.k_in ? kp : -1);
+  float v = 0.f;
+  if (src >= 0 && n < job.n_rows) v = (job.transpose ? job.w[(size_t)src * job.ld + n] : job.w[(size_t)n * job.ld + src]) * job.scale;
+  const __half hi = __float2half_rn(v);
+  const __half lo = __float2half_rn(v - __half2float(hi));
+  const int kb = kp >> 6, kk = kp & 63;
+  uint8_t* tile = (uint8_t*)job.out + (size_t)kb * 2 * kTileBytesW;
+  const size_t off = (size_t)(n >> 3) * 1024 + (n & 7) * 128 + (((kk >> 3) ^ (n & 7)) << 4) + (kk & 7) * 2;
+  *reinterpret_cast<__half*>(tile + off) = hi;
+  *reinterpret_cast<__half*>(tile + kTileBytesW + off) = lo;
+}
+
 // fp32 rows [n,256] <-> the pre-split operand image (per 128-row tile: 4 K-blocks x (hi 16 KB, lo 16 KB), SWIZZLE_128B)
 __global__ void k_rows_to_image(const float* __restrict__ x, long long n, uint8_t* __restrict__ img) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (row, 8-column chunk)
@@ -908,6 +930,22 @@ extern "C" int npcd_tc_pack_weights(const float* w, int k_in, const int* perm, i
   const int n = 256 * k_pad;
   tc::k_pack_weights<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, k_in, perm, k_pad, scale, (uint8_t*)out);
   return check_launch("npcd_tc_pack_weights");
+}
+
+extern "C" int npcd_tc_pack_weights_batched(const npcd_tc_pack_job* jobs, int n_jobs, void* stream) {
+  NPCD_CHECK_ARG(jobs && n_jobs >= 0 && n_jobs <= 24, "at most 24 jobs per call");
+  if (n_jobs == 0) return 0;
+  tc::PackJobs J;
+  memset(&J, 0, sizeof(J));
+  for (int i = 0; i < n_jobs; ++i) {
+    const npcd_tc_pack_job& j = jobs[i];
+    NPCD_CHECK_ARG(j.w && j.out, "null pointer");
+    NPCD_CHECK_ARG(j.k_in > 0 && j.k_pad > 0 && j.k_pad % 16 == 0 && j.k_pad <= 256 && (j.perm || j.k_in <= j.k_pad), "bad sizes");
+    NPCD_CHECK_ARG(j.n_rows > 0 && j.n_rows <= 256 && j.ld > 0 && !(j.perm && j.transpose), "bad job");
+    J.j[i] = j;
+  }
+  tc::k_pack_weights_batched<<<dim3(256, n_jobs), 256, 0, (cudaStream_t)stream>>>(J);
+  return check_launch("npcd_tc_pack_weights_batched");
 }
 
 extern "C" int npcd_tc_rows_to_image(const float* rows, long long n, void* image, void* stream) {

@@ -43,12 +43,15 @@ class MLP(Module):
         return {"simt": "f32", "tc": "f32 (fp16 2-way split, 3-product tcgen05 emulation, fp32 accumulate)"}[self.mlp_impl]
 
     # ---- weights packed for the kernels, re-packed whenever a parameter changes (optimizer step, load_state_dict) ----
-    def packed_weights(self):
+    def packed_weights(self, for_training: bool = False):
         params = list(self.parameters())
         key = (self.mlp_impl,) + tuple((p.data_ptr(), p._version) for p in params)
         if self._packed is None or key != self._packed_key:
-            cls = ops.PackedTcWeights if self.mlp_impl == "tc" else ops.PackedSimtWeights
-            self._packed = cls(self.aggregator.local_field, self.shape_net, self.channel_net, self.aggregator.in_dim)
+            if self.mlp_impl == "tc":  # training: the transposed operands of the backward kernels ride in the same pack launch
+                self._packed = ops.PackedTcWeights(self.aggregator.local_field, self.shape_net, self.channel_net, self.aggregator.in_dim,
+                                                   for_training=for_training)
+            else:
+                self._packed = ops.PackedSimtWeights(self.aggregator.local_field, self.shape_net, self.channel_net, self.aggregator.in_dim)
             self._packed_key = key
         return self._packed
 
@@ -68,7 +71,7 @@ class MLP(Module):
             lin = lambda seq: [m for m in seq if isinstance(m, torch.nn.Linear)]
             params = [t for l in lin(self.aggregator.local_field) + lin(self.shape_net) + lin(self.channel_net)
                       for t in (l.weight, l.bias)]
-            return ops.FieldFn.apply(kp_feat, nbr_idx, sample_pos, kp_pos, n_samples_dev, self.packed_weights(), *params)
+            return ops.FieldFn.apply(kp_feat, nbr_idx, sample_pos, kp_pos, n_samples_dev, self.packed_weights(for_training=True), *params)
         return self.evaluate_autograd_unfused(nbr_idx, sample_pos, kp_pos, kp_feat)
 
     def evaluate_autograd_unfused(self, nbr_idx, sample_pos, kp_pos, kp_feat):

@@ -57,7 +57,9 @@ def _pool_acquire(tag: str, nbytes: int, dev):
         if b.numel() >= nbytes:
             return free.pop(i)
     free.clear()  # every pooled block is too small: drop them, allocate with headroom
-    return torch.empty(int(nbytes * 1.3) + 4096, dtype=torch.uint8, device=dev)
+    # the kept-sample count of a training step varies by +-30 % around its mean; 1.6x headroom makes a regrowth (a cudaMalloc of
+    # gigabytes: ~190 ms measured) a once-per-run event instead of a once-per-few-dozen-steps one
+    return torch.empty(int(nbytes * 1.6) + 4096, dtype=torch.uint8, device=dev)
 
 
 def _pool_release(tag: str, buf):
@@ -304,117 +306,169 @@ def pair_input_perm(feat_dim: int = 32, n_freqs: int = 10):
 
 class PackedTcWeights:
     """MLP weights packed for ``npcd_field_tc_fwd``: pre-swizzled fp16 hi/lo tiles on the device, power-of-two scaled; biases and
-    the two narrow output layers as HOST arrays (they travel to the kernel by value; see include/npcd_b200.h)."""
+    the two narrow output layers as HOST arrays (they travel to the kernel by value; see include/npcd_b200.h).
 
-    def __init__(self, local_field, shape_net, channel_net, feat_dim: int):
+    Re-built whenever a parameter changes, i.e. on every training step -- so the whole build is ONE multi-tensor max|w| reduction, one
+    device->host transfer and ONE batched pack launch (`npcd_tc_pack_weights_batched`: 10 forward layers and, with ``for_training``,
+    the 4 + 6 transposed operands of the fused backward kernels) instead of ~65 small launches."""
+
+    def __init__(self, local_field, shape_net, channel_net, feat_dim: int, for_training: bool = False):
         if feat_dim != 32:
             raise NotImplementedError("tensor-core field kernel is specialised for feat_dim=32 (use mlp_impl='simt')")
         lin = lambda seq: [m for m in seq if isinstance(m, torch.nn.Linear)]
         lf, sn, cn = lin(local_field), lin(shape_net), lin(channel_net)
         assert len(lf) == 5 and len(sn) == 2 and len(cn) == 5, "unexpected MLP depth"
         dev = lf[0].weight.device
+        self.dev = dev
         self.keep = []
         s = _lib.TcWeights()
         s.feat_dim = feat_dim
-        perm0 = torch.tensor(pair_input_perm(), dtype=torch.int32, device=dev)
-        self.keep.append(perm0)
+        self.perm0 = _pair_perm_tensor(dev)
         layers = [lf[0], lf[1], lf[2], lf[3], lf[4], sn[0], cn[0], cn[1], cn[2], cn[3]]
-        # inference folds local_field.8 (linear, no activation, `fields/aggregators/mlp.py:84`) into the two layers that consume its
-        # output: W' = W W_8, b' = W b_8 + b (float64 product, rounded once) -- one 256x256 GEMM less per shading sample
-        w8, b8 = lf[4].weight.detach().double(), lf[4].bias.detach().double()
-        folded = [((l.weight.detach().double() @ w8).float().contiguous(), (l.weight.detach().double() @ b8 + l.bias.detach().double()).float())
-                  for l in (sn[0], cn[0])]
+        self.layers = layers
+        ws = [l.weight.detach().float().contiguous() for l in layers]
+        self.ws = ws
         # one device->host transfer for everything the host needs: per-layer max|w| (scales), biases, narrow output layers
-        small = torch.cat([torch.stack([l.weight.detach().float().abs().max() for l in layers] + [w.abs().max() for w, _ in folded])]
+        small = torch.cat([torch.stack(torch._foreach_norm(ws, float("inf")))]
                           + [l.bias.detach().float().reshape(-1) for l in layers]
                           + [sn[1].weight.detach().float().reshape(-1), sn[1].bias.detach().float().reshape(-1),
-                             cn[4].weight.detach().float().reshape(-1), cn[4].bias.detach().float().reshape(-1)]
-                          + [b.reshape(-1) for _, b in folded]).cpu().numpy()
-        maxabs, fold_maxabs, off = small[:10], small[10:12], 12
+                             cn[4].weight.detach().float().reshape(-1), cn[4].bias.detach().float().reshape(-1)]).cpu().numpy()
+        maxabs = small[:10]
         self.maxabs = maxabs
+        self._off = 10
+        self._small = small
         self.pair_linears = lf[:4]
         self.head_linears = [cn[3], cn[2], cn[1], cn[0], sn[0], lf[4]]  # order of use in npcd_heads_tc_bwd
         self._dgrad = None
         self._hdgrad = None
-
-        def host(n):
-            nonlocal off
-            a = np.ascontiguousarray(small[off:off + n], dtype=np.float32)
-            off += n
-            self.keep.append(a)
-            return a.ctypes.data
+        self._folded = None
+        self.scales = [2.0 ** math.floor(math.log2(4.0 / float(m))) if m > 0 else 1.0 for m in maxabs]
+        jobs = []
 
         def layer(dst, i, k_pad, perm=None):
-            l = layers[i]
-            w = l.weight.detach().float().contiguous()
+            w = ws[i]
             assert w.shape[0] == HIDDEN
-            scale = 2.0 ** math.floor(math.log2(4.0 / float(maxabs[i]))) if maxabs[i] > 0 else 1.0
-            n_kb = (k_pad + 63) // 64
-            out = torch.zeros(n_kb * 2 * 32768, dtype=torch.uint8, device=dev)
-            call("npcd_tc_pack_weights", ptr(w), w.shape[1], ptr(perm), k_pad, float(scale), ptr(out), _stream())
-            _count(1)
-            self.keep += [w, out]
-            dst.packed_w, dst.bias, dst.inv_scale, dst.k_pad = out.data_ptr(), host(HIDDEN), 1.0 / scale, k_pad
+            out = torch.empty(((k_pad + 63) // 64) * 2 * 32768, dtype=torch.uint8, device=dev)
+            if k_pad % 64:
+                out.zero_()  # the tail of the last K-block is never written by the pack kernel
+            jobs.append(self._job(w, w.shape[1], HIDDEN, w.shape[1], k_pad, False, perm, self.scales[i], out))
+            dst.packed_w, dst.bias, dst.inv_scale, dst.k_pad = out.data_ptr(), self._host(HIDDEN), 1.0 / self.scales[i], k_pad
 
-        layer(s.pair[0], 0, 112, perm0)
+        layer(s.pair[0], 0, 112, self.perm0)
         for i in range(1, 4):
             layer(s.pair[i], i, 256)
         layer(s.agg, 4, 256)
         layer(s.shape, 5, 256)
         for i in range(4):
             layer(s.chan[i], 6 + i, 256)
-        s.shape_out_w, s.shape_out_b = host(HIDDEN), host(1)
-        s.chan_out_w, s.chan_out_b = host(3 * HIDDEN), host(3)
+        s.shape_out_w, s.shape_out_b = self._host(HIDDEN), self._host(1)
+        s.chan_out_w, s.chan_out_b = self._host(3 * HIDDEN), self._host(3)
+        if for_training:
+            jobs += self._dgrad_jobs() + self._hdgrad_jobs()
+        self._run(jobs)
         self.struct = s
-        # second view of the same weights for the folded heads stage (stages bit 2): shape / chan[0] replaced, agg unused
-        f = _lib.TcWeights()
-        C.memmove(C.byref(f), C.byref(s), C.sizeof(_lib.TcWeights))
-        for dst, (w, _), m in ((f.shape, folded[0], fold_maxabs[0]), (f.chan[0], folded[1], fold_maxabs[1])):
-            scale = 2.0 ** math.floor(math.log2(4.0 / float(m))) if m > 0 else 1.0
-            out = torch.zeros(4 * 2 * 32768, dtype=torch.uint8, device=dev)
-            call("npcd_tc_pack_weights", ptr(w), HIDDEN, None, HIDDEN, float(scale), ptr(out), _stream())
+        self.error_flag = _error_flag(dev)
+
+    # ---- helpers --------------------------------------------------------------------------------------------------------
+    def _host(self, n):
+        a = np.ascontiguousarray(self._small[self._off:self._off + n], dtype=np.float32)
+        self._off += n
+        self.keep.append(a)
+        return a.ctypes.data
+
+    def _job(self, w, ld, n_rows, k_in, k_pad, transpose, perm, scale, out):
+        self.keep += [w, out]
+        j = _lib.PackJob()
+        j.w, j.ld, j.n_rows, j.k_in, j.k_pad, j.transpose = w.data_ptr(), ld, n_rows, k_in, k_pad, int(transpose)
+        j.perm, j.scale, j.out = (perm.data_ptr() if perm is not None else None), float(scale), out.data_ptr()
+        return j
+
+    def _run(self, jobs):
+        if jobs:
+            arr = (_lib.PackJob * len(jobs))(*jobs)
+            call("npcd_tc_pack_weights_batched", arr, len(jobs), _stream())
             _count(1)
-            self.keep += [w, out]
-            dst.packed_w, dst.bias, dst.inv_scale, dst.k_pad = out.data_ptr(), host(HIDDEN), 1.0 / scale, HIDDEN
-        self.struct_folded = f
-        self.error_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def _dgrad_jobs(self):
+        """W_l^T of the four pair layers as B operands of `npcd_pair_tc_bwd` ([in, out] row-major, read transposed straight from
+        the nn.Linear weights); layer 0 keeps only its 32 feature rows (the other input columns have no gradient consumer)."""
+        ptrs, invs = (C.c_void_p * 4)(), (C.c_float * 4)()
+        jobs = []
+        for l in range(4):
+            w = self.ws[l]
+            out = torch.empty(4 * 2 * 32768, dtype=torch.uint8, device=self.dev)
+            jobs.append(self._job(w, w.shape[1], 32 if l == 0 else HIDDEN, HIDDEN, HIDDEN, True, None, self.scales[l], out))
+            ptrs[l], invs[l] = out.data_ptr(), 1.0 / self.scales[l]
+        self._dgrad = (ptrs, invs, None)
+        return jobs
+
+    def _hdgrad_jobs(self):
+        """W^T of channel_net.6,4,2,0, shape_net.0 and local_field.8 as B operands of `npcd_heads_tc_bwd`; channel_net.0 and
+        shape_net.0 share one scale (their two GEMMs accumulate into one TMEM accumulator)."""
+        idx = [9, 8, 7, 6, 5, 4]  # positions of those layers in the layer table
+        scales = [self.scales[i] for i in idx]
+        scales[3] = scales[4] = min(scales[3], scales[4])
+        ptrs, invs = (C.c_void_p * 6)(), (C.c_float * 6)()
+        jobs = []
+        for j, i in enumerate(idx):
+            out = torch.empty(4 * 2 * 32768, dtype=torch.uint8, device=self.dev)
+            jobs.append(self._job(self.ws[i], HIDDEN, HIDDEN, HIDDEN, HIDDEN, True, None, scales[j], out))
+            ptrs[j], invs[j] = out.data_ptr(), 1.0 / scales[j]
+        self._hdgrad = (ptrs, invs, None)
+        return jobs
 
     def dgrad_pack(self):
-        """W_l^T of the four pair layers packed as B operands of the fused backward (`npcd_pair_tc_bwd`): [in, out] row-major;
-        layer 0 keeps only its 32 feature rows (the other input columns have no gradient consumer), zero-padded to 256 rows."""
         if self._dgrad is None:
-            dev = self.error_flag.device
-            ptrs, invs, keep = (C.c_void_p * 4)(), (C.c_float * 4)(), []
-            for l, lin in enumerate(self.pair_linears):
-                w = lin.weight.detach().float()
-                wt = w.t().contiguous() if l > 0 else torch.cat([w[:, :32].t(), w.new_zeros(HIDDEN - 32, HIDDEN)]).contiguous()
-                scale = 2.0 ** math.floor(math.log2(4.0 / float(self.maxabs[l]))) if self.maxabs[l] > 0 else 1.0
-                out = torch.zeros(4 * 2 * 32768, dtype=torch.uint8, device=dev)
-                call("npcd_tc_pack_weights", ptr(wt), HIDDEN, None, HIDDEN, float(scale), ptr(out), _stream())
-                _count(1)
-                keep += [wt, out]
-                ptrs[l], invs[l] = out.data_ptr(), 1.0 / scale
-            self._dgrad = (ptrs, invs, keep)
+            self._run(self._dgrad_jobs())
         return self._dgrad
 
     def heads_dgrad_pack(self):
-        """W^T of channel_net.6,4,2,0, shape_net.0 and local_field.8 as B operands of `npcd_heads_tc_bwd`; channel_net.0 and
-        shape_net.0 share one scale (their two GEMMs accumulate into one TMEM accumulator)."""
         if self._hdgrad is None:
-            dev = self.error_flag.device
-            idx = [9, 8, 7, 6, 5, 4]  # positions of those layers in the maxabs table
-            scales = [2.0 ** math.floor(math.log2(4.0 / float(self.maxabs[i]))) if self.maxabs[i] > 0 else 1.0 for i in idx]
-            scales[3] = scales[4] = min(scales[3], scales[4])
-            ptrs, invs, keep = (C.c_void_p * 6)(), (C.c_float * 6)(), []
-            for j, lin in enumerate(self.head_linears):
-                wt = lin.weight.detach().float().t().contiguous()
-                out = torch.zeros(4 * 2 * 32768, dtype=torch.uint8, device=dev)
-                call("npcd_tc_pack_weights", ptr(wt), HIDDEN, None, HIDDEN, float(scales[j]), ptr(out), _stream())
-                _count(1)
-                keep += [wt, out]
-                ptrs[j], invs[j] = out.data_ptr(), 1.0 / scales[j]
-            self._hdgrad = (ptrs, invs, keep)
+            self._run(self._hdgrad_jobs())
         return self._hdgrad
+
+    def folded_struct(self):
+        """Inference view of the same weights with `local_field.8` (linear, no activation, `fields/aggregators/mlp.py:84`) folded into
+        the two layers that consume its output: W' = W W_8, b' = W b_8 + b (float64 product, rounded once) -- one 256x256 GEMM less
+        per shading sample (``stages`` bit 2 of `npcd_field_tc_fwd`).  Built on first use (never during training)."""
+        if self._folded is None:
+            lf4, sn0, cn0 = self.layers[4], self.layers[5], self.layers[6]
+            w8, b8 = lf4.weight.detach().double(), lf4.bias.detach().double()
+            folded = [((l.weight.detach().double() @ w8).float().contiguous(), (l.weight.detach().double() @ b8 + l.bias.detach().double()).float())
+                      for l in (sn0, cn0)]
+            small = torch.cat([torch.stack([w.abs().max() for w, _ in folded])] + [b.reshape(-1) for _, b in folded]).cpu().numpy()
+            f = _lib.TcWeights()
+            C.memmove(C.byref(f), C.byref(self.struct), C.sizeof(_lib.TcWeights))
+            jobs = []
+            for k, (dst, (w, _)) in enumerate(((f.shape, folded[0]), (f.chan[0], folded[1]))):
+                m = float(small[k])
+                scale = 2.0 ** math.floor(math.log2(4.0 / m)) if m > 0 else 1.0
+                out = torch.empty(4 * 2 * 32768, dtype=torch.uint8, device=self.dev)
+                jobs.append(self._job(w, HIDDEN, HIDDEN, HIDDEN, HIDDEN, False, None, scale, out))
+                bias = np.ascontiguousarray(small[2 + k * HIDDEN:2 + (k + 1) * HIDDEN], dtype=np.float32)
+                self.keep.append(bias)
+                dst.packed_w, dst.bias, dst.inv_scale, dst.k_pad = out.data_ptr(), bias.ctypes.data, 1.0 / scale, HIDDEN
+            self._run(jobs)
+            self._folded = f
+        return self._folded
+
+
+_PERM_CACHE = {}
+_FLAG_CACHE = {}
+
+
+def _pair_perm_tensor(dev):
+    t = _PERM_CACHE.get(dev)
+    if t is None:
+        t = _PERM_CACHE[dev] = torch.tensor(pair_input_perm(), dtype=torch.int32, device=dev)
+    return t
+
+
+def _error_flag(dev):
+    t = _FLAG_CACHE.get(dev)
+    if t is None:
+        t = _FLAG_CACHE[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+    return t
 
 
 # inference: fold local_field.8 into the layers that consume it (tests flip this to compare both heads stages)
@@ -444,7 +498,7 @@ def field_tc_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity: 
             ptr(ws), nbytes, ptr(rgbs), ptr(feat))
     _timed("pair_mlp", lambda: call("npcd_field_tc_fwd", *args, 1, ptr(weights.error_flag), sm_count(dev), _stream()))
     if FOLD_HEADS and not want_feat:  # local_field.8 folded into shape_net.0 / channel_net.0: 5 GEMMs per sample instead of 6
-        fargs = args[:6] + (C.byref(weights.struct_folded),) + args[7:]
+        fargs = args[:6] + (C.byref(weights.folded_struct()),) + args[7:]
         _timed("heads", lambda: call("npcd_field_tc_fwd", *fargs, 4, ptr(weights.error_flag), sm_count(dev), _stream()))
     else:
         _timed("heads", lambda: call("npcd_field_tc_fwd", *args, 2, ptr(weights.error_flag), sm_count(dev), _stream()))

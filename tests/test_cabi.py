@@ -103,7 +103,7 @@ def test_training_stash_layout_is_consistent(lib):
         fn.restype = ctypes.c_int
         fn.argtypes = [ctypes.c_longlong, ctypes.c_void_p]
         assert fn(cap, ctypes.byref(lay)) == 0
-        assert lay.max_tiles == cap * 8 // 121 + 2 and lay.h_tiles == (cap + 127) // 128
+        assert lay.max_tiles == cap * 8 // 121 + cap // 1024 + 4 and lay.h_tiles == (cap + 127) // 128  # greedy tiles, one short tile per 1024-sample block
         offs = list(lay.x) + list(lay.dp) + list(lay.mask) + [lay.wn, lay.idx, lay.samp, lay.rows_dev] + list(lay.hx) + list(lay.hdp) \
             + list(lay.hmask) + [lay.g4, lay.d_agg, lay.total]
         assert all(o % 256 == 0 for o in offs) and offs == sorted(offs) and len(set(offs)) == len(offs)
