@@ -1065,3 +1065,33 @@ def test_fused_valid_ray_subsampling(torch_cuda):
     assert float((hits[v0] - trials * p).abs().max()) < 5 * sigma
     empty, n_e = ops.subsample_valid_rays(torch.zeros((3, 64), dtype=torch.int32, device="cuda"), 3, 64, 128, seed=0)
     assert n_e == 0 and empty.numel() == 0
+
+
+@pytest.mark.parametrize("P", [64, 1024, 2048, 3000])
+def test_knn_query_other_point_counts(P, syn, cameras, torch_cuda):
+    """Point counts other than the reference's 512: the shared-memory kernels take n_points <= 2048, larger clouds the generic
+    global-memory kernels; both against the oracle, bit-exact, on a 24x24 view of a random cloud."""
+    torch = torch_cuda
+    from npcd_b200 import ops
+
+    poses, intr = cameras
+    rng = np.random.default_rng(P)
+    pts = (rng.normal(0, 1, (1, P, 3)) * np.array([0.35, 0.2, 0.15])).astype(np.float32).clip(-0.95, 0.95)
+    res = 24
+    e, k = poses[[3, 77]][None], syn.scale_intrinsics(intr[[3, 77]], res)[None]
+    rays = ops.rays_generate(_t(torch, e.reshape(-1, 4, 4)), _t(torch, k.reshape(-1, 3, 3)), res)
+    grid = ops.grid_build(_t(torch, pts))
+    vb, cnt = ops.march_count(rays, grid, 2, 0.08, 50)
+    assert (grid.masks is not None) == (P <= 2048)
+    off = ops.scan_counts(cnt)
+    S = int(off[-1].item())
+    nbr, pos, _ = ops.knn_fill(rays, grid, 2, 0.08, vb, off, S)
+    o, d = orc.generate_rays(e.reshape(-1, 4, 4), k.reshape(-1, 3, 3), res)
+    o, d = o.reshape(1, 2, -1, 3), d.reshape(1, 2, -1, 3)
+    s0, e0 = orc.get_ray_limits(o, d)
+    x = orc.sample_positions(o, d, orc.sample_depths(s0, e0))
+    ref = orc.query_keypoints_exact(x, pts)
+    assert S == ref["neighbor_idx"].shape[0] and S > 0
+    np.testing.assert_array_equal(cnt.cpu().numpy().reshape(-1), ref["ray_count"].reshape(-1))
+    np.testing.assert_array_equal(nbr.cpu().numpy(), ref["neighbor_idx"])
+    np.testing.assert_array_equal(pos.cpu().numpy()[:, :3], ref["shading_pts"])
