@@ -227,7 +227,8 @@ __global__ void __launch_bounds__(128) k_knn_fill(const float* __restrict__ cam,
 //   * k_knn_fill_s: thread per kept sample of the chunk (its ray found by a binary search over the chunk's offsets in shared memory).
 constexpr int kSmemMaxPoints = 2048;
 constexpr int kChunk = 256;       // rays per CTA
-constexpr int kQueue = 4096;      // uncertain samples queued per CTA (overflow: tested in line by the owning lane)
+constexpr int kWarpQueue = 512;   // uncertain samples queued per warp (8 warps per CTA: 8 KB)
+constexpr int kQueue = 8 * kWarpQueue;
 constexpr int kFineRes = kGrid * 4;
 
 struct SGrid {
@@ -300,7 +301,6 @@ __global__ void __launch_bounds__(kChunk) k_march_count_s(const float* __restric
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ uint32_t valid_s[kChunk * 4];
   __shared__ uint16_t queue[kQueue];
-  __shared__ int q_count, q_valid;
   __shared__ float step_tab[kDepthRes];  // i / 127 rounded once (math_utils.py:106-115): saves an IEEE division per depth sample
   const int obj = blockIdx.x / chunks_per_obj, chunk = blockIdx.x % chunks_per_obj;
   const long long rays_per_obj = (long long)rays_per_view * views_per_obj;
@@ -311,7 +311,6 @@ __global__ void __launch_bounds__(kChunk) k_march_count_s(const float* __restric
   const ulonglong2* mk = masks ? masks + (size_t)obj * kGridCells : nullptr;
   for (int i = threadIdx.x; i < kChunk * 4; i += blockDim.x) valid_s[i] = 0u;
   for (int i = threadIdx.x; i < kDepthRes; i += blockDim.x) step_tab[i] = __fdiv_rn((float)i, (float)(kDepthRes - 1));
-  if (threadIdx.x == 0) { q_count = 0; q_valid = kQueue; }
   __syncthreads();
   // sample_depth() of common.cuh with the division looked up
   auto depth_of = [&](float t0, float t1, int i, const float* jit) {
@@ -332,94 +331,117 @@ __global__ void __launch_bounds__(kChunk) k_march_count_s(const float* __restric
     z = axpy_rn(oz, t, __ldg(dirs + ray * 3 + 2));
   };
 
-  // ---- pass 1: classify ----
-  for (int r = warp; r < n_local; r += n_warps) {
-    const long long ray = ray0 + r;
-    const int view = (int)(ray / rays_per_view);
-    const float ox = __ldg(cam + view * 3), oy = __ldg(cam + view * 3 + 1), oz = __ldg(cam + view * 3 + 2);
-    const float dx = __ldg(dirs + ray * 3), dy = __ldg(dirs + ray * 3 + 1), dz = __ldg(dirs + ray * 3 + 2);
-    const float t0 = __ldg(start + ray), t1 = __ldg(end + ray);
-    const float* jit = jitter ? jitter + ray * kDepthRes : nullptr;
-    int i_lo = 0, i_hi = kDepthRes - 1;  // conservative sample range inside the object's box (see k_march_count)
-    if (aabb) {
-      const float* bx = aabb + (size_t)obj * 6;
-      float tmin = -INFINITY, tmax = INFINITY;
-      bool miss = false;
-      const float o3[3] = {ox, oy, oz}, d3[3] = {dx, dy, dz};
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        const float lo = __ldg(bx + a), hi = __ldg(bx + 3 + a);
-        if (fabsf(d3[a]) < 1e-12f) {
-          miss |= (o3[a] < lo || o3[a] > hi);
-        } else {
-          const float inv = 1.0f / d3[a];
-          const float ta = (lo - o3[a]) * inv, tb = (hi - o3[a]) * inv;
-          tmin = fmaxf(tmin, fminf(ta, tb));
-          tmax = fminf(tmax, fmaxf(ta, tb));
-        }
-      }
-      const float span = t1 - t0;
-      if (miss || tmin > tmax || !(span > 0.f)) {
-        if (miss || tmin > tmax) i_hi = -1;
-      } else {
-        const float sc = (float)(kDepthRes - 1) / span;
-        const float flo = (tmin - t0) * sc - 2.0f, fhi = (tmax - t0) * sc + 2.0f;
-        i_lo = flo <= 0.f ? 0 : (flo >= (float)kDepthRes ? kDepthRes : (int)flo);
-        i_hi = fhi >= (float)(kDepthRes - 1) ? kDepthRes - 1 : (fhi < 0.f ? -1 : (int)fhi + 1);
-        i_hi = min(i_hi, kDepthRes - 1);
+  // Every warp owns every n_warps-th group of 8 of the CTA's rays and a private queue of uncertain samples; nothing in the loop below needs a
+  // CTA-wide barrier (a version that drained one shared queue in rounds between __syncthreads lost more to the barrier imbalance
+  // -- most warps of a round hold rays that miss the cloud -- than it won).  Per group of 8 rays:
+  //   1a, lane per ray : ray parameters + clip against the object's box -> conservative sample range [i_lo, i_hi]
+  //                      (30 % of the executed instructions when every lane of a warp repeated this for one ray);
+  //   1b, warp per ray : only rays whose range is not empty, parameters broadcast by shuffles; 32 samples classified at a time,
+  //                      uncertain ones appended to the warp's queue;
+  //   2 , lane per queued sample (whenever the queue could not take another ray, and at the end): exact early-exit test, hits
+  //                      OR-ed into the shared validity words.  (ncu on the first version, one shared queue that overflowed into an
+  //                      in-line test: 39 % of the instructions ran at 2-3 active lanes.)
+  uint16_t* wq = queue + warp * kWarpQueue;
+  int qn = 0;  // warp-uniform
+  auto drain = [&]() {
+    for (int q0 = 0; q0 < qn; q0 += 32) {
+      const int q = q0 + lane;
+      if (q < qn) {
+        const int item = wq[q];
+        const int r = item >> 7, i = item & 127;
+        float x, y, z;
+        sample_xyz(ray0 + r, i, x, y, z);
+        if (any_within(g, x, y, z, T)) atomicOr(&valid_s[r * 4 + (i >> 5)], 1u << (i & 31));
       }
     }
+    __syncwarp();
+    qn = 0;
+  };
+  for (int g0 = warp * 8; g0 < n_local; g0 += n_warps * 8) {  // groups of 8 rays, interleaved over the warps (load balance)
+    const int r_mine = g0 + lane;  // lanes 0..7 own one ray each
+    const bool has_ray = lane < 8 && r_mine < n_local;
+    float ox = 0.f, oy = 0.f, oz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f, t0 = 0.f, t1 = 0.f;
+    int i_lo = 0, i_hi = -1;
+    if (has_ray) {
+      const long long ray = ray0 + r_mine;
+      const int view = (int)(ray / rays_per_view);
+      ox = __ldg(cam + view * 3), oy = __ldg(cam + view * 3 + 1), oz = __ldg(cam + view * 3 + 2);
+      dx = __ldg(dirs + ray * 3), dy = __ldg(dirs + ray * 3 + 1), dz = __ldg(dirs + ray * 3 + 2);
+      t0 = __ldg(start + ray), t1 = __ldg(end + ray);
+      i_hi = kDepthRes - 1;  // conservative sample range inside the object's box (see k_march_count)
+      if (aabb) {
+        const float* bx = aabb + (size_t)obj * 6;
+        float tmin = -INFINITY, tmax = INFINITY;
+        bool miss = false;
+        const float o3[3] = {ox, oy, oz}, d3[3] = {dx, dy, dz};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (j * 32 > i_hi || j * 32 + 31 < i_lo) continue;  // warp-uniform
-      const int i = j * 32 + lane;
-      const float t = depth_of(t0, t1, i, jit);
-      const float x = axpy_rn(ox, t, dx), y = axpy_rn(oy, t, dy), z = axpy_rn(oz, t, dz);
-      bool sure = false, unc = false;
-      if (i >= i_lo && i <= i_hi) {
-        const int fx = fine_coord(x), fy = fine_coord(y), fz = fine_coord(z);
-        const int c = ((fz >> 2) * kGrid + (fy >> 2)) * kGrid + (fx >> 2);  // == grid_coord cell: scaling by 4 commutes with rounding
-        if ((g.occ[c >> 5] >> (c & 31)) & 1u) {
-          // samples pushed outside the cube (jitter, rounding) are clamped into border sub-cells they do not lie in: exact test
-          const bool border = fx == 0 || fy == 0 || fz == 0 || fx == kFineRes - 1 || fy == kFineRes - 1 || fz == kFineRes - 1;
-          if (mk && !border) {
-            const ulonglong2 m = __ldg(mk + c);
-            const int bit = ((fz & 3) * 4 + (fy & 3)) * 4 + (fx & 3);
-            sure = (m.x >> bit) & 1ull;
-            unc = !sure && ((m.y >> bit) & 1ull);
+        for (int a = 0; a < 3; ++a) {
+          const float lo = __ldg(bx + a), hi = __ldg(bx + 3 + a);
+          if (fabsf(d3[a]) < 1e-12f) {
+            miss |= (o3[a] < lo || o3[a] > hi);
           } else {
-            unc = true;
+            const float inv = 1.0f / d3[a];
+            const float ta = (lo - o3[a]) * inv, tb = (hi - o3[a]) * inv;
+            tmin = fmaxf(tmin, fminf(ta, tb));
+            tmax = fminf(tmax, fmaxf(ta, tb));
           }
         }
-      }
-      const uint32_t w_sure = __ballot_sync(0xffffffffu, sure);
-      const uint32_t w_unc = __ballot_sync(0xffffffffu, unc);
-      if (lane == 0 && w_sure) valid_s[r * 4 + j] = w_sure;
-      __syncwarp();  // the plain store is ordered before the atomicOr of the overflow path below
-      if (w_unc) {
-        const int n = __popc(w_unc);
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&q_count, n);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base + n <= kQueue) {
-          if (unc) queue[base + __popc(w_unc & ((1u << lane) - 1u))] = (uint16_t)((r << 7) | i);
+        const float span = t1 - t0;
+        if (miss || tmin > tmax || !(span > 0.f)) {
+          if (miss || tmin > tmax) i_hi = -1;
         } else {
-          if (lane == 0) atomicMin(&q_valid, base);
-          if (unc && any_within(g, x, y, z, T)) atomicOr(&valid_s[r * 4 + j], 1u << lane);
+          const float sc = (float)(kDepthRes - 1) / span;
+          const float flo = (tmin - t0) * sc - 2.0f, fhi = (tmax - t0) * sc + 2.0f;
+          i_lo = flo <= 0.f ? 0 : (flo >= (float)kDepthRes ? kDepthRes : (int)flo);
+          i_hi = fhi >= (float)(kDepthRes - 1) ? kDepthRes - 1 : (fhi < 0.f ? -1 : (int)fhi + 1);
+          i_hi = min(i_hi, kDepthRes - 1);
         }
       }
     }
+    uint32_t todo = __ballot_sync(0xffffffffu, has_ray && i_hi >= i_lo);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int r = g0 + src;
+      const float rox = __shfl_sync(0xffffffffu, ox, src), roy = __shfl_sync(0xffffffffu, oy, src), roz = __shfl_sync(0xffffffffu, oz, src);
+      const float rdx = __shfl_sync(0xffffffffu, dx, src), rdy = __shfl_sync(0xffffffffu, dy, src), rdz = __shfl_sync(0xffffffffu, dz, src);
+      const float rt0 = __shfl_sync(0xffffffffu, t0, src), rt1 = __shfl_sync(0xffffffffu, t1, src);
+      const int r_lo = __shfl_sync(0xffffffffu, i_lo, src), r_hi = __shfl_sync(0xffffffffu, i_hi, src);
+      const float* jit = jitter ? jitter + (ray0 + r) * kDepthRes : nullptr;
+      if (qn > kWarpQueue - kDepthRes) drain();  // room for every sample of this ray
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j * 32 > r_hi || j * 32 + 31 < r_lo) continue;  // warp-uniform
+        const int i = j * 32 + lane;
+        const float t = depth_of(rt0, rt1, i, jit);
+        const float x = axpy_rn(rox, t, rdx), y = axpy_rn(roy, t, rdy), z = axpy_rn(roz, t, rdz);
+        bool sure = false, unc = false;
+        if (i >= r_lo && i <= r_hi) {
+          const int fx = fine_coord(x), fy = fine_coord(y), fz = fine_coord(z);
+          const int c = ((fz >> 2) * kGrid + (fy >> 2)) * kGrid + (fx >> 2);  // == grid_coord cell: scaling by 4 commutes with rounding
+          if ((g.occ[c >> 5] >> (c & 31)) & 1u) {
+            // samples pushed outside the cube (jitter, rounding) are clamped into border sub-cells they do not lie in: exact test
+            const bool border = fx == 0 || fy == 0 || fz == 0 || fx == kFineRes - 1 || fy == kFineRes - 1 || fz == kFineRes - 1;
+            if (mk && !border) {
+              const ulonglong2 m = __ldg(mk + c);
+              const int bit = ((fz & 3) * 4 + (fy & 3)) * 4 + (fx & 3);
+              sure = (m.x >> bit) & 1ull;
+              unc = !sure && ((m.y >> bit) & 1ull);
+            } else {
+              unc = true;
+            }
+          }
+        }
+        const uint32_t w_sure = __ballot_sync(0xffffffffu, sure);
+        const uint32_t w_unc = __ballot_sync(0xffffffffu, unc);
+        if (lane == 0 && w_sure) valid_s[r * 4 + j] = w_sure;  // this warp owns ray r: ordered before its own atomicOr in drain()
+        if (unc) wq[qn + __popc(w_unc & ((1u << lane) - 1u))] = (uint16_t)((r << 7) | i);
+        qn += __popc(w_unc);
+      }
+      __syncwarp();
+    }
   }
-  __syncthreads();
-  // ---- pass 2: exact test of the queued samples, one per thread ----
-  const int n_items = min(q_count, q_valid);
-  for (int q = threadIdx.x; q < n_items; q += blockDim.x) {
-    const int item = queue[q];
-    const int r = item >> 7, i = item & 127;
-    float x, y, z;
-    sample_xyz(ray0 + r, i, x, y, z);
-    if (any_within(g, x, y, z, T)) atomicOr(&valid_s[r * 4 + (i >> 5)], 1u << (i & 31));
-  }
+  drain();
   __syncthreads();
   // ---- pass 3: store ----
   for (int i = threadIdx.x; i < n_local * 4; i += blockDim.x) valid_bits[ray0 * 4 + i] = valid_s[i];

@@ -19,6 +19,9 @@ from torch.nn import Embedding as _TorchEmbedding
 
 class FlexEmbedding(_TorchEmbedding):
     def get_extra_state(self):
+        lazy = getattr(self.weight, "lazy_opt", None)
+        if lazy is not None:
+            lazy.flush()  # a checkpoint must hold the dense-Adam table (optim.LazyRowAdam)
         return {"weight": self.weight}
 
     def set_extra_state(self, state):

@@ -66,6 +66,9 @@ class PointNeRF(nn.Module):
 
     def get_all_feats(self):
         w = self.feats.get_emb().weight
+        lazy = getattr(w, "lazy_opt", None)
+        if lazy is not None:
+            lazy.flush()  # rows the lazy optimiser has not touched lately: bring the whole table to the dense-Adam state first
         f = self.opt.model.kp.feat_dim
         if self.opt.model.embedding.type == "VariationalEmbedding":
             return w.reshape(w.shape[0], self.opt.model.kp.num, 2 * f)[:, :, :f]
