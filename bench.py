@@ -439,13 +439,21 @@ def run_train(args):
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     a.record()
     marks[0].record()
+    host_ms = []
     for i in range(args.steps):
+        t_host = time.perf_counter()
         loss = step()
+        host_ms.append(1e3 * (time.perf_counter() - t_host))
         marks[i + 1].record()
     b.record()
     barrier()
     clocks = sampler.stop() if sampler else None
-    per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))
+    raw_steps = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
+    per_step = sorted(raw_steps)
+    if os.environ.get("NPCD_BENCH_TRACE") and rank == 0:  # development aid: which step spiked, and was its sample count a new maximum?
+        worst = int(np.argmax(raw_steps))
+        print(json.dumps({"worst_step": worst, "ms": raw_steps[worst], "S": [s_ for s_, _ in stats],
+                          "host_ms": host_ms}), file=sys.stderr)
     t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
