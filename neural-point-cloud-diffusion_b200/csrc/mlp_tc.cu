@@ -139,9 +139,16 @@ __device__ __forceinline__ void epi_chunk_store(const Params& P, int l, float in
   if (mask_out) *mask_out = mbits;
 }
 
+// Weight sharing across a 2-CTA cluster.  ncu on the single-CTA version: 878 GB per step of L2 -> SM reads, all of it the 0.90 MB of
+// packed weights re-streamed for every 128-row tile -- energy that buys no FLOPs on a board sitting on its power cap.  Both CTAs of a
+// cluster walk the same weight schedule, so CTA 0's producer issues ONE multicast bulk copy per ring stage that lands in both shared
+// memories (and completes both full-barriers); a stage is reused once BOTH CTAs' MMAs have drained it (commit multicast to both
+// empty-barriers, count 2).  A CTA that has one tile fewer than its partner keeps consuming the ring without issuing MMAs.
+constexpr bool kCluster = true;
+
 // ------------------------------------------------------------------------------------------------------------- kernel ----
 template <int kMode>
-__global__ void __launch_bounds__(kMode == MODE_HEADS_TRAIN ? kThreadsTcTrainHeads : kThreadsTc, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_TRAIN ? kThreadsTcTrainHeads : kThreadsTc, 1)
     k_field_tc(const __grid_constant__ Params P) {
   constexpr bool kPair = kMode == MODE_PAIR || kMode == MODE_PAIR_TRAIN;
   constexpr bool kTrainP = kMode == MODE_PAIR_TRAIN;
@@ -162,7 +169,7 @@ __global__ void __launch_bounds__(kMode == MODE_HEADS_TRAIN ? kThreadsTcTrainHea
     return;
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(bar(kBarWFull + i), 1); mbar_init(bar(kBarWEmpty + i), 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(bar(kBarWFull + i), 1); mbar_init(bar(kBarWEmpty + i), kCluster ? 2 : 1); }
     // heads training: a K-block is free for the next tile's first operand once the last layer's MMAs AND the stash copy are done
     for (int i = 0; i < 4; ++i) { mbar_init(bar(kBarARdy + i), 8); mbar_init(bar(kBarA0Rdy + i), 1); mbar_init(bar(kBarAFree + i), kTrainH ? 2 : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar(kBarAccRdy + i), 1); mbar_init(bar(kBarAccFree + i), 8); }
@@ -172,27 +179,35 @@ __global__ void __launch_bounds__(kMode == MODE_HEADS_TRAIN ? kThreadsTcTrainHea
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (kCluster) cluster_sync_all();  // the partner's barriers are initialised before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const long long S = min(*P.n_samples_dev, P.capacity);
   const int n_tiles = kPair ? *P.n_tiles_dev : (int)((S + 127) / 128);
   const int n_layers = P.n_layers;
+  // weight-ring passes of this cluster = tiles of its even CTA (the odd one has as many or one fewer)
+  const uint32_t cta_rank = kCluster ? cluster_ctarank() : 0u;
+  const int first_cta = kCluster ? (int)(blockIdx.x & ~1u) : (int)blockIdx.x;
+  const int n_pass = n_tiles > first_cta ? (n_tiles - first_cta + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (warp == 0) {
     // ================================================= weight producer ==================================================
     // (whole warp runs the loop so every value stays warp-uniform; one elected lane issues the copies)
     int st = 0;
     uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int pass = 0; pass < n_pass; ++pass) {
       for (int l = 0; l < n_layers; ++l) {
         const int nkb = (P.layers[l].ksteps + 3) >> 2;
         const uint8_t* src = P.layers[l].w;
         for (int t = 0; t < 2 * nkb; ++t) {
-          mbar_wait(bar(kBarWEmpty + st), ph ^ 1);
+          mbar_wait(bar(kBarWEmpty + st), ph ^ 1);  // cluster: both CTAs have drained this stage
           if (elect_one()) {
             mbar_expect_tx(bar(kBarWFull + st), kTileBytesW);
-            bulk_g2s(smem_u32(sW + st * kTileBytesW), src + (size_t)t * kTileBytesW, kTileBytesW, bar(kBarWFull + st));
+            if (!kCluster)
+              bulk_g2s(smem_u32(sW + st * kTileBytesW), src + (size_t)t * kTileBytesW, kTileBytesW, bar(kBarWFull + st));
+            else if (cta_rank == 0)
+              bulk_g2s_mc(smem_u32(sW + st * kTileBytesW), src + (size_t)t * kTileBytesW, kTileBytesW, bar(kBarWFull + st), 0x3);
           }
           __syncwarp();
           if (++st == kStages) { st = 0; ph ^= 1; }
@@ -210,7 +225,23 @@ __global__ void __launch_bounds__(kMode == MODE_HEADS_TRAIN ? kThreadsTcTrainHea
     uint32_t lc = 0;                // running layer counter: layer lc accumulates into TMEM columns (lc & 1) * 256
     const uint64_t desc_a0 = make_desc(smem_u32(sA));
     const uint64_t desc_w0 = make_desc(smem_u32(sW));
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int pass = 0, tile = blockIdx.x; pass < n_pass; ++pass, tile += gridDim.x) {
+      if (tile >= n_tiles) {
+        // the partner CTA still has a tile: keep the shared weight ring turning (no MMAs here, plain arrives on both empty-barriers)
+        for (int l = 0; l < n_layers; ++l) {
+          const int nkb = (P.layers[l].ksteps + 3) >> 2;
+          for (int t = 0; t < 2 * nkb; ++t) {
+            mbar_wait(bar(kBarWFull + st), ph_w);
+            if (elect_one()) {
+              mbar_arrive(bar(kBarWEmpty + st));
+              mbar_arrive_remote(bar(kBarWEmpty + st), cta_rank ^ 1u);
+            }
+            __syncwarp();
+            if (++st == kStages) { st = 0; ph_w ^= 1; }
+          }
+        }
+        continue;
+      }
       for (int l = 0; l < n_layers; ++l, ++lc) {
         const uint32_t ab = lc & 1u;
         const uint32_t d_tmem = tmem_base + ab * 256u;
@@ -242,7 +273,7 @@ __global__ void __launch_bounds__(kMode == MODE_HEADS_TRAIN ? kThreadsTcTrainHea
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
               if (ks < ks_n) umma_f16(d_tmem, a_lo + 2 * ks, b + 2 * ks, kIdesc, 1u);
-            umma_commit(bar(kBarWEmpty + st));
+            if (kCluster) umma_commit_mc(bar(kBarWEmpty + st), 0x3); else umma_commit(bar(kBarWEmpty + st));
           }
           __syncwarp();
           if (++st == kStages) { st = 0; ph_w ^= 1; }
@@ -254,7 +285,7 @@ __global__ void __launch_bounds__(kMode == MODE_HEADS_TRAIN ? kThreadsTcTrainHea
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
               if (ks < ks_n) umma_f16(d_tmem, a_hi + 2 * ks, b + 2 * ks, kIdesc, 1u);
-            umma_commit(bar(kBarWEmpty + st));
+            if (kCluster) umma_commit_mc(bar(kBarWEmpty + st), 0x3); else umma_commit(bar(kBarWEmpty + st));
             if (l == n_layers - 1) umma_commit(bar(kBarAFree + kb));  // this K-block may take the next tile's first operand
             if (kb == nkb - 1) umma_commit(bar(kBarAccRdy + ab));
           }
@@ -750,6 +781,7 @@ __global__ void __launch_bounds__(kMode == MODE_HEADS_TRAIN ? kThreadsTcTrainHea
   }
   tc_fence_before();
   __syncthreads();
+  if (kCluster) cluster_sync_all();  // the partner may still multicast into / signal this CTA's shared memory until it is done too
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -1011,7 +1043,8 @@ int launch_tc(const tc::Params& P, long long tiles, int num_sms, cudaStream_t st
     return 2;
   }
   if (num_sms <= 0) num_sms = 148;
-  const unsigned grid = (unsigned)(tiles < num_sms ? (tiles > 0 ? tiles : 1) : num_sms);
+  unsigned grid = (unsigned)(tiles < num_sms ? (tiles > 0 ? tiles : 1) : num_sms);
+  if (tc::kCluster) grid = (grid + 1u) & ~1u;  // whole 2-CTA clusters
   tc::k_field_tc<kMode><<<grid, kMode == tc::MODE_HEADS_TRAIN ? tc::kThreadsTcTrainHeads : tc::kThreadsTc, tc::kSmemTotal, st>>>(P);
   return check_launch(what);
 }
