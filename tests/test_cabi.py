@@ -4,6 +4,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -159,3 +160,86 @@ def test_training_side_modules_fail_loudly_without_cuda():
         NeuralPointCloudTVLoss(holder, 1.0, False)(None, None, {"feats": mean, "coords": torch.zeros(2, 8, 3)}, 0)
     # the reference-style lookup of the same module still works on CPU (plain embedding): only the fused kernels need the device
     assert emb(torch.tensor([2])).shape == (1, 8, 4)
+
+
+def test_argument_errors_of_the_round1b_entry_points(lib):
+    """Null pointers / bad sizes of the newer entry points are rejected on the host (rc 1 + message), before any launch."""
+    import npcd_b200  # noqa: F401
+    from npcd_b200 import _lib
+
+    L = _lib.load()
+    err = lambda: L.npcd_last_error()
+    assert L.npcd_grid_build_masks(None, 1, 512, 0.08, None, None) == 1 and b"null pointer" in err()
+    assert L.npcd_grid_build_masks(ctypes.c_void_p(8), 1, 512, 0.5, ctypes.c_void_p(8), None) == 1 and b"radius" in err()
+    assert L.npcd_subsample_valid_rays(None, 4, 112, 10, 1, None, None) == 1 and b"null pointer" in err()
+    assert L.npcd_subsample_valid_rays(None, 0, 112, 10, 1, None, None) == 0  # nothing to do
+    assert L.npcd_count_valid_rays(None, 4, 112, None, None, None) == 1
+    assert L.npcd_embed_adam_rows(None, None, None, None, None, 2, 128, None, 1, 1e-3, 0.9, 0.999, 1e-8, None) == 1
+    assert L.npcd_embed_adam_rows(None, None, None, None, None, 0, 128, None, 1, 1e-3, 0.9, 0.999, 1e-8, None) == 0
+    assert L.npcd_embed_adam_rows(None, None, None, None, None, 2, 128, None, 0, 1e-3, 0.9, 0.999, 1e-8, None) == 1  # steps are 1-based
+    assert L.npcd_embed_fwd(None, None, 2, 16, 4, None, None, None, None, None, None) == 1
+    assert L.npcd_kl_fwd(None, None, 8, 4, 1.0, None, None) == 1
+    jobs = (_lib.PackJob * 1)()
+    assert L.npcd_tc_pack_weights_batched(jobs, 1, None) == 1 and b"null pointer" in err()  # empty job
+    assert L.npcd_tc_pack_weights_batched(jobs, 25, None) == 1 and b"24 jobs" in err()
+    assert L.npcd_tc_pack_weights_batched(jobs, 0, None) == 0
+    # impl selector of the query kernels
+    p8 = ctypes.c_void_p(8)
+    assert L.npcd_march_count(p8, p8, p8, p8, None, 1024, 128, 8, 4096, p8, p8, p8, None, None, 0.08, 50, p8, p8, 2, None) == 1
+    assert b"shared-memory kernels" in err()
+    assert L.npcd_march_count(p8, p8, p8, p8, None, 1024, 128, 8, 512, p8, p8, p8, None, None, 0.08, 50, p8, p8, 7, None) == 1
+
+
+def test_lazy_row_adam_algorithm_equals_dense_adam_in_numpy():
+    """The lazy scheme itself, restated in numpy next to the dense oracle: replaying the missed zero-gradient steps when a row is
+    READ (before the forward) and applying the current gradient afterwards gives the dense optimiser's table, bit for bit in this
+    arithmetic, for random touch patterns -- while skipping the catch-up before the read does not (the gradient of the KL term sees
+    a stale row)."""
+    from oracle import embedding_oracle as eo
+
+    rng = np.random.default_rng(0)
+    n_obj, P, F, lr, kw = 9, 4, 3, 1e-2, 0.5
+    table0 = np.concatenate([rng.standard_normal((n_obj, P, F)), -4 + 0.3 * rng.standard_normal((n_obj, P, F))], -1)
+    table0 = table0.reshape(n_obj, -1).astype(np.float32)
+
+    def loss_grad(w, batch, eps, c):
+        B = len(batch)
+        return eo.dense_row_grad(w, batch, P, F, eps, c, np.full((B, P), 1.0 / (B * P)), kw, n_obj)
+
+    def run(lazy, catch_up_before_read=True):
+        w = table0.copy()
+        m, v = np.zeros_like(w), np.zeros_like(w)
+        last = np.zeros(n_obj, np.int64)
+        r = np.random.default_rng(1)
+
+        def replay(rows, upto):  # zero-gradient dense steps last+1 .. upto of the given rows
+            for row in rows:
+                for s in range(int(last[row]) + 1, upto + 1):
+                    eo.adam_dense_step(w[row:row + 1], m[row:row + 1], v[row:row + 1], np.zeros((1, w.shape[1]), np.float32), s, lr)
+                last[row] = max(last[row], upto)
+
+        for t in range(1, 15):
+            batch = r.integers(0, n_obj, size=3)
+            eps = r.standard_normal((3, P, F)).astype(np.float32)
+            c = r.standard_normal((3, P, F)).astype(np.float32)
+            if lazy and catch_up_before_read:
+                replay(set(batch.tolist()), t - 1)
+            g = loss_grad(w, batch, eps, c)
+            if lazy:
+                rows = sorted(set(batch.tolist()))
+                replay(rows, t - 1)
+                for row in rows:
+                    eo.adam_dense_step(w[row:row + 1], m[row:row + 1], v[row:row + 1], g[row:row + 1], t, lr)
+                    last[row] = t
+            else:
+                eo.adam_dense_step(w, m, v, g, t, lr)
+        if lazy:
+            replay(range(n_obj), 14)
+        return w, m, v
+
+    dense = run(False)
+    lazy = run(True)
+    for a, b in zip(dense, lazy):
+        np.testing.assert_array_equal(a, b)
+    stale = run(True, catch_up_before_read=False)
+    assert np.abs(stale[0] - dense[0]).max() > 0
