@@ -502,7 +502,7 @@ def field_tc_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity: 
         _timed("heads", lambda: call("npcd_field_tc_fwd", *fargs, 4, ptr(weights.error_flag), sm_count(dev), _stream()))
     else:
         _timed("heads", lambda: call("npcd_field_tc_fwd", *args, 2, ptr(weights.error_flag), sm_count(dev), _stream()))
-    _count(6)  # pair-offset scan (3 launches) + tile starts + pair kernel + heads kernel
+    _count(8)  # pair-offset scan (3 launches) + greedy tile starts (walk, scan, walk) + pair kernel + heads kernel
     if want_agg:
         agg = torch.empty((capacity, HIDDEN), device=dev)
         call("npcd_tc_image_to_rows", ptr(ws), capacity, ptr(agg), _stream())
@@ -743,7 +743,7 @@ def pair_tc_train_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capac
         _stream()))
     agg = torch.empty((capacity, HIDDEN), device=dev)
     call("npcd_tc_image_to_rows", ptr(ws), capacity, ptr(agg), _stream())
-    _count(6)
+    _count(7)  # pair-offset scan (3) + greedy tile starts (3) + pair kernel
     return agg, stash
 
 
@@ -825,7 +825,7 @@ def field_tc_train_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capa
         "npcd_field_tc_train_fwd", ptr(nbr_idx), ptr(sample_pos), ptr(kp_pos), ptr(kp_feat), ptr(n_samples_dev), capacity,
         C.byref(weights.struct), ptr(ws), nbytes, C.byref(lay), ptr(stash.buf), lay.total, ptr(rgbs), ptr(weights.error_flag),
         sm_count(dev), _stream()))
-    _count(7)
+    _count(9)  # pair-offset scan (3) + greedy tile starts (3) + pair kernel + heads kernel + stash bookkeeping
     return rgbs, stash, ws
 
 
