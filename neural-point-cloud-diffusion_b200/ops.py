@@ -743,7 +743,7 @@ def pair_tc_train_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capac
         _stream()))
     agg = torch.empty((capacity, HIDDEN), device=dev)
     call("npcd_tc_image_to_rows", ptr(ws), capacity, ptr(agg), _stream())
-    _count(7)  # pair-offset scan (3) + greedy tile starts (3) + pair kernel
+    _count(8)  # pair-offset scan (3) + greedy tile starts (3) + pair kernel + image -> rows
     return agg, stash
 
 
