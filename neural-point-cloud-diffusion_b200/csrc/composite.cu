@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(256) k_composite_fwd(const float4* __restrict_
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long sel = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   uint32_t dmin = 0xffffffffu, dmax = 0u;
+  bool has_samples = false;  // warp-uniform
   if (sel < n_sel) {
     const long long off = ray_offset[sel];
     const int n = (int)(ray_offset[sel + 1] - off);
@@ -82,7 +83,9 @@ __global__ void __launch_bounds__(256) k_composite_fwd(const float4* __restrict_
       carry *= __shfl_sync(0xffffffffu, incl, 31);
       if (i < n) { dmin = min(dmin, f2ord(s.t)); dmax = max(dmax, f2ord(s.t)); }
     }
-    sw = warp_sum(sw); swt = warp_sum(swt); r = warp_sum(r); g = warp_sum(g); b = warp_sum(b);
+    // 3 of 4 rays of the eval workload carry no sample: their warps skip the five sum reductions and the range reduction below
+    if (n > 0) { sw = warp_sum(sw); swt = warp_sum(swt); r = warp_sum(r); g = warp_sum(g); b = warp_sum(b); }
+    has_samples = n > 0;
     if (lane == 0) {
       if (n == 0) {
         const float e = ray_end[ray_ids ? ray_ids[sel] : sel];
@@ -96,10 +99,12 @@ __global__ void __launch_bounds__(256) k_composite_fwd(const float4* __restrict_
       out_rgb[sel * 3 + 0] = r + bg; out_rgb[sel * 3 + 1] = g + bg; out_rgb[sel * 3 + 2] = b + bg;
     }
   }
+  if (has_samples) {  // otherwise lane 0 alone holds a value (ray_end of a sample-free ray) and it is the lane that publishes
 #pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    dmin = min(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
-    dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    for (int o = 16; o; o >>= 1) {
+      dmin = min(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+      dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    }
   }
   __shared__ uint32_t smin[8], smax[8];
   if (lane == 0) { smin[warp] = dmin; smax[warp] = dmax; }
