@@ -106,9 +106,12 @@ def embedding_tables(module: torch.nn.Module) -> List[torch.nn.Module]:
     return out
 
 
-class PointNeRFAdam:
-    """Drop-in for the trainer's ``torch.optim.Adam(model.pointnerf.parameters(), lr)`` with ``zero_grad()`` / ``step()`` /
-    ``state_dict()``: lazy dense-equivalent row Adam on the latent tables, torch's Adam on the MLP tensors."""
+class PointNeRFAdam(torch.optim.Adam):
+    """Drop-in for the trainer's ``torch.optim.Adam(model.pointnerf.parameters(), lr)``.  It IS a ``torch.optim.Adam`` over the 24 MLP
+    tensors (so ``param_groups`` logging, `StepLR` and the checkpoint savers of `npcd/train/pointnerf_training.py:104-105,184,315` keep
+    working) and additionally runs the lazy dense-equivalent row Adam on the latent tables, whose modules it switches to compact row
+    gradients.  The lazy replay assumes the learning rate did not change between a row's last step and now -- the reference's
+    schedule is constant (`StepLR(gamma=1.0)`, `pointnerf_training.py:105`)."""
 
     def __init__(self, pointnerf: torch.nn.Module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
         from .parallel import mlp_parameters
@@ -118,26 +121,32 @@ class PointNeRFAdam:
             m.row_sparse_grad = True
             self.rows.append(LazyRowAdam(m.get_emb().weight, lr, betas, eps))
         self.mlp_params = mlp_parameters(pointnerf)
-        self.mlp = torch.optim.Adam(self.mlp_params, lr=lr, betas=betas, eps=eps)
+        super().__init__(self.mlp_params, lr=lr, betas=betas, eps=eps)
 
     def zero_grad(self, set_to_none: bool = True):
-        self.mlp.zero_grad(set_to_none=set_to_none)
+        super().zero_grad(set_to_none=set_to_none)
         for r in self.rows:
             r.zero_grad()
 
-    def step(self):
+    @torch.no_grad()
+    def step(self, closure=None):
+        lr = float(self.param_groups[0]["lr"])
         for r in self.rows:
+            r.lr = lr
             r.step()
-        self.mlp.step()
+        return super().step(closure)
 
     def flush(self):
         for r in self.rows:
             r.flush()
 
     def state_dict(self):
-        return {"mlp": self.mlp.state_dict(), "rows": [r.state_dict() for r in self.rows]}
+        sd = super().state_dict()
+        sd["rows"] = [r.state_dict() for r in self.rows]
+        return sd
 
     def load_state_dict(self, sd):
-        self.mlp.load_state_dict(sd["mlp"])
-        for r, s in zip(self.rows, sd["rows"]):
+        rows = sd.get("rows", [])
+        super().load_state_dict({k: v for k, v in sd.items() if k != "rows"})
+        for r, s in zip(self.rows, rows):
             r.load_state_dict(s)

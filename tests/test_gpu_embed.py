@@ -145,6 +145,8 @@ def test_pointnerf_adam_trains_through_the_dropin(syn, weights):
         w.view(n_obj, 512, 64)[:, :, 32:] = -4.0
     m.train()
     opt = PointNeRFAdam(m, lr=1e-3)
+    assert isinstance(opt, torch.optim.Optimizer) and opt.param_groups[0]["lr"] == 1e-3
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=1, gamma=1.0)  # what the reference trainer wraps around it
     holder = types.SimpleNamespace(pointnerf=m)
     kl, tv = NeuralPointCloudKLLoss(holder, 1e-3, False), NeuralPointCloudTVLoss(holder, 1e-3, False)
     poses, intr = syn.load_cameras()
@@ -161,8 +163,12 @@ def test_pointnerf_adam_trains_through_the_dropin(syn, weights):
         loss.backward()
         assert w.grad is None
         opt.step()
+        sched.step()
     torch.cuda.synchronize()
     assert torch.isfinite(loss)
+    sd = opt.state_dict()  # checkpoint savers call this (npcd/utils/checkpoint_utils.py:214,245); it flushes the lazy rows
+    assert set(sd) == {"state", "param_groups", "rows"} and int(sd["rows"][0]["step"]) == 2
+    opt.load_state_dict(sd)
     changed = (w.detach() - w0).abs().amax(dim=1) > 0
     assert changed.cpu().tolist() == [True, False, True, False]
     assert any(float((p.detach() - q).abs().max()) > 0 for p, q in zip(opt.mlp_params, p0))
