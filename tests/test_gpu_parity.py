@@ -1095,3 +1095,37 @@ def test_knn_query_other_point_counts(P, syn, cameras, torch_cuda):
     np.testing.assert_array_equal(cnt.cpu().numpy().reshape(-1), ref["ray_count"].reshape(-1))
     np.testing.assert_array_equal(nbr.cpu().numpy(), ref["neighbor_idx"])
     np.testing.assert_array_equal(pos.cpu().numpy()[:, :3], ref["shading_pts"])
+
+
+def test_voxel_grid_dropin_query_layout(syn, cameras, torch_cuda):
+    """Secondary entry: the `torch_knnquery.VoxelGrid` call sites of the reference (`pointnerf.py:20,67-75`,
+    `aggregator.py:20,63-73`) against the exact oracle: ray mask, per-ray slot layout (-1 padded), global neighbour ids, locations."""
+    torch = torch_cuda
+    from npcd_b200.voxel_grid import VoxelGrid
+
+    poses, intr = cameras
+    coords, _ = syn.make_clouds([2, 3])
+    res, SR = 12, 50
+    e, k = poses[[10, 140]][None].repeat(2, 0), syn.scale_intrinsics(intr[[10, 140]], res)[None].repeat(2, 0)
+    o, d = orc.generate_rays(e.reshape(-1, 4, 4), k.reshape(-1, 3, 3), res)
+    o, d = o.reshape(2, 2, -1, 3), d.reshape(2, 2, -1, 3)
+    s0, e0 = orc.get_ray_limits(o, d)
+    x = orc.sample_positions(o, d, orc.sample_depths(s0, e0))  # [B,T,R,D,3]
+    ref = orc.query_keypoints_exact(x, coords, max_shading_pts=SR)
+    vg = VoxelGrid((0.04, 0.04, 0.04), (2, 2, 2), (3, 3, 3), 4, 5000, (-1.0, -1.0, -1.0, 1.0, 1.0, 1.0))
+    assert vg.vsize_tup == (0.04, 0.04, 0.04)
+    vg.set_pointset(_t(torch, coords), None)
+    B, T, R, D = x.shape[:4]
+    raypos = _t(torch, x.reshape(B, T * R, D, 3))
+    sample_idx, sample_loc, ray_mask = vg.query(raypos, 8, 2, SR)
+    rc = ref["ray_count"].reshape(B, T * R)
+    assert ray_mask.shape == (B, T * R) and int(ray_mask.sum()) == sample_idx.shape[0] == int((rc > 0).sum())
+    np.testing.assert_array_equal(ray_mask.cpu().numpy().astype(bool), rc > 0)
+    assert sample_idx.shape[1:] == (SR, 8) and sample_loc.shape[1:] == (SR, 3)
+    got_idx, got_loc = sample_idx.cpu().numpy(), sample_loc.cpu().numpy()
+    counts = rc[rc > 0]
+    slot = np.arange(SR)[None, :] < counts[:, None]
+    # valid slots in ray-major order == the oracle's compact lists; the rest is -1
+    np.testing.assert_array_equal(got_idx[slot], ref["neighbor_idx"])
+    np.testing.assert_array_equal(got_loc[slot], ref["shading_pts"])
+    assert (got_idx[~slot] == -1).all()
