@@ -94,7 +94,7 @@ struct Params {
   long long capacity;
   int* error_flag;
   // training stash (MODE_PAIR_TRAIN): everything the fused backward (pair_bwd_tc.cu) and the weight-gradient GEMMs need
-  uint8_t* stash_x[4];      // operand images of the layer inputs X_0 (112 columns, 2 K-blocks) and X_1..X_3 (4 K-blocks), per tile
+  uint8_t* stash_x[4];      // operand images of the layer inputs X_0 (96 columns, 2 K-blocks) and X_1..X_3 (4 K-blocks), per tile
   uint32_t* stash_mask[4];  // [tile][128 rows][8] sign bits (y > 0) of the outputs of layers 0..3 (LeakyReLU derivative)
   float* stash_wn;          // [tile][128] normalised inverse-distance weight of every row
   int* stash_idx;           // [tile][128] global point index of every row (-1 = padding)
@@ -440,10 +440,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
 
     if (kPair) {
       // ------------------------------------------------------------------------------------------------- pair mode ----
-      // layer-0 input, 112 columns: [feat 0..31 | x: d, sin*10, cos*10, 0,0,0 | y: ... | z: ... | 8 zeros]
-      // (the column order is OURS; the first-layer weights are permuted to match when they are packed).
-      // half 0 owns columns 0..55 (K-block 0, chunks 0..6); half 1 owns 56..111 (K-block 0 chunk 7, K-block 1 chunks 0..5).
-      uint4 pre_hi[7], pre_lo[7];
+      // layer-0 input, 96 columns = 6 K-steps for the 95 real ones (a 112-column layout with per-axis groups cost a seventh):
+      //   [feat 0..31 | x: (sin, cos) of octaves 0..7 | d_x, (sin, cos)_x of octaves 8, 9 | y: d, (sin, cos) x 10 | z: d, (sin, cos) x 10 | 0]
+      // (the column order is OURS; the first-layer weights are permuted to match when they are packed, ops.pair_input_perm).
+      // half 0 owns columns 0..47 (K-block 0, chunks 0..5); half 1 owns 48..95 (K-block 0 chunks 6, 7; K-block 1 chunks 0..3).
+      uint4 pre_hi[6], pre_lo[6];
 
       auto prologue_compute = [&](int tile, int buf) {
         const int s_begin = __ldg(P.tile_start + tile), s_end = __ldg(P.tile_start + tile + 1);
@@ -481,29 +482,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
           P.stash_samp[(size_t)tile * 128 + row] = row < n_rows ? s_begin + (int)row_samp[row] : -1;
         }
         const float d3[3] = {x.x - px, x.y - py, x.z - pz};
-        auto enc_group = [&](int c, int first_chunk) {  // 24 columns -> pre chunks first_chunk .. first_chunk + 2
-          float v[24];
-          v[0] = d3[c];
-          float fr = 3.14159274101257324f;
+        // (sin, cos) of d * 2^i * pi for n consecutive octaves starting with frequency fr0, interleaved into v[0 .. 2n)
+        auto octaves = [&](float d, float fr0, int n, float* v) {
+          float fr = fr0;
 #pragma unroll
           for (int i = 0; i < kFreqs; ++i) {
-            float sn, cs;
-            sincos_small(d3[c] * fr, sn, cs);
-            v[1 + i] = sn;
-            v[1 + kFreqs + i] = cs;
-            fr *= 2.0f;
-          }
-          v[21] = v[22] = v[23] = 0.f;
-          if (idx < 0) {
-#pragma unroll
-            for (int i = 0; i < 24; ++i) v[i] = 0.f;
-          }
-#pragma unroll
-          for (int ch = 0; ch < 3; ++ch) {
-            const float y[8] = {v[ch * 8], v[ch * 8 + 1], v[ch * 8 + 2], v[ch * 8 + 3], v[ch * 8 + 4], v[ch * 8 + 5], v[ch * 8 + 6], v[ch * 8 + 7]};
-            split8(y, pre_hi[first_chunk + ch], pre_lo[first_chunk + ch]);
+            if (i < n) {
+              float sn, cs;
+              sincos_small(d * fr, sn, cs);
+              v[2 * i] = sn;
+              v[2 * i + 1] = cs;
+              fr *= 2.0f;
+            }
           }
         };
+        const float kPi = 3.14159274101257324f;
         if (half == 0) {
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {
@@ -515,13 +508,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
             }
             split8(y, pre_hi[ch], pre_lo[ch]);
           }
-          enc_group(0, 4);
+          float v[16];
+          octaves(d3[0], kPi, 8, v);
+          if (idx < 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0.f;
+          }
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            const float y[8] = {v[ch * 8], v[ch * 8 + 1], v[ch * 8 + 2], v[ch * 8 + 3], v[ch * 8 + 4], v[ch * 8 + 5], v[ch * 8 + 6], v[ch * 8 + 7]};
+            split8(y, pre_hi[4 + ch], pre_lo[4 + ch]);
+          }
           const float nrm = sqrtf(d3[0] * d3[0] + d3[1] * d3[1] + d3[2] * d3[2]);
           wts_all[buf * 128 + row] = idx >= 0 ? 1.0f / (nrm + 1e-5f) : 0.f;
         } else {
-          enc_group(1, 0);
-          enc_group(2, 3);
-          pre_hi[6] = pre_lo[6] = make_uint4(0u, 0u, 0u, 0u);
+          float v[48];
+          v[0] = d3[0];
+          octaves(d3[0], kPi * 256.0f, 2, v + 1);
+          v[5] = d3[1];
+          octaves(d3[1], kPi, kFreqs, v + 6);
+          v[26] = d3[2];
+          octaves(d3[2], kPi, kFreqs, v + 27);
+          v[47] = 0.f;
+          if (idx < 0) {
+#pragma unroll
+            for (int i = 0; i < 48; ++i) v[i] = 0.f;
+          }
+#pragma unroll
+          for (int ch = 0; ch < 6; ++ch) {
+            const float y[8] = {v[ch * 8], v[ch * 8 + 1], v[ch * 8 + 2], v[ch * 8 + 3], v[ch * 8 + 4], v[ch * 8 + 5], v[ch * 8 + 6], v[ch * 8 + 7]};
+            split8(y, pre_hi[ch], pre_lo[ch]);
+          }
         }
       };
       // store the K-block-kb part of the staged layer-0 input and publish that K-block
@@ -530,22 +547,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
         if (kb == 0) {
           if (half == 0) {
 #pragma unroll
-            for (int c = 0; c < 7; ++c) {
+            for (int c = 0; c < 6; ++c) {
               uint8_t* p = sA + rowbase + ((c ^ x7) << 4);
               *reinterpret_cast<uint4*>(p) = pre_hi[c];
               *reinterpret_cast<uint4*>(p + kTileBytesA) = pre_lo[c];
             }
           } else {
-            uint8_t* p = sA + rowbase + ((7 ^ x7) << 4);
-            *reinterpret_cast<uint4*>(p) = pre_hi[0];
-            *reinterpret_cast<uint4*>(p + kTileBytesA) = pre_lo[0];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint8_t* p = sA + rowbase + (((6 + c) ^ x7) << 4);
+              *reinterpret_cast<uint4*>(p) = pre_hi[c];
+              *reinterpret_cast<uint4*>(p + kTileBytesA) = pre_lo[c];
+            }
           }
         } else if (half == 1) {
 #pragma unroll
-          for (int c = 0; c < 6; ++c) {
+          for (int c = 0; c < 4; ++c) {
             uint8_t* p = sA + 2 * kTileBytesA + rowbase + ((c ^ x7) << 4);
-            *reinterpret_cast<uint4*>(p) = pre_hi[c + 1];
-            *reinterpret_cast<uint4*>(p + kTileBytesA) = pre_lo[c + 1];
+            *reinterpret_cast<uint4*>(p) = pre_hi[c + 2];
+            *reinterpret_cast<uint4*>(p + kTileBytesA) = pre_lo[c + 2];
           }
         }
         publish(kBarARdy + kb);

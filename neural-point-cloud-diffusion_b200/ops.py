@@ -289,18 +289,28 @@ class PackedSimtWeights:
         self.struct = s
 
 
+PAIR_IN_COLS = 96  # width of OUR first-layer input image: the 95 real columns + 1 zero = 6 K-steps of 16
+
+
 def pair_input_perm(feat_dim: int = 32, n_freqs: int = 10):
     """Source column (in the reference's [feat | d(3) | per-axis sin*10, cos*10] order, `aggregators/mlp.py:82`,
-    `positional_encoder.py:17-20`) of every column of OUR 112-wide first-layer input (-1 = zero padding)."""
+    `positional_encoder.py:17-20`) of every column of OUR 96-wide first-layer input (-1 = zero padding).  Layout (mlp_tc.cu prologue):
+    [feat 0..31 | x: (sin, cos) of octaves 0..7 | d_x, (sin, cos)_x of octaves 8, 9 | y: d, (sin, cos) x 10 | z: d, (sin, cos) x 10 | 0]."""
     assert feat_dim == 32 and n_freqs == 10
+    sin = lambda c, i: 35 + 20 * c + i
+    cos = lambda c, i: 35 + 20 * c + 10 + i
     perm = list(range(32))
-    for c in range(3):
+    for i in range(8):
+        perm += [sin(0, i), cos(0, i)]
+    perm.append(32)
+    for i in (8, 9):
+        perm += [sin(0, i), cos(0, i)]
+    for c in (1, 2):
         perm.append(32 + c)
-        perm += [35 + 20 * c + i for i in range(10)]
-        perm += [35 + 20 * c + 10 + i for i in range(10)]
-        perm += [-1, -1, -1]
-    perm += [-1] * 8
-    assert len(perm) == 112
+        for i in range(10):
+            perm += [sin(c, i), cos(c, i)]
+    perm.append(-1)
+    assert len(perm) == PAIR_IN_COLS and sorted(p for p in perm if p >= 0) == list(range(95))
     return perm
 
 
@@ -354,7 +364,7 @@ class PackedTcWeights:
             jobs.append(self._job(w, w.shape[1], HIDDEN, w.shape[1], k_pad, False, perm, self.scales[i], out))
             dst.packed_w, dst.bias, dst.inv_scale, dst.k_pad = out.data_ptr(), self._host(HIDDEN), 1.0 / self.scales[i], k_pad
 
-        layer(s.pair[0], 0, 112, self.perm0)
+        layer(s.pair[0], 0, PAIR_IN_COLS, self.perm0)
         for i in range(1, 4):
             layer(s.pair[i], i, 256)
         layer(s.agg, 4, 256)
@@ -693,7 +703,7 @@ _PAIR_COL_OF_REF = None
 
 
 def pair_ref_col_map(dev):
-    """int32 [95]: position, in OUR 112-column first-layer input order, of every reference input column (wgrad un-permutation)."""
+    """int32 [95]: position, in OUR 96-column first-layer input order, of every reference input column (wgrad un-permutation)."""
     global _PAIR_COL_OF_REF
     if _PAIR_COL_OF_REF is None or _PAIR_COL_OF_REF.device != dev:
         perm = pair_input_perm()
@@ -774,7 +784,7 @@ def pair_tc_bwd(d_agg, stash: PairStash, weights: "PackedTcWeights", n_points_to
     def grads():
         probs = []
         for l in range(4):
-            probs.append(dict(a=stash.image(lay.dp[l], 4, HIDDEN, None), b=stash.image(lay.x[l], 2 if l == 0 else 4, 112 if l == 0 else HIDDEN, None),
+            probs.append(dict(a=stash.image(lay.dp[l], 4, HIDDEN, None), b=stash.image(lay.x[l], 2 if l == 0 else 4, PAIR_IN_COLS if l == 0 else HIDDEN, None),
                               n_out=95 if l == 0 else HIDDEN, col_perm=pair_ref_col_map(dev) if l == 0 else None, out_scale=inv_s,
                               rows_dev=rows_dev))
         res.extend(tc_wgrad_grouped(probs))

@@ -261,7 +261,7 @@ def test_pair_backward_exact_given_stash(syn, model, torch_cuda):
         m = buf[lay.mask[l]:lay.mask[l] + rows * 32].view(np.uint32).reshape(rows, 8)
         masks.append(((m[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).reshape(rows, 256).astype(bool))
     X = [_decode_image(buf, lay.x[0], n_tiles, 2)] + [_decode_image(buf, lay.x[l], n_tiles, 4) for l in (1, 2, 3)]
-    X[0][:, 112:] = 0.0  # the first-layer input has 112 columns; the rest of its second K-block is never written nor read
+    X[0][:, ops.PAIR_IN_COLS:] = 0.0  # the first-layer input has 96 columns; the rest of its second K-block is never written nor read
     lf = [m for m in model.field.aggregator.local_field if hasattr(m, "weight")]
     W = [l.weight.detach().cpu().numpy().astype(np.float64) for l in lf[:4]]
     Bv = [l.bias.detach().cpu().numpy().astype(np.float64) for l in lf[:4]]
