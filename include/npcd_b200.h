@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define NPCD_B200_ABI_VERSION 2
+#define NPCD_B200_ABI_VERSION 3
 
 const char* npcd_last_error(void);
 int npcd_abi_version(void);
@@ -80,11 +80,13 @@ int npcd_knn_fill(const float* cam_centers, const float* dirs, const float* ray_
 /* ---- Q3: train-mode valid-ray subsampling, replaces Aggregator.subsample_valid_rays (fields/aggregators/aggregator.py:78-119) ------
  *   npcd_count_valid_rays: n_valid [n_views] = #rays of the view with ray_count > 0, min_valid [1] = their minimum (the host reads it:
  *     n = min(min_valid, ray_subsamples) sizes every output, aggregator.py:102-103).
- *   npcd_subsample_valid_rays: per view a uniform random n_keep-subset of its valid rays (counter-based generator on `seed`), written
- *     as global ray ids view * rays_per_view + ray in ascending order: ray_ids [n_views, n_keep] int32 (n_keep <= every n_valid).   */
+ *   npcd_subsample_valid_rays: per view a uniform random n_keep-subset of its valid rays (counter-based generator keyed by `seed`,
+ *     the GLOBAL view number view_offset + view and the draw, so an object-sharded batch picks the same rays as the whole batch
+ *     would), written as ray ids view * rays_per_view + ray in ascending order: ray_ids [n_views, n_keep] int32
+ *     (n_keep <= every n_valid).                                                                                                   */
 int npcd_count_valid_rays(const int* ray_count, long long n_views, int rays_per_view, int* n_valid, int* min_valid, void* stream);
 int npcd_subsample_valid_rays(const int* ray_count, long long n_views, int rays_per_view, int n_keep, unsigned long long seed,
-                              int* ray_ids, void* stream);
+                              long long view_offset, int* ray_ids, void* stream);
 
 /* ---- field: gather + posenc + pair MLP + aggregation + density/colour heads -------------------------------------------------
  * Replaces aggregators.MLP.get_local_feat / aggregate_local_feat (fields/aggregators/mlp.py:36-125), Aggregator.get_keypoint_data
@@ -149,6 +151,7 @@ typedef struct {
   const int* perm;
   float scale;
   void* out;
+  int format; /* 0: fp16 hi + fp16 lo tiles ("f16x3" scheme); 1: fp16 + e4m3 tiles ("f16+e4m3x2" scheme, see npcd_tc_pack_weights_f8) */
 } npcd_tc_pack_job;
 int npcd_tc_pack_weights_batched(const npcd_tc_pack_job* jobs, int n_jobs, void* stream);
 /* workspace (device bytes) for `capacity` kept samples (< 2^27 per launch): the pre-split [S,256] aggregate image that links the
@@ -158,7 +161,9 @@ int npcd_field_tc_fwd(const int* nbr_idx, const float* sample_pos, const float* 
                       const long long* n_samples_dev, long long capacity, const npcd_mlp_tc_weights* weights, void* workspace,
                       size_t workspace_bytes, float* rgbs, float* feat_out,
                       int stages /* bit0: dense packing + pair MLP + aggregation -> workspace, bit1: heads -> rgbs, bit2: heads with
-                                    local_field.8 folded into W->shape / W->chan[0] by the caller (W' = W W_8, b' = W b_8 + b; W->agg unused) */,
+                                    local_field.8 folded into W->shape / W->chan[0] by the caller (W' = W W_8, b' = W b_8 + b; W->agg unused),
+                                    bit3: `weights` were packed in format 1 -- run the "f16 + e4m3 x 2" operand scheme (one fp16
+                                    product + two e4m3 correction products per layer instead of three fp16 products) */,
                       int* error_flag /* device int, optional */, int num_sms, void* stream);
 /* fp32 rows [n,256] <-> the pre-split operand image the tensor-core kernels exchange: per 128-row tile 4 K-blocks x
  * (fp16 hi 16 KB, fp16 lo 16 KB) in the SWIZZLE_128B layout; ceil(n / 128) * 128 KB.                                           */
@@ -167,6 +172,16 @@ int npcd_tc_image_to_rows(const void* image, long long n, float* rows, void* str
 /* self-test: out[s,:] = x[s,:] @ W^T + b for one packed 256x256 layer; `image` = npcd_tc_rows_to_image(x) */
 int npcd_tc_linear_probe(const void* image, const long long* n_rows_dev, long long capacity, const npcd_tc_layer* layer, float* out,
                          int* error_flag, int num_sms, void* stream);
+/* The "f16 + e4m3 x 2" operand scheme (inference): an activation y travels as fp16(8 y) plus the two bytes e4m3((8 y - fp16(8 y)) 2^8)
+ * and e4m3(y / 2); a weight w (times the layer's power-of-two `scale`) as fp16(2^13 w), e4m3(2^5 w) and e4m3((2^13 w - fp16(2^13 w)) 2^4).
+ * A layer is then ONE kind::f16 product plus TWO kind::f8f6f4 products (twice the tensor rate) into the same fp32 accumulator:
+ * relative error ~2^-16 per product instead of 2^-22, measured well inside the 1e-4 bar on RGB (tests/test_gpu_precision.py).
+ * Same sizes and call shapes as the format-0 functions above.                                                                       */
+int npcd_tc_pack_weights_f8(const float* w, int k_in, const int* perm, int k_pad /* multiple of 32 */, float scale, void* out, void* stream);
+int npcd_tc_rows_to_image_f8(const float* rows, long long n, void* image, void* stream);
+int npcd_tc_image_to_rows_f8(const void* image, long long n, float* rows, void* stream);
+int npcd_tc_linear_probe_f8(const void* image, const long long* n_rows_dev, long long capacity, const npcd_tc_layer* layer, float* out,
+                            int* error_flag, int num_sms, void* stream);
 
 /* ---- generic fp32-accurate tensor-core GEMM (training path: forward / dgrad / wgrad of the nn.Linear layers, row B* of
  * SURVEY.md section 8; the reference runs them as fp32 cuBLAS GEMMs under autograd) ------------------------------------------

@@ -10,7 +10,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnpcd_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _lock = threading.Lock()
 _lib = None
@@ -68,7 +68,7 @@ class PackJob(C.Structure):
     """mirror of ``npcd_tc_pack_job``"""
 
     _fields_ = [("w", P), ("ld", C.c_longlong), ("n_rows", C.c_int), ("k_in", C.c_int), ("k_pad", C.c_int), ("transpose", C.c_int),
-                ("perm", P), ("scale", C.c_float), ("out", P)]
+                ("perm", P), ("scale", C.c_float), ("out", P), ("format", C.c_int)]
 
 
 class PairStashLayout(C.Structure):
@@ -99,11 +99,15 @@ SIGNATURES = {
     "npcd_scan_counts": [P, P, L, P, P, C.c_size_t, P],
     "npcd_knn_fill": [P, P, P, P, P, P, L, P, P, I, I, I, P, P, F, L, P, P, P, I, P],
     "npcd_count_valid_rays": [P, L, I, P, P, P],
-    "npcd_subsample_valid_rays": [P, L, I, I, C.c_ulonglong, P, P],
+    "npcd_subsample_valid_rays": [P, L, I, I, C.c_ulonglong, L, P, P],
     "npcd_knn_points": [P, P, L, I, I, P, P, F, P, P],
     "npcd_field_simt_fwd": [P, P, P, P, P, L, P, P, P, P, I, I, P],
     "npcd_tc_pack_weights": [P, I, P, I, F, P, P],
     "npcd_tc_pack_weights_batched": [P, I, P],
+    "npcd_tc_pack_weights_f8": [P, I, P, I, F, P, P],
+    "npcd_tc_rows_to_image_f8": [P, L, P, P],
+    "npcd_tc_image_to_rows_f8": [P, L, P, P],
+    "npcd_tc_linear_probe_f8": [P, P, L, P, P, P, I, P],
     "npcd_field_tc_workspace_bytes": [L, P],
     "npcd_field_tc_fwd": [P, P, P, P, P, L, P, P, C.c_size_t, P, P, I, P, I, P],
     "npcd_tc_rows_to_image": [P, L, P, P],
@@ -145,16 +149,20 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.isfile(LIB_PATH):
-            from . import build as _build
+        # build.build() is a no-op when the digest stamp of csrc/ + include/ matches the library on disk, so a stale .so is never
+        # used silently after a source edit; without nvcc (or sources) an existing library is taken as is
+        from . import build as _build
 
-            try:
+        try:
+            if os.path.isdir(_build.CSRC) and (_build.have_nvcc() or not os.path.isfile(LIB_PATH)):
                 _build.build()
-            except Exception as e:  # noqa: BLE001
+        except Exception as e:  # noqa: BLE001
+            if not os.path.isfile(LIB_PATH):
                 raise RuntimeError(
                     f"libnpcd_b200.so is missing and could not be built ({e}); there is no CPU fallback. "
                     "Run `python -c 'import __graft_entry__ as g; g.build()'`."
                 ) from e
+            raise RuntimeError(f"libnpcd_b200.so is older than its sources and the rebuild failed: {e}") from e
         try:
             lib = C.CDLL(LIB_PATH)
         except OSError as e:

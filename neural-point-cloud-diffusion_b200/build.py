@@ -29,6 +29,18 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+def have_nvcc() -> bool:
+    try:
+        n = _nvcc()
+    except RuntimeError:
+        return False
+    if n == "nvcc":
+        import shutil
+
+        return shutil.which("nvcc") is not None
+    return True
+
+
 def _digest(paths) -> str:
     h = hashlib.sha256()
     for p in sorted(paths):

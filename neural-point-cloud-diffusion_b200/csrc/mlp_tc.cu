@@ -107,6 +107,7 @@ struct Params {
 // One chunk (32 accumulator columns starting at c0) of an ACT / LINEAR epilogue: y = [lrelu](acc * inv + b) -> fp16 hi/lo ->
 // K-block (c0 >> 6) of the A operand, 16-byte chunks (c0 & 63) / 8 .. +3.
 // slope = 0.01 (LeakyReLU) or 1 (linear layer: max(y, y) = y).
+template <bool kF8 = false>
 __device__ __forceinline__ void epi_chunk_store(const Params& P, int l, float inv, float slope, const uint32_t (&v)[32], int c0,
                                                 uint8_t* sA, uint32_t rowbase, int x7, float* feat_row, uint32_t* mask_out = nullptr) {
   uint32_t mbits = 0u;
@@ -123,18 +124,31 @@ __device__ __forceinline__ void epi_chunk_store(const Params& P, int l, float in
     act2(v[g * 8 + 4], v[g * 8 + 5], inv2, b1.x, b1.y, slope2, y[4], y[5]);
     act2(v[g * 8 + 6], v[g * 8 + 7], inv2, b1.z, b1.w, slope2, y[6], y[7]);
     if (feat_row) {
-      *reinterpret_cast<float4*>(feat_row + c0 + g * 8) = make_float4(y[0], y[1], y[2], y[3]);
-      *reinterpret_cast<float4*>(feat_row + c0 + g * 8 + 4) = make_float4(y[4], y[5], y[6], y[7]);
+      const float fm = kF8 ? 1.0f / kF8ActScale : 1.0f;  // the f8 scheme carries activations times kF8ActScale
+      *reinterpret_cast<float4*>(feat_row + c0 + g * 8) = make_float4(y[0] * fm, y[1] * fm, y[2] * fm, y[3] * fm);
+      *reinterpret_cast<float4*>(feat_row + c0 + g * 8 + 4) = make_float4(y[4] * fm, y[5] * fm, y[6] * fm, y[7] * fm);
     }
     if (mask_out) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) mbits |= (y[j] > 0.f ? 1u : 0u) << (g * 8 + j);
     }
-    uint4 hi, lo;
-    split8(y, hi, lo);
     uint8_t* p = kb_base + (((c16_0 + g) ^ x7) << 4);
-    *reinterpret_cast<uint4*>(p) = hi;
-    *reinterpret_cast<uint4*>(p + kTileBytesA) = lo;
+    if (!kF8) {
+      uint4 hi, lo;
+      split8(y, hi, lo);
+      *reinterpret_cast<uint4*>(p) = hi;
+      *reinterpret_cast<uint4*>(p + kTileBytesA) = lo;
+    } else {
+      uint4 hi;
+      uint2 lo8, hi8;
+      split8_f8(y, hi, lo8, hi8);
+      *reinterpret_cast<uint4*>(p) = hi;
+      const int c8 = c16_0 + g;  // 8-column group within the K-block
+      uint8_t* q = kb_base + kTileBytesA + ((((c8 >> 1)) ^ x7) << 4) + (c8 & 1) * 8;
+      uint8_t* r = kb_base + kTileBytesA + ((((c8 >> 1) + 4) ^ x7) << 4) + (c8 & 1) * 8;
+      *reinterpret_cast<uint2*>(q) = lo8;
+      *reinterpret_cast<uint2*>(r) = hi8;
+    }
   }
   if (mask_out) *mask_out = mbits;
 }
@@ -147,9 +161,10 @@ __device__ __forceinline__ void epi_chunk_store(const Params& P, int l, float in
 constexpr bool kCluster = true;
 
 // ------------------------------------------------------------------------------------------------------------- kernel ----
-template <int kMode>
+template <int kMode, bool kF8 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_TRAIN ? kThreadsTcTrainHeads : kThreadsTc, 1)
     k_field_tc(const __grid_constant__ Params P) {
+  static_assert(!kF8 || kMode == MODE_PAIR || kMode == MODE_HEADS || kMode == MODE_PROBE, "the f8 operand scheme is inference-only");
   constexpr bool kPair = kMode == MODE_PAIR || kMode == MODE_PAIR_TRAIN;
   constexpr bool kTrainP = kMode == MODE_PAIR_TRAIN;
   constexpr bool kTrainH = kMode == MODE_HEADS_TRAIN;
@@ -242,6 +257,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
         }
         continue;
       }
+      const bool has_next = tile + (int)gridDim.x < n_tiles;
       for (int l = 0; l < n_layers; ++l, ++lc) {
         const uint32_t ab = lc & 1u;
         const uint32_t d_tmem = tmem_base + ab * 256u;
@@ -270,9 +286,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
               if (ks < ks_n) umma_f16(d_tmem, a_hi + 2 * ks, b + 2 * ks, kIdesc, (kb | ks) != 0);
+            if (!kF8) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              if (ks < ks_n) umma_f16(d_tmem, a_lo + 2 * ks, b + 2 * ks, kIdesc, 1u);
+              for (int ks = 0; ks < 4; ++ks)
+                if (ks < ks_n) umma_f16(d_tmem, a_lo + 2 * ks, b + 2 * ks, kIdesc, 1u);
+            }
             if (kCluster) umma_commit_mc(bar(kBarWEmpty + st), 0x3); else umma_commit(bar(kBarWEmpty + st));
           }
           __syncwarp();
@@ -282,11 +300,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
           tc_fence_after();
           if (elect_one()) {
             const uint64_t b = desc_w0 + (uint64_t)(st * (kTileBytesW >> 4));
+            if (!kF8) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              if (ks < ks_n) umma_f16(d_tmem, a_hi + 2 * ks, b + 2 * ks, kIdesc, 1u);
+              for (int ks = 0; ks < 4; ++ks)
+                if (ks < ks_n) umma_f16(d_tmem, a_hi + 2 * ks, b + 2 * ks, kIdesc, 1u);
+            } else {
+              // the 8-bit tile: row = [lo8 of the 64 columns | hi8 of the 64 columns] against [Whi8 | Wlo8]; a K = 32 step
+              // covers two fp16 K-steps, so a K-block with ks_n fp16 steps takes ks_n / 2 steps in each 64-byte half
+#pragma unroll
+              for (int k8 = 0; k8 < 2; ++k8)
+                if (2 * k8 < ks_n) umma_f8(d_tmem, a_lo + 2 * k8, b + 2 * k8, kIdesc, 1u);
+#pragma unroll
+              for (int k8 = 0; k8 < 2; ++k8)
+                if (2 * k8 < ks_n) umma_f8(d_tmem, a_lo + 4 + 2 * k8, b + 4 + 2 * k8, kIdesc, 1u);
+            }
             if (kCluster) umma_commit_mc(bar(kBarWEmpty + st), 0x3); else umma_commit(bar(kBarWEmpty + st));
-            if (l == n_layers - 1) umma_commit(bar(kBarAFree + kb));  // this K-block may take the next tile's first operand
+            // this K-block may take the next tile's first operand (arrive only where somebody waits: pair mode restages
+            // K-blocks 0..1, and the last tile of a CTA has no successor)
+            if (l == n_layers - 1 && has_next && (!kPair || kb < 2)) umma_commit(bar(kBarAFree + kb));
             if (kb == nkb - 1) umma_commit(bar(kBarAccRdy + ab));
           }
           __syncwarp();
@@ -357,7 +388,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
               bulk_commit();
               bulk_wait_read0();
               mbar_arrive(bar(kBarStash + kb));
-              if (j == 3) mbar_arrive(bar(kBarAFree + kb));  // C3 is out: the loader may take this K-block after the last MMAs
+              // C3 is out: the loader may take this K-block after the last MMAs (no successor tile: nobody waits)
+              if (j == 3 && tile + (int)gridDim.x < n_tiles) mbar_arrive(bar(kBarAFree + kb));
             }
             __syncwarp();
           }
@@ -429,7 +461,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
         uint32_t* mptr = nullptr;
         if (kTrainP) mptr = P.stash_mask[l] + ((size_t)tile_now * 128 + row) * 8 + (2 * i + half);
         if (kTrainH && l >= 2) mptr = P.hstash_mask[l - 1] + ((size_t)tile_now * 128 + row) * 8 + (2 * i + half);
-        epi_chunk_store(P, l, inv, slope, v[i & 1], (2 * i + half) * 32, sA, rowbase, x7, feat_row, mptr);
+        epi_chunk_store<kF8>(P, l, inv, slope, v[i & 1], (2 * i + half) * 32, sA, rowbase, x7, feat_row, mptr);
         if (i == 3) release_acc(ab);
         publish(kBarARdy + i);
         if (kTrain) sd_pending |= 1u << i;
@@ -444,7 +476,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
       //   [feat 0..31 | x: (sin, cos) of octaves 0..7 | d_x, (sin, cos)_x of octaves 8, 9 | y: d, (sin, cos) x 10 | z: d, (sin, cos) x 10 | 0]
       // (the column order is OURS; the first-layer weights are permuted to match when they are packed, ops.pair_input_perm).
       // half 0 owns columns 0..47 (K-block 0, chunks 0..5); half 1 owns 48..95 (K-block 0 chunks 6, 7; K-block 1 chunks 0..3).
-      uint4 pre_hi[6], pre_lo[6];
+      uint4 pre_hi[6], pre_lo[6];  // f8 scheme: pre_lo[c] = {lo8 (8 B), hi8 (8 B)} of the chunk
+
+      auto split_pre = [&](const float (&y)[8], int c) {
+        if (!kF8) {
+          split8(y, pre_hi[c], pre_lo[c]);
+        } else {
+          const float ys[8] = {y[0] * kF8ActScale, y[1] * kF8ActScale, y[2] * kF8ActScale, y[3] * kF8ActScale,
+                               y[4] * kF8ActScale, y[5] * kF8ActScale, y[6] * kF8ActScale, y[7] * kF8ActScale};
+          uint2 lo8, hi8;
+          split8_f8(ys, pre_hi[c], lo8, hi8);
+          pre_lo[c] = make_uint4(lo8.x, lo8.y, hi8.x, hi8.y);
+        }
+      };
+      // store chunk c (8 columns) of K-block kb of the staged layer-0 input
+      auto store_pre = [&](int kb, int c, int src) {
+        uint8_t* t = sA + kb * 2 * kTileBytesA + rowbase;
+        *reinterpret_cast<uint4*>(t + ((c ^ x7) << 4)) = pre_hi[src];
+        if (!kF8) {
+          *reinterpret_cast<uint4*>(t + kTileBytesA + ((c ^ x7) << 4)) = pre_lo[src];
+        } else {
+          *reinterpret_cast<uint2*>(t + kTileBytesA + (((c >> 1) ^ x7) << 4) + (c & 1) * 8) = make_uint2(pre_lo[src].x, pre_lo[src].y);
+          *reinterpret_cast<uint2*>(t + kTileBytesA + ((((c >> 1) + 4) ^ x7) << 4) + (c & 1) * 8) = make_uint2(pre_lo[src].z, pre_lo[src].w);
+        }
+      };
 
       auto prologue_compute = [&](int tile, int buf) {
         const int s_begin = __ldg(P.tile_start + tile), s_end = __ldg(P.tile_start + tile + 1);
@@ -506,7 +561,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
               const float4 f1 = __ldg(reinterpret_cast<const float4*>(P.kp_feat + (size_t)idx * 32 + ch * 8 + 4));
               y[0] = f0.x; y[1] = f0.y; y[2] = f0.z; y[3] = f0.w; y[4] = f1.x; y[5] = f1.y; y[6] = f1.z; y[7] = f1.w;
             }
-            split8(y, pre_hi[ch], pre_lo[ch]);
+            split_pre(y, ch);
           }
           float v[16];
           octaves(d3[0], kPi, 8, v);
@@ -517,7 +572,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
 #pragma unroll
           for (int ch = 0; ch < 2; ++ch) {
             const float y[8] = {v[ch * 8], v[ch * 8 + 1], v[ch * 8 + 2], v[ch * 8 + 3], v[ch * 8 + 4], v[ch * 8 + 5], v[ch * 8 + 6], v[ch * 8 + 7]};
-            split8(y, pre_hi[4 + ch], pre_lo[4 + ch]);
+            split_pre(y, 4 + ch);
           }
           const float nrm = sqrtf(d3[0] * d3[0] + d3[1] * d3[1] + d3[2] * d3[2]);
           wts_all[buf * 128 + row] = idx >= 0 ? 1.0f / (nrm + 1e-5f) : 0.f;
@@ -537,7 +592,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
 #pragma unroll
           for (int ch = 0; ch < 6; ++ch) {
             const float y[8] = {v[ch * 8], v[ch * 8 + 1], v[ch * 8 + 2], v[ch * 8 + 3], v[ch * 8 + 4], v[ch * 8 + 5], v[ch * 8 + 6], v[ch * 8 + 7]};
-            split8(y, pre_hi[ch], pre_lo[ch]);
+            split_pre(y, ch);
           }
         }
       };
@@ -547,26 +602,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
         if (kb == 0) {
           if (half == 0) {
 #pragma unroll
-            for (int c = 0; c < 6; ++c) {
-              uint8_t* p = sA + rowbase + ((c ^ x7) << 4);
-              *reinterpret_cast<uint4*>(p) = pre_hi[c];
-              *reinterpret_cast<uint4*>(p + kTileBytesA) = pre_lo[c];
-            }
+            for (int c = 0; c < 6; ++c) store_pre(0, c, c);
           } else {
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              uint8_t* p = sA + rowbase + (((6 + c) ^ x7) << 4);
-              *reinterpret_cast<uint4*>(p) = pre_hi[c];
-              *reinterpret_cast<uint4*>(p + kTileBytesA) = pre_lo[c];
-            }
+            for (int c = 0; c < 2; ++c) store_pre(0, 6 + c, c);
           }
         } else if (half == 1) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint8_t* p = sA + 2 * kTileBytesA + rowbase + ((c ^ x7) << 4);
-            *reinterpret_cast<uint4*>(p) = pre_hi[c + 2];
-            *reinterpret_cast<uint4*>(p + kTileBytesA) = pre_lo[c + 2];
-          }
+          for (int c = 0; c < 4; ++c) store_pre(1, c, c + 2);
         }
         publish(kBarARdy + kb);
         if (kTrain) sd_pending |= 1u << kb;
@@ -667,12 +710,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
               }
               const long long s = (long long)s_begin + sl;
               const int col = 128 * pass + 8 * c8;
-              uint4 hi, lo;
-              split8(acc, hi, lo);
-              uint8_t* p = P.img + (size_t)(s >> 7) * kImgTileBytes + (size_t)(col >> 6) * (2 * kTileBytesA) +
-                           swz((int)(s & 127), (col & 63) >> 3);
-              *reinterpret_cast<uint4*>(p) = hi;
-              *reinterpret_cast<uint4*>(p + kTileBytesA) = lo;
+              uint8_t* kbp = P.img + (size_t)(s >> 7) * kImgTileBytes + (size_t)(col >> 6) * (2 * kTileBytesA);
+              if (!kF8) {
+                uint4 hi, lo;
+                split8(acc, hi, lo);
+                uint8_t* p = kbp + swz((int)(s & 127), (col & 63) >> 3);
+                *reinterpret_cast<uint4*>(p) = hi;
+                *reinterpret_cast<uint4*>(p + kTileBytesA) = lo;
+              } else {  // acc already carries kF8ActScale (the layer-3 epilogue scale and bias include it)
+                uint4 hi;
+                uint2 lo8, hi8;
+                split8_f8(acc, hi, lo8, hi8);
+                *reinterpret_cast<uint4*>(kbp + swz((int)(s & 127), (col & 63) >> 3)) = hi;
+                *reinterpret_cast<uint2*>(kbp + kTileBytesA + swz8_lo((int)(s & 127), (col & 63) >> 3)) = lo8;
+                *reinterpret_cast<uint2*>(kbp + kTileBytesA + swz8_hi((int)(s & 127), (col & 63) >> 3)) = hi8;
+              }
             }
             epi_bar_sync();  // the staging area is rewritten by the next pass / the next tile's layer-0 epilogue
           }
@@ -810,20 +862,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
 
 // Pack an fp32 [256, k_in] nn.Linear weight into per-K-block pre-swizzled fp16 hi/lo tiles (the exact shared-memory image the
 // MMA descriptors expect), multiplied by `scale` (a power of two).  perm[k'] = source column of packed column k' (or -1 = 0).
+// format 0: fp16 hi tile + fp16 lo tile; format 1 (f16 + e4m3 x 2 scheme, tc_ptx.cuh): fp16 tile of v * 2^13 + one 8-bit tile whose
+// row n is [Whi8 = e4m3(v * 2^5) of the 64 columns | Wlo8 = e4m3((v * 2^13 - W16) * 2^4) of the 64 columns]
+__device__ __forceinline__ void pack_weight_element(uint8_t* tile, int n, int kk, float v, int format) {
+  const size_t off = (size_t)(n >> 3) * 1024 + (n & 7) * 128 + (((kk >> 3) ^ (n & 7)) << 4) + (kk & 7) * 2;
+  if (format == 0) {
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    *reinterpret_cast<__half*>(tile + off) = hi;
+    *reinterpret_cast<__half*>(tile + kTileBytesW + off) = lo;
+  } else {
+    const float vs = v * 8192.0f;
+    const __half hi = __float2half_rn(vs);
+    *reinterpret_cast<__half*>(tile + off) = hi;
+    const uint32_t w8 = cvt_e4m3x2_f32(v * 32.0f, (vs - __half2float(hi)) * 16.0f);  // byte 0 = Whi8, byte 1 = Wlo8
+    const int c8 = kk >> 3;
+    uint8_t* t8 = tile + kTileBytesW;
+    t8[(size_t)(n >> 3) * 1024 + (n & 7) * 128 + (((c8 >> 1) ^ (n & 7)) << 4) + (c8 & 1) * 8 + (kk & 7)] = (uint8_t)(w8 & 0xffu);
+    t8[(size_t)(n >> 3) * 1024 + (n & 7) * 128 + ((((c8 >> 1) + 4) ^ (n & 7)) << 4) + (c8 & 1) * 8 + (kk & 7)] = (uint8_t)(w8 >> 8);
+  }
+}
+
 __global__ void k_pack_weights(const float* __restrict__ w, int k_in, const int* __restrict__ perm, int k_pad, float scale,
-                               uint8_t* __restrict__ out) {
+                               uint8_t* __restrict__ out, int format) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (n, k') pairs
   if (idx >= 256 * k_pad) return;
   const int n = idx / k_pad, kp = idx % k_pad;
   const int src = perm ? perm[kp] : (kp < k_in ? kp : -1);
   const float v = src >= 0 ? w[(size_t)n * k_in + src] * scale : 0.f;
-  const __half hi = __float2half_rn(v);
-  const __half lo = __float2half_rn(v - __half2float(hi));
-  const int kb = kp >> 6, kk = kp & 63;
-  uint8_t* tile = out + (size_t)kb * 2 * kTileBytesW;
-  const size_t off = (size_t)(n >> 3) * 1024 + (n & 7) * 128 + (((kk >> 3) ^ (n & 7)) << 4) + (kk & 7) * 2;
-  *reinterpret_cast<__half*>(tile + off) = hi;
-  *reinterpret_cast<__half*>(tile + kTileBytesW + off) = lo;
+  pack_weight_element(out + (size_t)(kp >> 6) * 2 * kTileBytesW, n, kp & 63, v, format);
 }
 
 // Batched variant: every weight matrix of a training step (10 forward layers, 4 + 6 transposed dgrad operands) in ONE launch;
@@ -839,16 +906,11 @@ __global__ void __launch_bounds__(256) k_pack_weights_batched(const __grid_const
   const int src = job.perm ? job.perm[kp] : (kp < job.k_in ? kp : -1);
   float v = 0.f;
   if (src >= 0 && n < job.n_rows) v = (job.transpose ? job.w[(size_t)src * job.ld + n] : job.w[(size_t)n * job.ld + src]) * job.scale;
-  const __half hi = __float2half_rn(v);
-  const __half lo = __float2half_rn(v - __half2float(hi));
-  const int kb = kp >> 6, kk = kp & 63;
-  uint8_t* tile = (uint8_t*)job.out + (size_t)kb * 2 * kTileBytesW;
-  const size_t off = (size_t)(n >> 3) * 1024 + (n & 7) * 128 + (((kk >> 3) ^ (n & 7)) << 4) + (kk & 7) * 2;
-  *reinterpret_cast<__half*>(tile + off) = hi;
-  *reinterpret_cast<__half*>(tile + kTileBytesW + off) = lo;
+  pack_weight_element((uint8_t*)job.out + (size_t)(kp >> 6) * 2 * kTileBytesW, n, kp & 63, v, job.format);
 }
 
 // fp32 rows [n,256] <-> the pre-split operand image (per 128-row tile: 4 K-blocks x (hi 16 KB, lo 16 KB), SWIZZLE_128B)
+template <bool kF8>
 __global__ void k_rows_to_image(const float* __restrict__ x, long long n, uint8_t* __restrict__ img) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (row, 8-column chunk)
   if (i >= n * 32) return;
@@ -856,29 +918,61 @@ __global__ void k_rows_to_image(const float* __restrict__ x, long long n, uint8_
   const int c8 = (int)(i & 31);
   const float4 a = __ldg(reinterpret_cast<const float4*>(x + s * kHidden + c8 * 8));
   const float4 b = __ldg(reinterpret_cast<const float4*>(x + s * kHidden + c8 * 8 + 4));
-  const float y[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  uint4 hi, lo;
-  split8(y, hi, lo);
-  uint8_t* p = img + (size_t)(s >> 7) * kImgTileBytes + (size_t)(c8 >> 3) * (2 * kTileBytesA) + swz((int)(s & 127), c8 & 7);
-  *reinterpret_cast<uint4*>(p) = hi;
-  *reinterpret_cast<uint4*>(p + kTileBytesA) = lo;
+  uint8_t* kbp = img + (size_t)(s >> 7) * kImgTileBytes + (size_t)(c8 >> 3) * (2 * kTileBytesA);
+  if (!kF8) {
+    const float y[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint4 hi, lo;
+    split8(y, hi, lo);
+    uint8_t* p = kbp + swz((int)(s & 127), c8 & 7);
+    *reinterpret_cast<uint4*>(p) = hi;
+    *reinterpret_cast<uint4*>(p + kTileBytesA) = lo;
+  } else {
+    const float k = kF8ActScale;
+    const float y[8] = {a.x * k, a.y * k, a.z * k, a.w * k, b.x * k, b.y * k, b.z * k, b.w * k};
+    uint4 hi;
+    uint2 lo8, hi8;
+    split8_f8(y, hi, lo8, hi8);
+    *reinterpret_cast<uint4*>(kbp + swz((int)(s & 127), c8 & 7)) = hi;
+    *reinterpret_cast<uint2*>(kbp + kTileBytesA + swz8_lo((int)(s & 127), c8 & 7)) = lo8;
+    *reinterpret_cast<uint2*>(kbp + kTileBytesA + swz8_hi((int)(s & 127), c8 & 7)) = hi8;
+  }
 }
 
+// (f8 scheme: the value the tensor cores see through the fp16 and lo8 parts, (A16 + lo8 / 2^8) / 2^3)
+template <bool kF8>
 __global__ void k_image_to_rows(const uint8_t* __restrict__ img, long long n, float* __restrict__ x) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * 32) return;
   const long long s = i >> 5;
   const int c8 = (int)(i & 31);
-  const uint8_t* p = img + (size_t)(s >> 7) * kImgTileBytes + (size_t)(c8 >> 3) * (2 * kTileBytesA) + swz((int)(s & 127), c8 & 7);
-  const uint4 hi = *reinterpret_cast<const uint4*>(p), lo = *reinterpret_cast<const uint4*>(p + kTileBytesA);
-  const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
+  const uint8_t* kbp = img + (size_t)(s >> 7) * kImgTileBytes + (size_t)(c8 >> 3) * (2 * kTileBytesA);
+  const uint8_t* p = kbp + swz((int)(s & 127), c8 & 7);
+  const uint4 hi = *reinterpret_cast<const uint4*>(p);
+  const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w};
   float y[8];
+  if (!kF8) {
+    const uint4 lo = *reinterpret_cast<const uint4*>(p + kTileBytesA);
+    const uint32_t l[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
-    const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&l[j]));
-    y[2 * j] = fh.x + fl.x;
-    y[2 * j + 1] = fh.y + fl.y;
+    for (int j = 0; j < 4; ++j) {
+      const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
+      const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&l[j]));
+      y[2 * j] = fh.x + fl.x;
+      y[2 * j + 1] = fh.y + fl.y;
+    }
+  } else {
+    const uint2 lo8 = *reinterpret_cast<const uint2*>(kbp + kTileBytesA + swz8_lo((int)(s & 127), c8 & 7));
+    const uint32_t l[2] = {lo8.x, lo8.y};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
+      const uint16_t two = (uint16_t)(l[j >> 1] >> (16 * (j & 1)));
+      uint32_t h2;
+      asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h2) : "h"(two));
+      const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&h2));
+      y[2 * j] = (fh.x + fl.x * (1.0f / 256.0f)) * (1.0f / kF8ActScale);
+      y[2 * j + 1] = (fh.y + fl.y * (1.0f / 256.0f)) * (1.0f / kF8ActScale);
+    }
   }
   *reinterpret_cast<float4*>(x + s * kHidden + c8 * 8) = make_float4(y[0], y[1], y[2], y[3]);
   *reinterpret_cast<float4*>(x + s * kHidden + c8 * 8 + 4) = make_float4(y[4], y[5], y[6], y[7]);
@@ -980,8 +1074,16 @@ extern "C" int npcd_tc_pack_weights(const float* w, int k_in, const int* perm, i
   NPCD_CHECK_ARG(w && out, "null pointer");
   NPCD_CHECK_ARG(k_in > 0 && k_pad > 0 && k_pad % 16 == 0 && k_pad <= 256 && (perm || k_in <= k_pad), "bad sizes");
   const int n = 256 * k_pad;
-  tc::k_pack_weights<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, k_in, perm, k_pad, scale, (uint8_t*)out);
+  tc::k_pack_weights<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, k_in, perm, k_pad, scale, (uint8_t*)out, 0);
   return check_launch("npcd_tc_pack_weights");
+}
+
+extern "C" int npcd_tc_pack_weights_f8(const float* w, int k_in, const int* perm, int k_pad, float scale, void* out, void* stream) {
+  NPCD_CHECK_ARG(w && out, "null pointer");
+  NPCD_CHECK_ARG(k_in > 0 && k_pad > 0 && k_pad % 32 == 0 && k_pad <= 256 && (perm || k_in <= k_pad), "bad sizes");
+  const int n = 256 * k_pad;
+  tc::k_pack_weights<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, k_in, perm, k_pad, scale, (uint8_t*)out, 1);
+  return check_launch("npcd_tc_pack_weights_f8");
 }
 
 extern "C" int npcd_tc_pack_weights_batched(const npcd_tc_pack_job* jobs, int n_jobs, void* stream) {
@@ -994,6 +1096,7 @@ extern "C" int npcd_tc_pack_weights_batched(const npcd_tc_pack_job* jobs, int n_
     NPCD_CHECK_ARG(j.w && j.out, "null pointer");
     NPCD_CHECK_ARG(j.k_in > 0 && j.k_pad > 0 && j.k_pad % 16 == 0 && j.k_pad <= 256 && (j.perm || j.k_in <= j.k_pad), "bad sizes");
     NPCD_CHECK_ARG(j.n_rows > 0 && j.n_rows <= 256 && j.ld > 0 && !(j.perm && j.transpose), "bad job");
+    NPCD_CHECK_ARG(j.format == 0 || (j.format == 1 && j.k_pad % 32 == 0), "bad format");
     J.j[i] = j;
   }
   tc::k_pack_weights_batched<<<dim3(256, n_jobs), 256, 0, (cudaStream_t)stream>>>(J);
@@ -1003,15 +1106,29 @@ extern "C" int npcd_tc_pack_weights_batched(const npcd_tc_pack_job* jobs, int n_
 extern "C" int npcd_tc_rows_to_image(const float* rows, long long n, void* image, void* stream) {
   NPCD_CHECK_ARG(n >= 0 && (n == 0 || (rows && image)), "bad arguments");
   if (n == 0) return 0;
-  tc::k_rows_to_image<<<(unsigned)((n * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rows, n, (uint8_t*)image);
+  tc::k_rows_to_image<false><<<(unsigned)((n * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rows, n, (uint8_t*)image);
   return check_launch("npcd_tc_rows_to_image");
+}
+
+extern "C" int npcd_tc_rows_to_image_f8(const float* rows, long long n, void* image, void* stream) {
+  NPCD_CHECK_ARG(n >= 0 && (n == 0 || (rows && image)), "bad arguments");
+  if (n == 0) return 0;
+  tc::k_rows_to_image<true><<<(unsigned)((n * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rows, n, (uint8_t*)image);
+  return check_launch("npcd_tc_rows_to_image_f8");
 }
 
 extern "C" int npcd_tc_image_to_rows(const void* image, long long n, float* rows, void* stream) {
   NPCD_CHECK_ARG(n >= 0 && (n == 0 || (rows && image)), "bad arguments");
   if (n == 0) return 0;
-  tc::k_image_to_rows<<<(unsigned)((n * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)image, n, rows);
+  tc::k_image_to_rows<false><<<(unsigned)((n * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)image, n, rows);
   return check_launch("npcd_tc_image_to_rows");
+}
+
+extern "C" int npcd_tc_image_to_rows_f8(const void* image, long long n, float* rows, void* stream) {
+  NPCD_CHECK_ARG(n >= 0 && (n == 0 || (rows && image)), "bad arguments");
+  if (n == 0) return 0;
+  tc::k_image_to_rows<true><<<(unsigned)((n * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)image, n, rows);
+  return check_launch("npcd_tc_image_to_rows_f8");
 }
 
 // workspace layout: [operand image | pair_off (capacity+1) | tile_start (max_tiles+2) | n_tiles (1, padded) | cub scratch]
@@ -1047,17 +1164,24 @@ int tc_workspace_layout(long long capacity, TcWorkspace* w) {
   return 0;
 }
 
-void fill_layer(tc::Params& P, int i, const npcd_tc_layer& src, int epi) {
+// f8 scheme (tc_ptx.cuh): the accumulator holds 2^16 x the pre-scaled product, and a layer whose output becomes the next operand
+// (ACT / LINEAR / AGG epilogues) produces it times kF8ActScale -- both folded into the epilogue's scale and bias here.
+void fill_layer(tc::Params& P, int i, const npcd_tc_layer& src, int epi, bool f8 = false) {
   P.layers[i].w = (const uint8_t*)src.packed_w;
   P.layers[i].inv_scale = src.inv_scale;
   P.layers[i].ksteps = src.k_pad / 16;
   P.layers[i].epi = epi;
   memcpy(P.bias[i], src.bias, sizeof(float) * 256);
+  if (f8) {
+    const float out_mult = (epi == tc::EPI_ACT || epi == tc::EPI_LINEAR || epi == tc::EPI_AGG) ? tc::kF8ActScale : 1.0f;
+    P.layers[i].inv_scale = src.inv_scale * tc::kF8AccScaleInv * out_mult;
+    for (int c = 0; c < 256; ++c) P.bias[i][c] *= out_mult;
+  }
 }
 
-template <int kMode>
+template <int kMode, bool kF8 = false>
 int launch_tc(const tc::Params& P, long long tiles, int num_sms, cudaStream_t st, const char* what) {
-  cudaError_t e = cudaFuncSetAttribute(tc::k_field_tc<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal);
+  cudaError_t e = cudaFuncSetAttribute(tc::k_field_tc<kMode, kF8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal);
   if (e != cudaSuccess) {
     set_error("%s: cannot opt in to %d bytes of shared memory: %s", what, tc::kSmemTotal, cudaGetErrorString(e));
     return 2;
@@ -1065,14 +1189,14 @@ int launch_tc(const tc::Params& P, long long tiles, int num_sms, cudaStream_t st
   if (num_sms <= 0) num_sms = 148;
   unsigned grid = (unsigned)(tiles < num_sms ? (tiles > 0 ? tiles : 1) : num_sms);
   if (tc::kCluster) grid = (grid + 1u) & ~1u;  // whole 2-CTA clusters
-  tc::k_field_tc<kMode><<<grid, kMode == tc::MODE_HEADS_TRAIN ? tc::kThreadsTcTrainHeads : tc::kThreadsTc, tc::kSmemTotal, st>>>(P);
+  tc::k_field_tc<kMode, kF8><<<grid, kMode == tc::MODE_HEADS_TRAIN ? tc::kThreadsTcTrainHeads : tc::kThreadsTc, tc::kSmemTotal, st>>>(P);
   return check_launch(what);
 }
 }  // namespace
 
 namespace {
 // dense packing (pair_off = exclusive scan of the neighbour counts, greedy tile starts) + the pair kernel
-template <int kMode>
+template <int kMode, bool kF8 = false>
 int pair_stage(const int* nbr_idx, const float* sample_pos, const float* kp_pos, const float* kp_feat, const long long* n_samples_dev,
                long long capacity, const npcd_mlp_tc_weights* W, const TcWorkspace& ws, uint8_t* base,
                const npcd_pair_stash_layout* layout, uint8_t* stash, int* error_flag, int num_sms, cudaStream_t st) {
@@ -1100,7 +1224,7 @@ int pair_stage(const int* nbr_idx, const float* sample_pos, const float* kp_pos,
   if (rc) return rc;
   static thread_local tc::Params P;  // ~11 KB: keep it off the stack
   memset(&P, 0, sizeof(P));
-  for (int i = 0; i < 4; ++i) fill_layer(P, i, W->pair[i], i < 3 ? tc::EPI_ACT : tc::EPI_AGG);
+  for (int i = 0; i < 4; ++i) fill_layer(P, i, W->pair[i], i < 3 ? tc::EPI_ACT : tc::EPI_AGG, kF8);
   P.n_layers = 4;
   P.nbr_idx = nbr_idx; P.sample_pos = (const float4*)sample_pos; P.kp_pos = kp_pos; P.kp_feat = kp_feat;
   P.pair_off = pair_off; P.tile_start = tile_start; P.n_tiles_dev = n_tiles_dev; P.img = img;
@@ -1114,22 +1238,22 @@ int pair_stage(const int* nbr_idx, const float* sample_pos, const float* kp_pos,
     P.stash_idx = (int*)(stash + layout->idx);
     P.stash_samp = (int*)(stash + layout->samp);
   }
-  return launch_tc<kMode>(P, ws.max_tiles, num_sms, st, "npcd_field_tc_fwd(pair)");
+  return launch_tc<kMode, kF8>(P, ws.max_tiles, num_sms, st, "npcd_field_tc_fwd(pair)");
 }
 }  // namespace
 
 namespace {
-template <int kMode>
+template <int kMode, bool kF8 = false>
 int heads_stage(const npcd_mlp_tc_weights* W, uint8_t* img, float* rgbs, float* feat_out, const long long* n_samples_dev,
                 long long capacity, const npcd_pair_stash_layout* layout, uint8_t* stash, int* error_flag, int num_sms, cudaStream_t st,
                 bool folded = false) {
   static thread_local tc::Params P;
   memset(&P, 0, sizeof(P));
   const int o = folded ? 1 : 0;  // folded: W->shape / W->chan[0] already contain local_field.8 (W' = W W_8, b' = W b_8 + b)
-  if (!folded) fill_layer(P, 0, W->agg, tc::EPI_LINEAR);
-  fill_layer(P, 1 - o, W->shape, tc::EPI_DOT1);
-  for (int i = 0; i < 3; ++i) fill_layer(P, 2 + i - o, W->chan[i], tc::EPI_ACT);
-  fill_layer(P, 5 - o, W->chan[3], tc::EPI_DOT3);
+  if (!folded) fill_layer(P, 0, W->agg, tc::EPI_LINEAR, kF8);
+  fill_layer(P, 1 - o, W->shape, tc::EPI_DOT1, kF8);
+  for (int i = 0; i < 3; ++i) fill_layer(P, 2 + i - o, W->chan[i], tc::EPI_ACT, kF8);
+  fill_layer(P, 5 - o, W->chan[3], tc::EPI_DOT3, kF8);
   P.n_layers = 6 - o;
   P.layer_ofs = o;
   P.img = img; P.rgbs = (float4*)rgbs; P.feat_out = feat_out;
@@ -1142,7 +1266,7 @@ int heads_stage(const npcd_mlp_tc_weights* W, uint8_t* img, float* rgbs, float* 
     for (int i = 0; i < 6; ++i) P.hstash_x[i] = stash + layout->hx[i];
     for (int i = 0; i < 5; ++i) P.hstash_mask[i] = (uint32_t*)(stash + layout->hmask[i]);
   }
-  return launch_tc<kMode>(P, (capacity + 127) / 128, num_sms, st, "npcd_field_tc_fwd(heads)");
+  return launch_tc<kMode, kF8>(P, (capacity + 127) / 128, num_sms, st, "npcd_field_tc_fwd(heads)");
 }
 }  // namespace
 
@@ -1174,15 +1298,20 @@ extern "C" int npcd_field_tc_fwd(const int* nbr_idx, const float* sample_pos, co
   int* pair_off = (int*)(base + ws.pair_off);
   int* tile_start = (int*)(base + ws.tile_off);
   int* n_tiles_dev = (int*)(base + ws.ntiles_off);
+  const bool f8 = (stages & 8) != 0;  // W was packed with format 1 (f16 + e4m3 x 2 operand scheme)
   if (stages & 1) {
-    rc = pair_stage<tc::MODE_PAIR>(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, W, ws, base, nullptr, nullptr,
-                                   error_flag, num_sms, st);
+    rc = f8 ? pair_stage<tc::MODE_PAIR, true>(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, W, ws, base, nullptr, nullptr,
+                                              error_flag, num_sms, st)
+            : pair_stage<tc::MODE_PAIR>(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, W, ws, base, nullptr, nullptr,
+                                        error_flag, num_sms, st);
     if (rc) return rc;
   }
   NPCD_CHECK_ARG(!(stages & 4) || !feat_out, "the folded heads stage has no local_field.8 output to return");
   if (stages & 6)
-    rc = heads_stage<tc::MODE_HEADS>(W, img, rgbs, feat_out, n_samples_dev, capacity, nullptr, nullptr, error_flag, num_sms, st,
-                                     (stages & 4) != 0);
+    rc = f8 ? heads_stage<tc::MODE_HEADS, true>(W, img, rgbs, feat_out, n_samples_dev, capacity, nullptr, nullptr, error_flag, num_sms, st,
+                                                (stages & 4) != 0)
+            : heads_stage<tc::MODE_HEADS>(W, img, rgbs, feat_out, n_samples_dev, capacity, nullptr, nullptr, error_flag, num_sms, st,
+                                          (stages & 4) != 0);
   return rc;
 }
 
@@ -1200,6 +1329,21 @@ extern "C" int npcd_tc_linear_probe(const void* image, const long long* n_rows_d
   P.feat_out = out;
   P.n_samples_dev = n_rows_dev; P.capacity = capacity; P.error_flag = error_flag;
   return launch_tc<tc::MODE_PROBE>(P, (capacity + 127) / 128, num_sms, (cudaStream_t)stream, "npcd_tc_linear_probe");
+}
+
+// same for the f16 + e4m3 x 2 operand scheme: `image` = npcd_tc_rows_to_image_f8(x), layer packed by npcd_tc_pack_weights_f8
+extern "C" int npcd_tc_linear_probe_f8(const void* image, const long long* n_rows_dev, long long capacity, const npcd_tc_layer* layer,
+                                       float* out, int* error_flag, int num_sms, void* stream) {
+  NPCD_CHECK_ARG(image && n_rows_dev && layer && out, "null pointer");
+  NPCD_CHECK_ARG(capacity > 0, "bad capacity");
+  static thread_local tc::Params P;
+  memset(&P, 0, sizeof(P));
+  fill_layer(P, 0, *layer, tc::EPI_DUMP, true);
+  P.n_layers = 1;
+  P.img = (uint8_t*)const_cast<void*>(image);
+  P.feat_out = out;
+  P.n_samples_dev = n_rows_dev; P.capacity = capacity; P.error_flag = error_flag;
+  return launch_tc<tc::MODE_PROBE, true>(P, (capacity + 127) / 128, num_sms, (cudaStream_t)stream, "npcd_tc_linear_probe_f8");
 }
 
 // ---- training forward of the pair stage: same kernel, plus the stash the fused backward needs ------------------------------

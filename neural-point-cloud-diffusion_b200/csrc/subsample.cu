@@ -38,7 +38,7 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
 }
 
 __global__ void __launch_bounds__(128) k_subsample_valid(const int* __restrict__ ray_count, int R, int n_keep, unsigned long long seed,
-                                                         int* __restrict__ ray_ids) {
+                                                         unsigned long long view_offset, int* __restrict__ ray_ids) {
   extern __shared__ int list[];  // [R] valid ray ids of this view, in ray order
   __shared__ int warp_base[5];
   __shared__ int n_valid_s;
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(128) k_subsample_valid(const int* __restrict__
     n_valid_s = base;
     const int n = min(n_keep, base);
     for (int i = 0; i < n; ++i) {  // partial Fisher-Yates: list[0..n) becomes a uniform random n-subset
-      const uint64_t u = mix64(seed ^ mix64(((uint64_t)view << 32) | (uint32_t)i));
+      const uint64_t u = mix64(seed ^ mix64(((view_offset + (uint64_t)view) << 32) | (uint32_t)i));
       const int j = i + (int)(((u >> 32) * (uint64_t)(base - i)) >> 32);
       const int t = list[i];
       list[i] = list[j];
@@ -98,14 +98,15 @@ extern "C" int npcd_count_valid_rays(const int* ray_count, long long n_views, in
 }
 
 extern "C" int npcd_subsample_valid_rays(const int* ray_count, long long n_views, int rays_per_view, int n_keep,
-                                         unsigned long long seed, int* ray_ids, void* stream) {
-  NPCD_CHECK_ARG(n_views >= 0 && rays_per_view > 0 && n_keep >= 0, "bad sizes");
+                                         unsigned long long seed, long long view_offset, int* ray_ids, void* stream) {
+  NPCD_CHECK_ARG(n_views >= 0 && rays_per_view > 0 && n_keep >= 0 && view_offset >= 0, "bad sizes");
   NPCD_CHECK_ARG((long long)rays_per_view * n_views < (1ll << 31), "ray ids must fit int32");
   if (n_views == 0 || n_keep == 0) return 0;
   NPCD_CHECK_ARG(ray_count && ray_ids, "null pointer");
   const size_t smem = (size_t)rays_per_view * sizeof(int);
   NPCD_CHECK_ARG(smem <= 200 * 1024, "rays_per_view too large for the shared-memory list");
   cudaFuncSetAttribute(k_subsample_valid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_subsample_valid<<<(unsigned)n_views, 128, smem, (cudaStream_t)stream>>>(ray_count, rays_per_view, n_keep, seed, ray_ids);
+  k_subsample_valid<<<(unsigned)n_views, 128, smem, (cudaStream_t)stream>>>(ray_count, rays_per_view, n_keep, seed,
+                                                                               (unsigned long long)view_offset, ray_ids);
   return check_launch("npcd_subsample_valid_rays");
 }

@@ -101,6 +101,16 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// e4m3 x e4m3 -> fp32 (M128 N256 K32): twice the K per instruction of kind::f16 at the same issue cost.  The instruction
+// descriptor bits are the same as make_idesc's (format field 0 = E4M3 for this kind, F16 for kind::f16).
+__device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -219,6 +229,56 @@ __device__ __forceinline__ void split8(const float (&y)[8], uint4& hi, uint4& lo
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// ---- "f16 + e4m3 x 2" operand scheme --------------------------------------------------------------
+// A layer output y is stored as  A16 = fp16(y * 2^3)  plus two e4m3 bytes per element,  lo8 = e4m3((y * 2^3 - A16) * 2^8)  and
+// hi8 = e4m3(A16 * 2^-4) = e4m3(y / 2);  a weight w (pre-scaled by 2^n so that max|w| lies in [2, 4)) as  W16 = fp16(w * 2^13),
+// Wlo8 = e4m3((w * 2^13 - W16) * 2^4)  and  Whi8 = e4m3(w * 2^5).  Then
+//     A16 * W16  +  lo8 * Whi8  +  hi8 * Wlo8   =  2^16 * y * w * (1 + O(2^-15)),
+// one kind::f16 product and two kind::f8f6f4 products (the correction terms only need the 4 significant bits e4m3 has), all three
+// accumulating into the same fp32 TMEM accumulator.  Ranges: fp16 overflows at |y| >= 8190, lo8 / hi8 saturate (satfinite, the
+// correction degrades gracefully) at |y| > 448 / 896; absolute resolution of the corrections 2^-22 and below.
+constexpr float kF8ActScale = 8.0f;          // 2^3: activations are stored times this
+constexpr float kF8AccScaleInv = 1.0f / 65536.0f;  // accumulator = 2^16 * (y . w_prescaled)
+
+__device__ __forceinline__ uint32_t cvt_e4m3x2_f32(float lo, float hi) {  // byte 0 = lo, byte 1 = hi
+  uint16_t r;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t cvt_e4m3x2_f16x2(uint32_t h2) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(r) : "r"(h2));
+  return r;
+}
+// 8 values (already times kF8ActScale) -> fp16 image chunk (16 B), lo8 (8 B), hi8 (8 B)
+__device__ __forceinline__ void split8_f8(const float (&y)[8], uint4& hi, uint2& lo8, uint2& hi8) {
+  uint32_t h[4], l[4], g[4];
+  const __half2 sixteenth = __floats2half2_rn(0.0625f, 0.0625f);
+  const uint64_t k256 = pack2(256.0f, 256.0f);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __half2 hh = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
+    const float2 f = __half22float2(hh);
+    float r0, r1;
+    unpack2(mul2(sub2(pack2(y[2 * j], y[2 * j + 1]), pack2(f.x, f.y)), k256), r0, r1);
+    h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[j] = cvt_e4m3x2_f32(r0, r1);
+    const __half2 hs = __hmul2(hh, sixteenth);
+    g[j] = cvt_e4m3x2_f16x2(*reinterpret_cast<const uint32_t*>(&hs));
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo8 = make_uint2(l[0] | (l[1] << 16), l[2] | (l[3] << 16));
+  hi8 = make_uint2(g[0] | (g[1] << 16), g[2] | (g[3] << 16));
+}
+// byte offsets inside the 8-bit tile of a K-block (128 rows x 128 B, SWIZZLE_128B): lo8 of the 8 columns [8 c8, 8 c8 + 8) of `row`
+// (c8 = 0..7); the matching hi8 bytes sit 64 B further along the (unswizzled) row, i.e. at chunk (c8 >> 1) + 4
+__host__ __device__ __forceinline__ uint32_t swz8_lo(int row, int c8) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (((c8 >> 1) ^ (row & 7)) << 4) + (c8 & 1) * 8);
+}
+__host__ __device__ __forceinline__ uint32_t swz8_hi(int row, int c8) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((c8 >> 1) + 4) ^ (row & 7)) << 4) + (c8 & 1) * 8);
 }
 
 }  // namespace tc

@@ -38,9 +38,22 @@ class MLP(Module):
         self._packed_key = None
         # "tc": tcgen05 tensor-core kernels (mlp_tc.cu, default); "simt": fp32 CUDA-core kernels (mlp_simt.cu, any feat_dim)
         self.mlp_impl = "tc" if in_dim == 32 else "simt"
+        # operand scheme of the tensor-core INFERENCE kernels (training always runs "f16x3"); see PRECISIONS / DESIGN.md section 5
+        self.precision = ops.DEFAULT_PRECISION
 
-    def compute_dtype(self) -> str:
-        return {"simt": "f32", "tc": "f32 (fp16 2-way split, 3-product tcgen05 emulation, fp32 accumulate)"}[self.mlp_impl]
+    # fp16-equivalent tensor-core passes per algorithmic product of each scheme
+    PRECISIONS = {"f16x3": 3.0, "f16+e4m3x2": 2.0}
+
+    def mma_cost(self) -> float:
+        return self.PRECISIONS[self.precision]
+
+    def compute_dtype(self, training: bool = False) -> str:
+        if self.mlp_impl == "simt":
+            return "f32"
+        if training or self.precision == "f16x3":
+            return "f32 (fp16 2-way split, 3-product tcgen05 emulation, fp32 accumulate)"
+        return ("f32 (fp16 hi x hi product + two e4m3 correction products [lo x hi, hi x lo] on tcgen05, fp32 accumulate; "
+                "measured within the 1e-4 parity bar, DESIGN.md section 5)")
 
     # ---- weights packed for the kernels, re-packed whenever a parameter changes (optimizer step, load_state_dict) ----
     def packed_weights(self, for_training: bool = False):
@@ -57,8 +70,10 @@ class MLP(Module):
 
     def evaluate(self, nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, want_feat=False):
         """-> rgbs [capacity,4] = (r,g,b,sigma).  Fused CUDA path, no autograd."""
-        fn = ops.field_tc_fwd if self.mlp_impl == "tc" else ops.field_simt_fwd
-        return fn(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, self.packed_weights(), want_feat)
+        if self.mlp_impl == "tc":
+            return ops.field_tc_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, self.packed_weights(), want_feat,
+                                    precision=self.precision)
+        return ops.field_simt_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, self.packed_weights(), want_feat)
 
     def evaluate_autograd(self, nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev=None):
         """Differentiable w.r.t. kp_feat and the MLP parameters (`aggregators/mlp.py:69-88,119-121`, `field.py:126-141`).

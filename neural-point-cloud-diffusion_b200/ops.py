@@ -19,6 +19,9 @@ from ._lib import call, ptr
 K_NEIGHBORS = 8
 DEPTH_RES = 128
 HIDDEN = 256
+# operand scheme of the tensor-core inference kernels: "f16x3" (three fp16 products per layer) or "f16+e4m3x2" (fp16 hi x hi plus
+# two e4m3 correction products at twice the tensor rate); fields.MLP.precision overrides it per model
+DEFAULT_PRECISION = "f16x3"
 
 # number of kernels launched by this process through the C-ABI (bench.py reports it as gpu_launches)
 LAUNCHES = 0
@@ -225,18 +228,22 @@ def knn_fill(rays: Rays, grid: Grid, views_per_obj: int, radius: float, valid_bi
     return nbr, pos, sray
 
 
-def subsample_valid_rays(ray_count, n_views: int, rays_per_view: int, max_keep: int, seed: int):
+def subsample_valid_rays(ray_count, n_views: int, rays_per_view: int, max_keep: int, seed: int, group=None, view_offset: int = 0):
     """Q3 (`aggregator.py:78-119`): (ray_ids [n_views*n] int32 ascending per view, n) with n = min(min #valid rays, max_keep).
-    One host sync (n sizes the output)."""
+    One host sync (n sizes the output).  ``group``: object-sharded training -- the minimum runs over the views of ALL ranks
+    (`aggregator.py:102` takes it over the whole batch), one 1-int all-reduce."""
     dev = ray_count.device
     n_valid = torch.empty((n_views,), dtype=torch.int32, device=dev)
     min_valid = torch.empty((1,), dtype=torch.int32, device=dev)
     call("npcd_count_valid_rays", ptr(ray_count), n_views, rays_per_view, ptr(n_valid), ptr(min_valid), _stream())
     _count(2)
+    if group is not None:
+        torch.distributed.all_reduce(min_valid, op=torch.distributed.ReduceOp.MIN, group=group)
     n = min(int(min_valid.item()), int(max_keep)) if n_views > 0 else 0
     ray_ids = torch.empty((n_views * n,), dtype=torch.int32, device=dev)
     if n > 0:
-        call("npcd_subsample_valid_rays", ptr(ray_count), n_views, rays_per_view, n, int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(ray_ids), _stream())
+        call("npcd_subsample_valid_rays", ptr(ray_count), n_views, rays_per_view, n, int(seed) & 0xFFFFFFFFFFFFFFFF, int(view_offset),
+             ptr(ray_ids), _stream())
         _count(1)
     return ray_ids, n
 
@@ -353,16 +360,30 @@ class PackedTcWeights:
         self._hdgrad = None
         self._folded = None
         self.scales = [2.0 ** math.floor(math.log2(4.0 / float(m))) if m > 0 else 1.0 for m in maxabs]
+        self._bias = [self._host(HIDDEN) for _ in range(10)]
+        self._outs = (self._host(HIDDEN), self._host(1), self._host(3 * HIDDEN), self._host(3))
+        self._f8 = None
+        self._folded_f8 = None
+        jobs = self._fill(s, 0)
+        if for_training:
+            jobs += self._dgrad_jobs() + self._hdgrad_jobs()
+        self._run(jobs)
+        self.struct = s
+        self.error_flag = _error_flag(dev)
+
+    def _fill(self, s, fmt: int):
+        """Fills the layer table of ``s`` with freshly allocated packed-weight buffers in operand format ``fmt`` (0: fp16 hi/lo,
+        1: fp16 + e4m3) and returns the pack jobs that fill them."""
         jobs = []
 
         def layer(dst, i, k_pad, perm=None):
-            w = ws[i]
+            w = self.ws[i]
             assert w.shape[0] == HIDDEN
-            out = torch.empty(((k_pad + 63) // 64) * 2 * 32768, dtype=torch.uint8, device=dev)
+            out = torch.empty(((k_pad + 63) // 64) * 2 * 32768, dtype=torch.uint8, device=self.dev)
             if k_pad % 64:
                 out.zero_()  # the tail of the last K-block is never written by the pack kernel
-            jobs.append(self._job(w, w.shape[1], HIDDEN, w.shape[1], k_pad, False, perm, self.scales[i], out))
-            dst.packed_w, dst.bias, dst.inv_scale, dst.k_pad = out.data_ptr(), self._host(HIDDEN), 1.0 / self.scales[i], k_pad
+            jobs.append(self._job(w, w.shape[1], HIDDEN, w.shape[1], k_pad, False, perm, self.scales[i], out, fmt))
+            dst.packed_w, dst.bias, dst.inv_scale, dst.k_pad = out.data_ptr(), self._bias[i], 1.0 / self.scales[i], k_pad
 
         layer(s.pair[0], 0, PAIR_IN_COLS, self.perm0)
         for i in range(1, 4):
@@ -371,13 +392,22 @@ class PackedTcWeights:
         layer(s.shape, 5, 256)
         for i in range(4):
             layer(s.chan[i], 6 + i, 256)
-        s.shape_out_w, s.shape_out_b = self._host(HIDDEN), self._host(1)
-        s.chan_out_w, s.chan_out_b = self._host(3 * HIDDEN), self._host(3)
-        if for_training:
-            jobs += self._dgrad_jobs() + self._hdgrad_jobs()
-        self._run(jobs)
-        self.struct = s
-        self.error_flag = _error_flag(dev)
+        s.shape_out_w, s.shape_out_b, s.chan_out_w, s.chan_out_b = self._outs
+        return jobs
+
+    def struct_for(self, precision: str, folded: bool):
+        """The weight table the kernels take for an operand scheme: "f16x3" (packed at construction) or "f16+e4m3x2" (packed on
+        first use), optionally with `local_field.8` folded into the heads."""
+        if precision == "f16x3":
+            return self.folded_struct() if folded else self.struct
+        if precision != "f16+e4m3x2":
+            raise ValueError(f"unknown precision {precision!r}")
+        if self._f8 is None:
+            f = _lib.TcWeights()
+            f.feat_dim = self.struct.feat_dim
+            self._run(self._fill(f, 1))
+            self._f8 = f
+        return self.folded_struct(1) if folded else self._f8
 
     # ---- helpers --------------------------------------------------------------------------------------------------------
     def _host(self, n):
@@ -386,11 +416,11 @@ class PackedTcWeights:
         self.keep.append(a)
         return a.ctypes.data
 
-    def _job(self, w, ld, n_rows, k_in, k_pad, transpose, perm, scale, out):
+    def _job(self, w, ld, n_rows, k_in, k_pad, transpose, perm, scale, out, fmt: int = 0):
         self.keep += [w, out]
         j = _lib.PackJob()
         j.w, j.ld, j.n_rows, j.k_in, j.k_pad, j.transpose = w.data_ptr(), ld, n_rows, k_in, k_pad, int(transpose)
-        j.perm, j.scale, j.out = (perm.data_ptr() if perm is not None else None), float(scale), out.data_ptr()
+        j.perm, j.scale, j.out, j.format = (perm.data_ptr() if perm is not None else None), float(scale), out.data_ptr(), int(fmt)
         return j
 
     def _run(self, jobs):
@@ -437,30 +467,39 @@ class PackedTcWeights:
             self._run(self._hdgrad_jobs())
         return self._hdgrad
 
-    def folded_struct(self):
+    def folded_struct(self, fmt: int = 0):
         """Inference view of the same weights with `local_field.8` (linear, no activation, `fields/aggregators/mlp.py:84`) folded into
         the two layers that consume its output: W' = W W_8, b' = W b_8 + b (float64 product, rounded once) -- one 256x256 GEMM less
         per shading sample (``stages`` bit 2 of `npcd_field_tc_fwd`).  Built on first use (never during training)."""
+        if fmt == 1:
+            if self._folded_f8 is None:
+                self._folded_f8 = self._build_folded(1)
+            return self._folded_f8
         if self._folded is None:
+            self._folded = self._build_folded(0)
+        return self._folded
+
+    def _build_folded(self, fmt: int):
+        base = self.struct if fmt == 0 else self.struct_for("f16+e4m3x2", False)
+        if True:
             lf4, sn0, cn0 = self.layers[4], self.layers[5], self.layers[6]
             w8, b8 = lf4.weight.detach().double(), lf4.bias.detach().double()
             folded = [((l.weight.detach().double() @ w8).float().contiguous(), (l.weight.detach().double() @ b8 + l.bias.detach().double()).float())
                       for l in (sn0, cn0)]
             small = torch.cat([torch.stack([w.abs().max() for w, _ in folded])] + [b.reshape(-1) for _, b in folded]).cpu().numpy()
             f = _lib.TcWeights()
-            C.memmove(C.byref(f), C.byref(self.struct), C.sizeof(_lib.TcWeights))
+            C.memmove(C.byref(f), C.byref(base), C.sizeof(_lib.TcWeights))
             jobs = []
             for k, (dst, (w, _)) in enumerate(((f.shape, folded[0]), (f.chan[0], folded[1]))):
                 m = float(small[k])
                 scale = 2.0 ** math.floor(math.log2(4.0 / m)) if m > 0 else 1.0
                 out = torch.empty(4 * 2 * 32768, dtype=torch.uint8, device=self.dev)
-                jobs.append(self._job(w, HIDDEN, HIDDEN, HIDDEN, HIDDEN, False, None, scale, out))
+                jobs.append(self._job(w, HIDDEN, HIDDEN, HIDDEN, HIDDEN, False, None, scale, out, fmt))
                 bias = np.ascontiguousarray(small[2 + k * HIDDEN:2 + (k + 1) * HIDDEN], dtype=np.float32)
                 self.keep.append(bias)
                 dst.packed_w, dst.bias, dst.inv_scale, dst.k_pad = out.data_ptr(), bias.ctypes.data, 1.0 / scale, HIDDEN
             self._run(jobs)
-            self._folded = f
-        return self._folded
+            return f
 
 
 _PERM_CACHE = {}
@@ -492,7 +531,7 @@ def tc_workspace_bytes(capacity: int) -> int:
 
 
 def field_tc_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity: int, weights: PackedTcWeights,
-                 want_feat: bool = False, want_agg: bool = False):
+                 want_feat: bool = False, want_agg: bool = False, precision: str = "f16x3"):
     """Tensor-core (tcgen05) field: rgbs [capacity,4] = (r,g,b,sigma); feat [capacity,256] if requested
     (with want_agg: the aggregated pair features [capacity,256] recovered from the operand image, for tests)."""
     dev = sample_pos.device
@@ -504,43 +543,45 @@ def field_tc_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity: 
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     kp_pos = kp_pos.detach().contiguous().float()
     kp_feat = kp_feat.detach().contiguous().float()
-    args = (ptr(nbr_idx), ptr(sample_pos), ptr(kp_pos), ptr(kp_feat), ptr(n_samples_dev), capacity, C.byref(weights.struct),
-            ptr(ws), nbytes, ptr(rgbs), ptr(feat))
-    _timed("pair_mlp", lambda: call("npcd_field_tc_fwd", *args, 1, ptr(weights.error_flag), sm_count(dev), _stream()))
+    f8 = 8 if precision == "f16+e4m3x2" else 0  # `stages` bit 3: operand scheme of the packed weights
+    args = (ptr(nbr_idx), ptr(sample_pos), ptr(kp_pos), ptr(kp_feat), ptr(n_samples_dev), capacity,
+            C.byref(weights.struct_for(precision, False)), ptr(ws), nbytes, ptr(rgbs), ptr(feat))
+    _timed("pair_mlp", lambda: call("npcd_field_tc_fwd", *args, 1 | f8, ptr(weights.error_flag), sm_count(dev), _stream()))
     if FOLD_HEADS and not want_feat:  # local_field.8 folded into shape_net.0 / channel_net.0: 5 GEMMs per sample instead of 6
-        fargs = args[:6] + (C.byref(weights.folded_struct()),) + args[7:]
-        _timed("heads", lambda: call("npcd_field_tc_fwd", *fargs, 4, ptr(weights.error_flag), sm_count(dev), _stream()))
+        fargs = args[:6] + (C.byref(weights.struct_for(precision, True)),) + args[7:]
+        _timed("heads", lambda: call("npcd_field_tc_fwd", *fargs, 4 | f8, ptr(weights.error_flag), sm_count(dev), _stream()))
     else:
-        _timed("heads", lambda: call("npcd_field_tc_fwd", *args, 2, ptr(weights.error_flag), sm_count(dev), _stream()))
+        _timed("heads", lambda: call("npcd_field_tc_fwd", *args, 2 | f8, ptr(weights.error_flag), sm_count(dev), _stream()))
     _count(8)  # pair-offset scan (3 launches) + greedy tile starts (walk, scan, walk) + pair kernel + heads kernel
     if want_agg:
         agg = torch.empty((capacity, HIDDEN), device=dev)
-        call("npcd_tc_image_to_rows", ptr(ws), capacity, ptr(agg), _stream())
+        call("npcd_tc_image_to_rows_f8" if f8 else "npcd_tc_image_to_rows", ptr(ws), capacity, ptr(agg), _stream())
         _count(1)
         return rgbs, feat, agg
     return rgbs, feat
 
 
-def tc_rows_to_image(x):
-    """fp32 rows [n,256] -> the pre-split fp16 hi/lo operand image (uint8 [ceil(n/128) * 131072])."""
+def tc_rows_to_image(x, precision: str = "f16x3"):
+    """fp32 rows [n,256] -> the pre-split operand image (uint8 [ceil(n/128) * 131072]) of an operand scheme."""
     _need_cuda(x)
     x = x.contiguous().float()
     n = x.shape[0]
     img = torch.zeros(((n + 127) // 128) * 131072, dtype=torch.uint8, device=x.device)
-    call("npcd_tc_rows_to_image", ptr(x), n, ptr(img), _stream())
+    call("npcd_tc_rows_to_image" + ("_f8" if precision == "f16+e4m3x2" else ""), ptr(x), n, ptr(img), _stream())
     _count(1 if n else 0)
     return img
 
 
-def tc_image_to_rows(img, n: int):
+def tc_image_to_rows(img, n: int, precision: str = "f16x3"):
     out = torch.empty((n, HIDDEN), device=img.device)
-    call("npcd_tc_image_to_rows", ptr(img), n, ptr(out), _stream())
+    call("npcd_tc_image_to_rows" + ("_f8" if precision == "f16+e4m3x2" else ""), ptr(img), n, ptr(out), _stream())
     _count(1 if n else 0)
     return out
 
 
-def tc_linear_probe(x, linear: torch.nn.Linear):
+def tc_linear_probe(x, linear: torch.nn.Linear, precision: str = "f16x3"):
     """out = x @ W^T + b through the tcgen05 engine (one packed 256x256 layer); self-test of descriptors / swizzle / TMEM."""
+    sfx = "_f8" if precision == "f16+e4m3x2" else ""
     _need_cuda(x)
     dev = x.device
     x = x.contiguous().float()
@@ -550,13 +591,13 @@ def tc_linear_probe(x, linear: torch.nn.Linear):
     maxabs = float(w.abs().max().item())
     scale = 2.0 ** math.floor(math.log2(4.0 / maxabs)) if maxabs > 0 else 1.0
     packed = torch.zeros(4 * 2 * 32768, dtype=torch.uint8, device=dev)
-    call("npcd_tc_pack_weights", ptr(w), 256, None, 256, float(scale), ptr(packed), _stream())
+    call("npcd_tc_pack_weights" + sfx, ptr(w), 256, None, 256, float(scale), ptr(packed), _stream())
     lay = _lib.TcLayer(packed.data_ptr(), b.ctypes.data, 1.0 / scale, 256)
-    img = tc_rows_to_image(x)
+    img = tc_rows_to_image(x, precision)
     out = torch.zeros((n, HIDDEN), device=dev)
     nrows = torch.tensor([n], dtype=torch.int64, device=dev)
     err = torch.zeros(1, dtype=torch.int32, device=dev)
-    call("npcd_tc_linear_probe", ptr(img), ptr(nrows), n, C.byref(lay), ptr(out), ptr(err), sm_count(dev), _stream())
+    call("npcd_tc_linear_probe" + sfx, ptr(img), ptr(nrows), n, C.byref(lay), ptr(out), ptr(err), sm_count(dev), _stream())
     _count(2)
     torch.cuda.synchronize()
     if int(err.item()) != 0:
@@ -1026,6 +1067,16 @@ def composite_fwd(sample_pos, rgbs, ray_offset, ray_end, ray_ids=None, white_bac
                                      int(white_back), ptr(mask), ptr(depth), ptr(rgb), ptr(range_scratch), int(init_range), _stream()))
     _count((1 if init_range else 0) + (1 if n else 0))
     return mask, depth, rgb, range_scratch
+
+
+def range_all_reduce(range_scratch, group):
+    """Object-sharded rendering: the depth clamp range (`renderer.py:154-156`) becomes the [min, max] over ALL ranks' slot depths.
+    ``range_scratch`` holds two order-preserving uint32 encodings of floats; flipping the sign bit makes int32 order match."""
+    flip = torch.tensor(-2 ** 31, dtype=torch.int32, device=range_scratch.device)
+    s = torch.bitwise_xor(range_scratch, flip)
+    torch.distributed.all_reduce(s[0:1], op=torch.distributed.ReduceOp.MIN, group=group)
+    torch.distributed.all_reduce(s[1:2], op=torch.distributed.ReduceOp.MAX, group=group)
+    range_scratch.copy_(torch.bitwise_xor(s, flip))
 
 
 def clamp_depth(depth, range_scratch, want_clamped: bool = False):

@@ -56,19 +56,44 @@ class LazyRowAdam:
              self.eps, ops._stream())
         ops._count(2)
 
+    def _merged_grads(self):
+        grads = self.table.row_grads
+        if not grads:
+            return None
+        if len(grads) > 1:  # the table was looked up several times in one step: one launch over the concatenation sums duplicates
+            grads = [(torch.cat([g[0] for g in grads]).contiguous(), torch.cat([g[1] for g in grads]).contiguous())]
+            self.table.row_grads = grads
+        return grads[0]
+
+    @torch.no_grad()
+    def grad_sq_norm(self):
+        """Squared L2 norm of this table's (row-sparse) gradient as a device scalar; duplicated objects are summed first, like the
+        dense ``weight.grad`` of `nn.Embedding` would hold them."""
+        g = self._merged_grads()
+        if g is None:
+            return None
+        idx, d_rows = g
+        uniq, inv = torch.unique(idx, return_inverse=True)
+        if uniq.numel() != idx.numel():
+            d_rows = torch.zeros((uniq.numel(), d_rows.shape[1]), device=d_rows.device).index_add_(0, inv, d_rows)
+        return (d_rows.double() ** 2).sum()
+
+    @torch.no_grad()
+    def scale_grad_(self, coef):
+        """Multiplies the pending row gradient by ``coef`` (python float or device scalar): gradient clipping, 1/world scaling."""
+        g = self._merged_grads()
+        if g is not None:
+            g[1].mul_(coef)
+
     @torch.no_grad()
     def step(self):
         """One optimiser step.  Like the dense optimiser the step counter advances on every call in which the table took part in
         the backward pass; rows without a gradient are caught up lazily."""
-        grads = self.table.row_grads
-        if not grads:
+        g = self._merged_grads()
+        if g is None:
             return
         self.step_count += 1
-        if len(grads) == 1:
-            idx, d_rows = grads[0]
-        else:  # the table was looked up several times in one step: one launch over the concatenation sums duplicates
-            idx = torch.cat([g[0] for g in grads]).contiguous()
-            d_rows = torch.cat([g[1] for g in grads]).contiguous()
+        idx, d_rows = g
         self._launch(idx, idx.numel(), d_rows)
 
     @torch.no_grad()
@@ -91,7 +116,7 @@ class LazyRowAdam:
 
     def load_state_dict(self, sd):
         """Accepts this class's own state or the per-parameter state of a dense `torch.optim.Adam` ({'step','exp_avg','exp_avg_sq'})."""
-        self.step_count = int(sd["step"])
+        self.step_count = int(float(sd["step"]))  # torch's Adam keeps `step` as a tensor
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
         self.row_step.fill_(self.step_count)  # a dense state is up to date on every row
@@ -130,11 +155,47 @@ class PointNeRFAdam(torch.optim.Adam):
 
     @torch.no_grad()
     def step(self, closure=None):
+        self.step_rows()
+        return self.step_mlp(closure)
+
+    @torch.no_grad()
+    def step_rows(self):
+        """The latent-table half of ``step`` (rows are rank-local under object sharding: a trainer launches the MLP-gradient
+        all-reduce asynchronously, calls this while it is in flight, then ``step_mlp``)."""
         lr = float(self.param_groups[0]["lr"])
         for r in self.rows:
             r.lr = lr
             r.step()
+
+    @torch.no_grad()
+    def step_mlp(self, closure=None):
+        """torch's Adam on the 24 MLP tensors."""
         return super().step(closure)
+
+    @torch.no_grad()
+    def clip_grad_norm_(self, max_norm: float, eps: float = 1e-6):
+        """`torch.nn.utils.clip_grad_norm_(model.pointnerf.parameters(), max_norm)` of the reference trainer
+        (`npcd/train/pointnerf_training.py:143-144`) INCLUDING the row-sparse latent-table gradient, which lives on
+        ``weight.row_grads`` (``weight.grad`` stays None, so the stock function would neither count nor scale it).  Returns the
+        total norm (device scalar); no host sync."""
+        grads = [p.grad for p in self.mlp_params if p.grad is not None]
+        sq = [(g.double() ** 2).sum() for g in grads] + [n for n in (r.grad_sq_norm() for r in self.rows) if n is not None]
+        if not sq:
+            return torch.zeros(())
+        total = torch.stack(sq).sum().sqrt().float()
+        coef = torch.clamp(max_norm / (total + eps), max=1.0)
+        if grads:
+            torch._foreach_mul_(grads, coef)
+        for r in self.rows:
+            r.scale_grad_(coef)
+        return total
+
+    @torch.no_grad()
+    def scale_row_grads_(self, coef):
+        """Object-sharded training: the row gradients of a rank come from the mean over ITS objects; times 1 / world they are the
+        gradients of the global-batch mean loss (`parallel` module docstring)."""
+        for r in self.rows:
+            r.scale_grad_(coef)
 
     def flush(self):
         for r in self.rows:
@@ -146,7 +207,28 @@ class PointNeRFAdam(torch.optim.Adam):
         return sd
 
     def load_state_dict(self, sd):
-        rows = sd.get("rows", [])
-        super().load_state_dict({k: v for k, v in sd.items() if k != "rows"})
-        for r, s in zip(self.rows, rows):
-            r.load_state_dict(s)
+        """Accepts its own ``state_dict()`` or the checkpoint of the reference trainer's dense ``torch.optim.Adam(
+        model.pointnerf.parameters())`` (`npcd/utils/checkpoint_utils.py`): there the single param group lists the trainable
+        parameters in ``model.parameters()`` order -- the latent table(s) first (`pointnerf.py:23`), then the 24 MLP tensors -- and
+        the table's dense state goes to the lazy row optimiser."""
+        if "rows" in sd:
+            super().load_state_dict({k: v for k, v in sd.items() if k != "rows"})
+            for r, s in zip(self.rows, sd["rows"]):
+                r.load_state_dict(s)
+            return
+        n_mlp = len(self.mlp_params)
+        groups = sd["param_groups"]
+        ids = [i for g in groups for i in g["params"]]
+        if len(ids) < n_mlp:
+            raise ValueError(f"dense optimizer state with {len(ids)} parameters cannot hold the {n_mlp} MLP tensors")
+        state = sd["state"]
+        # everything before the 24 MLP tensors is an embedding table (feats, then the frozen coords, which has no state)
+        table_ids, mlp_ids = ids[:len(ids) - n_mlp], ids[len(ids) - n_mlp:]
+        for r in self.rows:
+            hit = [i for i in table_ids if i in state and tuple(state[i]["exp_avg"].shape) == tuple(r.table.shape)]
+            if len(hit) != 1:
+                raise ValueError("dense optimizer state: no (unique) entry with the shape of the latent table")
+            r.load_state_dict(state[hit[0]])
+        g0 = dict(groups[0])
+        g0["params"] = list(range(n_mlp))
+        super().load_state_dict({"state": {k: state[i] for k, i in enumerate(mlp_ids) if i in state}, "param_groups": [g0]})

@@ -7,6 +7,16 @@ independent units, so:
   NVLink on the GPU box, gloo in the CPU tests), followed by a division by the world size so the result equals the
   single-process gradient of the mean loss over the global batch when every rank holds the same number of rays.
 
+Global-batch equivalence of the sharded step (``enable_global_batch`` + ``sharded_step``; hardware test
+`tests/test_gpu_configs.py::test_two_gpu_sharded_step_equals_single_process`): with W ranks of B/W objects each,
+  * the batch-coupled scalars of the reference are reduced over all ranks inside the renderer -- the valid-ray minimum
+    (`fields/aggregators/aggregator.py:102`, 1-int MIN), the depth clamp range (`renderers/renderer.py:154-156`, MIN + MAX) and the
+    shared pixel subset (`renderers/renderer.py:232-238`, broadcast from rank 0); every rank then holds the same number of rays;
+  * MLP gradients: sum over ranks / W (the bucket) = gradient of the global-batch mean loss;
+  * latent-row gradients come from the mean over the rank's OWN objects and are therefore W times the global-batch ones:
+    ``sharded_step`` scales them by 1 / W before the row optimiser runs.
+The invalid-ray fill (`renderers/renderer.py:40-43`) stays per rank: cameras outside the cube looking at it never produce one.
+
 One process per GPU (``torchrun``); everything here is backend-agnostic ``torch.distributed``.
 """
 from __future__ import annotations
@@ -119,3 +129,29 @@ def all_reduce_min_int(value: int, device, group: Optional[dist.ProcessGroup] = 
     t = torch.tensor([value], dtype=torch.int64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
     return int(t.item())
+
+
+def enable_global_batch(pointnerf: torch.nn.Module, group: Optional[dist.ProcessGroup] = None) -> None:
+    """Makes the renderer of ``pointnerf`` reduce its batch-coupled scalars over ``group`` (default: the world), so that an
+    object-sharded step reproduces the single-process step on the global batch (module docstring)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("enable_global_batch needs an initialised process group")
+    group = group if group is not None else dist.group.WORLD
+    pointnerf.renderer.process_group = group
+    # one base seed for the counter-based draws (pixel subset, valid-ray subset) of all ranks: rank 0's, broadcast once
+    dev = next(pointnerf.parameters()).device
+    base = torch.empty(1, dtype=torch.int64, device=dev if dist.get_backend(group) == "nccl" else "cpu").random_(0, 2 ** 62)
+    dist.broadcast(base, dist.get_global_rank(group, 0), group=group)
+    pointnerf.renderer._shared_seed = (int(base.item()), 0)
+
+
+def sharded_step(optimizer, bucket: "GradBucket", group: Optional[dist.ProcessGroup] = None) -> None:
+    """After ``loss.backward()`` on every rank: launch the MLP-gradient all-reduce asynchronously, run the (rank-local) latent-row
+    Adam while it is in flight, then the MLP Adam.  ``optimizer``: `optim.PointNeRFAdam`."""
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    work = bucket.all_reduce_mean(group, async_op=True)
+    if world > 1:
+        optimizer.scale_row_grads_(1.0 / world)
+    optimizer.step_rows()
+    bucket.finish(work, group)
+    optimizer.step_mlp()

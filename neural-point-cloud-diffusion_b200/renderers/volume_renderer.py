@@ -25,8 +25,10 @@ class _CompositeFn(torch.autograd.Function):
     """Compositing over compact per-ray sample lists; backward = ``npcd_composite_bwd``."""
 
     @staticmethod
-    def forward(ctx, rgbs, sample_pos, ray_offset, ray_end, ray_ids, white_back):
+    def forward(ctx, rgbs, sample_pos, ray_offset, ray_end, ray_ids, white_back, group=None):
         mask, depth, rgb, rng = ops.composite_fwd(sample_pos, rgbs, ray_offset, ray_end, ray_ids, white_back)
+        if group is not None:
+            ops.range_all_reduce(rng, group)
         clamped = ops.clamp_depth(depth, rng, want_clamped=True)
         ctx.save_for_backward(rgbs, sample_pos, ray_offset, mask, depth, clamped)
         ctx.white_back = white_back
@@ -36,7 +38,7 @@ class _CompositeFn(torch.autograd.Function):
     def backward(ctx, g_mask, g_depth, g_rgb):
         rgbs, sample_pos, ray_offset, mask, depth, clamped = ctx.saved_tensors
         g = ops.composite_bwd(sample_pos, rgbs, ray_offset, ctx.white_back, g_rgb, g_mask, g_depth, mask, depth, clamped)
-        return g, None, None, None, None, None
+        return g, None, None, None, None, None, None
 
 
 class VolumeRenderer(nn.Module):
@@ -57,19 +59,45 @@ class VolumeRenderer(nn.Module):
         self.randomize_depth_samples = False  # toggled by PointNeRF.train() (pointnerf.py:30-33)
         self.max_samples_per_chunk = 1 << 25  # kept shading samples per fused field launch (bounds the workspace: ~1.1 KB each)
         self.last_stats = {}
+        # object-sharded training with global-batch semantics (`parallel.enable_global_batch`): the batch-coupled scalars of the
+        # reference -- the valid-ray minimum (`aggregator.py:102`), the depth clamp range (`renderer.py:154-156`) and the shared
+        # pixel subset (`renderer.py:232-238`) -- are taken over all ranks of this group
+        self.process_group = None
+        self._shared_seed = None   # (base seed common to all ranks, calls so far): set by parallel.enable_global_batch
+
+    def _group(self):
+        g = self.process_group
+        if g is None or not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            return None
+        return g if torch.distributed.get_world_size(g) > 1 else None
 
     # ---- train-mode valid-ray subsampling (fields/aggregators/aggregator.py:78-119) ----
-    def _subsample_valid_rays(self, ray_count: Tensor, rng):
+    def _call_seed(self, rng):
+        """Seed of this call's counter-based draws: injected (tests), common to all ranks of the group, or torch's CPU generator."""
+        if rng is not None and hasattr(rng, "subsample_seed"):
+            return int(rng.subsample_seed)
+        if self._group() is not None and self._shared_seed is not None:
+            base, calls = self._shared_seed
+            self._shared_seed = (base, calls + 1)
+            return (base + 0x9E3779B97F4A7C15 * (calls + 1)) & 0x7FFFFFFFFFFFFFFF
+        return int(torch.empty((), dtype=torch.int64).random_().item())
+
+    def _subsample_valid_rays(self, ray_count: Tensor, rng, seed: int):
         """ray_count [N,R] -> (ray_ids [N*n] int32 ascending per view, n)."""
         N, R = ray_count.shape
-        if rng is None:
-            # fused path: count + select kernels, one host sync; the seed comes from torch's CPU generator (torch.manual_seed applies)
-            seed = int(torch.empty((), dtype=torch.int64).random_().item())
-            return ops.subsample_valid_rays(ray_count.contiguous(), N, R, self.field.aggregator.ray_subsamples, seed)
+        if rng is None or not hasattr(rng, "valid_ray_perm"):
+            # fused path: count + select kernels, one host sync.  Under object sharding the draws are keyed by the global view
+            # number and the minimum runs over all ranks, so the sharded batch keeps the rays the whole batch would keep.
+            g = self._group()
+            off = torch.distributed.get_rank(g) * N if g is not None else 0
+            return ops.subsample_valid_rays(ray_count.contiguous(), N, R, self.field.aggregator.ray_subsamples, seed, g, off)
         # injected permutation (parity tests against the reference's own randperm): the reference's op sequence in torch
         valid = ray_count > 0
         nvalid = valid.sum(-1)
-        n = int(min(int(nvalid.min().item()), self.field.aggregator.ray_subsamples)) if N > 0 else 0
+        nmin = nvalid.min() if N > 0 else torch.zeros((), dtype=torch.int64, device=ray_count.device)
+        if self._group() is not None:
+            torch.distributed.all_reduce(nmin, op=torch.distributed.ReduceOp.MIN, group=self._group())
+        n = int(min(int(nmin.item()), self.field.aggregator.ray_subsamples)) if N > 0 else 0
         if n == 0:
             return torch.zeros(0, dtype=torch.int32, device=ray_count.device), 0
         inst, ray = torch.nonzero(valid, as_tuple=True)
@@ -105,8 +133,17 @@ class VolumeRenderer(nn.Module):
 
         # R1/R2: rays (+ train-mode ray subset shared by all views, renderer.py:232-238)
         subset = None
+        seed = self._call_seed(rng) if sample else 0
         if self.ray_subsamples and sample:
-            perm = torch.as_tensor(rng.ray_perm(num_pix), device=dev) if rng is not None else torch.randperm(num_pix, device=dev)
+            if rng is not None:
+                perm = torch.as_tensor(rng.ray_perm(num_pix), device=dev)
+            elif self._group() is not None and self._shared_seed is not None:
+                # one pixel subset for the views of all ranks, like the single process: same generator state on every rank
+                gen = torch.Generator(device=dev)
+                gen.manual_seed(seed)
+                perm = torch.randperm(num_pix, device=dev, generator=gen)
+            else:
+                perm = torch.randperm(num_pix, device=dev)
             subset = perm[: self.ray_subsamples].contiguous()
         rays = ops.rays_generate(extr.reshape(N, 4, 4), intr.reshape(N, 3, 3), resolution, subset, self.cube_scale,
                                  want_origins=return_aux)
@@ -127,7 +164,7 @@ class VolumeRenderer(nn.Module):
         out_rays = R
         ray_ids = None
         if sample:
-            ray_ids, out_rays = self._subsample_valid_rays(ray_count.view(N, R), rng)
+            ray_ids, out_rays = self._subsample_valid_rays(ray_count.view(N, R), rng, seed)
         n_out = N * out_rays
         mask = torch.empty((n_out,), device=dev)
         depth = torch.empty((n_out,), device=dev)
@@ -144,7 +181,7 @@ class VolumeRenderer(nn.Module):
                 feat = None
             else:
                 rgbs, feat = self.field.evaluate(nbr, pos, kp_pos, kp_feat, ray_offset[-1:], S, want_feat=return_aux)
-            mask, depth, rgb = _CompositeFn.apply(rgbs, pos, ray_offset, rays.end.reshape(-1), ray_ids, self.white_back)
+            mask, depth, rgb = _CompositeFn.apply(rgbs, pos, ray_offset, rays.end.reshape(-1), ray_ids, self.white_back, self._group())
             self.last_stats = dict(S=S, Np=None)
             if return_aux:
                 aux = dict(neighbor_idx=nbr, sample_pos=pos, rgbs=rgbs, feat=feat, ray_offset=ray_offset, ray_count=ray_count,

@@ -58,7 +58,7 @@ def test_ctypes_binding_matches_header(lib):
 
 def test_abi_version_and_error_string(lib):
     lib.npcd_abi_version.restype = ctypes.c_int
-    assert lib.npcd_abi_version() == 2
+    assert lib.npcd_abi_version() == 3
     lib.npcd_last_error.restype = ctypes.c_char_p
     assert isinstance(lib.npcd_last_error(), bytes)
 
@@ -171,8 +171,8 @@ def test_argument_errors_of_the_round1b_entry_points(lib):
     err = lambda: L.npcd_last_error()
     assert L.npcd_grid_build_masks(None, 1, 512, 0.08, None, None) == 1 and b"null pointer" in err()
     assert L.npcd_grid_build_masks(ctypes.c_void_p(8), 1, 512, 0.5, ctypes.c_void_p(8), None) == 1 and b"radius" in err()
-    assert L.npcd_subsample_valid_rays(None, 4, 112, 10, 1, None, None) == 1 and b"null pointer" in err()
-    assert L.npcd_subsample_valid_rays(None, 0, 112, 10, 1, None, None) == 0  # nothing to do
+    assert L.npcd_subsample_valid_rays(None, 4, 112, 10, 1, 0, None, None) == 1 and b"null pointer" in err()
+    assert L.npcd_subsample_valid_rays(None, 0, 112, 10, 1, 0, None, None) == 0  # nothing to do
     assert L.npcd_count_valid_rays(None, 4, 112, None, None, None) == 1
     assert L.npcd_embed_adam_rows(None, None, None, None, None, 2, 128, None, 1, 1e-3, 0.9, 0.999, 1e-8, None) == 1
     assert L.npcd_embed_adam_rows(None, None, None, None, None, 0, 128, None, 1, 1e-3, 0.9, 0.999, 1e-8, None) == 0
