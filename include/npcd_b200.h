@@ -74,8 +74,30 @@ int npcd_knn_points(const float* x, const int* query_obj, long long n, int queri
 int npcd_knn_fill(const float* cam_centers, const float* dirs, const float* ray_start, const float* ray_end, const float* jitter,
                   const int* ray_ids, long long n_sel, const long long* ray_offset, const unsigned* valid_bits, int rays_per_view,
                   int views_per_obj, int n_points, const int* cell_start, const float* sorted_pts, float radius,
-                  long long capacity, int* nbr_idx, float* sample_pos, int* sample_ray, int impl /* as npcd_march_count */,
-                  void* stream);
+                  long long capacity, int* nbr_idx, float* sample_pos,
+                  float* sample_t /* optional [capacity]: the slot depths (= sample_pos[.][3]) as a dense array for the compositor */,
+                  int* sample_ray, int impl /* as npcd_march_count */, void* stream);
+
+/* ---- Q1: voxel-grid-compatible query mode (the semantics of the reference's deployed path through torch_knnquery.VoxelGrid,
+ * fields/aggregators/aggregator.py:59-76 with the options of pointnerf.py:147-153; source un-vendored => PARITY UNPINNED, checked
+ * against oracle/pointnerf_oracle.py::query_keypoints_voxel).  Call order: npcd_voxel_select -> npcd_grid_build(stored_pos) ->
+ * npcd_march_count(max_shading_pts = 128) -> npcd_voxel_filter -> npcd_scan_counts -> npcd_knn_fill -> npcd_voxel_slots ->
+ * field -> npcd_composite_fwd(slot).
+ *   npcd_voxel_dims:   voxels per axis (round((hi - lo) / voxel_size), at most 32) and 32-bit words of one object's bit set.
+ *   npcd_voxel_select: stored_pos [B,P,3] = the points a voxel keeps (<= max_points_per_voxel per voxel, LOWEST index wins; points
+ *                      outside the ranges are dropped too), dropped points moved to a far sentinel npcd_grid_build ignores;
+ *                      vox_bits [B,words] = kernel_size^3 dilation of the occupied voxels, bit (x * n + y) * n + z.
+ *   npcd_voxel_filter: cand_bits [n_rays,4] = the first max_shading_pts samples of each ray lying in a set voxel; valid_bits &= them;
+ *                      ray_count [n_rays] = kept samples (candidates with a stored neighbour within r).
+ *   npcd_voxel_slots:  slot [S] u8 = index of every kept sample among its ray's candidates (gaps = holes, aggregator.py:66-70).    */
+int npcd_voxel_dims(float voxel_size, float range_lo, float range_hi, int* n_vox, int* words);
+int npcd_voxel_select(const float* kp_pos, int n_obj, int n_points, float voxel_size, float range_lo, int n_vox,
+                      int max_points_per_voxel, int kernel_size, float* stored_pos, unsigned* vox_bits, void* stream);
+int npcd_voxel_filter(const float* cam_centers, const float* dirs, const float* ray_start, const float* ray_end, const float* jitter,
+                      long long n_rays, int rays_per_view, int views_per_obj, const unsigned* vox_bits, int n_vox, float voxel_size,
+                      float range_lo, int max_shading_pts, unsigned* valid_bits, unsigned* cand_bits, int* ray_count, void* stream);
+int npcd_voxel_slots(const long long* ray_offset, const int* ray_ids, const unsigned* valid_bits, const unsigned* cand_bits,
+                     long long n_sel, long long capacity, unsigned char* slot, void* stream);
 
 /* ---- Q3: train-mode valid-ray subsampling, replaces Aggregator.subsample_valid_rays (fields/aggregators/aggregator.py:78-119) ------
  *   npcd_count_valid_rays: n_valid [n_views] = #rays of the view with ray_count > 0, min_valid [1] = their minimum (the host reads it:
@@ -297,13 +319,17 @@ int npcd_pair_tc_bwd(const float* d_agg, const npcd_pair_stash_layout* layout, v
  *   global slot-depth range (init_range != 0 resets it first, so several view chunks can share one range);
  *   npcd_clamp_depth then applies renderer.py:154-156 and records out_clamped [n] u8 (optional; needed by the backward).
  *   Backward: g_* may be NULL; g_rgbs [S,4] = d/d(r,g,b,sigma).                                                                */
-int npcd_composite_fwd(const float* sample_pos, const float* rgbs, const long long* ray_offset, const int* ray_ids,
-                       const float* ray_end, long long n_sel, int white_back, float* out_mask, float* out_depth, float* out_rgb,
-                       void* range_scratch, int init_range, void* stream);
+/*   sample_t (optional): the slot depths as a dense [S] array (npcd_knn_fill), else sample_pos[.][3] is read;
+ *   slot (optional, voxel-compat mode): slot index of every kept sample (npcd_voxel_slots); a sample whose successor is not in the
+ *   next slot is followed by a hole and gets delta = 0 (alpha = 0), leading holes put ray_end into the clamp range.               */
+int npcd_composite_fwd(const float* sample_pos, const float* sample_t, const float* rgbs, const long long* ray_offset,
+                       const int* ray_ids, const float* ray_end, const unsigned char* slot, long long n_sel, int white_back,
+                       float* out_mask, float* out_depth, float* out_rgb, void* range_scratch, int init_range, void* stream);
 int npcd_clamp_depth(float* depth, long long n, const void* range_scratch, unsigned char* out_clamped, void* stream);
-int npcd_composite_bwd(const float* sample_pos, const float* rgbs, const long long* ray_offset, long long n_sel, int white_back,
-                       const float* g_rgb, const float* g_mask, const float* g_depth, const float* out_mask,
-                       const float* out_depth, const unsigned char* clamped, float* g_rgbs, void* stream);
+int npcd_composite_bwd(const float* sample_pos, const float* sample_t, const float* rgbs, const long long* ray_offset,
+                       const unsigned char* slot, long long n_sel, int white_back, const float* g_rgb, const float* g_mask,
+                       const float* g_depth, const float* out_mask, const float* out_depth, const unsigned char* clamped,
+                       float* g_rgbs, void* stream);
 
 /* ---- TV loss of the neural point cloud: the second caller of the kNN boundary (npcd/losses/neural_point_cloud_tv_loss.py:28-83).
  *   nbr_idx [n,8] = npcd_knn_points of every point against its own cloud (global indices, -1 padded);

@@ -97,7 +97,11 @@ SIGNATURES = {
     "npcd_march_count": [P, P, P, P, P, L, I, I, I, P, P, P, P, P, F, I, P, P, I, P],
     "npcd_scan_workspace_bytes": [L, P],
     "npcd_scan_counts": [P, P, L, P, P, C.c_size_t, P],
-    "npcd_knn_fill": [P, P, P, P, P, P, L, P, P, I, I, I, P, P, F, L, P, P, P, I, P],
+    "npcd_knn_fill": [P, P, P, P, P, P, L, P, P, I, I, I, P, P, F, L, P, P, P, P, I, P],
+    "npcd_voxel_dims": [F, F, F, P, P],
+    "npcd_voxel_select": [P, I, I, F, F, I, I, I, P, P, P],
+    "npcd_voxel_filter": [P, P, P, P, P, L, I, I, P, I, F, F, I, P, P, P, P],
+    "npcd_voxel_slots": [P, P, P, P, L, L, P, P],
     "npcd_count_valid_rays": [P, L, I, P, P, P],
     "npcd_subsample_valid_rays": [P, L, I, I, C.c_ulonglong, L, P, P],
     "npcd_knn_points": [P, P, L, I, I, P, P, F, P, P],
@@ -135,9 +139,9 @@ SIGNATURES = {
     "npcd_kl_fwd": [P, P, L, I, F, P, P],
     "npcd_kl_bwd": [P, P, L, I, F, P, P, P, P],
     "npcd_embed_adam_rows": [P, P, P, P, P, I, L, P, I, D, D, D, D, P],
-    "npcd_composite_fwd": [P, P, P, P, P, L, I, P, P, P, P, I, P],
+    "npcd_composite_fwd": [P, P, P, P, P, P, P, L, I, P, P, P, P, I, P],
     "npcd_clamp_depth": [P, L, P, P, P],
-    "npcd_composite_bwd": [P, P, P, L, I, P, P, P, P, P, P, P, P],
+    "npcd_composite_bwd": [P, P, P, P, P, L, I, P, P, P, P, P, P, P, P],
 }
 
 

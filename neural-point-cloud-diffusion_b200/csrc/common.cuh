@@ -16,6 +16,10 @@ constexpr int kFreqs = 10;        // positional-encoding octaves              (p
 constexpr int kGrid = 24;         // acceleration grid: 24^3 cells of 1/12 > r = 0.08 over [-1,1]^3
 constexpr int kGridCells = kGrid * kGrid * kGrid;
 constexpr int kGridWords = kGridCells / 32;
+// Position of a point that must stay invisible to every query (voxel-compat mode: points beyond a voxel's cap).  npcd_grid_build
+// files such points under the last cell without marking occupancy; every distance test against them fails.
+constexpr float kFarSentinel = 1e9f;
+__host__ __device__ inline bool is_far_sentinel(float x) { return !(fabsf(x) < 1e8f); }
 
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);

@@ -44,12 +44,19 @@ struct SampleTerms {
   float4 c;                       // r, g, b, sigma
 };
 
-__device__ __forceinline__ SampleTerms load_terms(const float4* __restrict__ sample_pos, const float4* __restrict__ rgbs,
+// `slot` (voxel-compat mode, else null): slot index of every kept sample among its ray's candidates.  A kept sample whose successor
+// does not sit in the very next slot is followed by a HOLE, whose depth is the running maximum = its own: delta = 0, alpha = 0
+// (renderer.py:106-108 cummax, volume_renderer.py:35-38).
+__device__ __forceinline__ SampleTerms load_terms(const float4* __restrict__ sample_pos, const float* __restrict__ sample_t,
+                                                  const float4* __restrict__ rgbs, const unsigned char* __restrict__ slot,
                                                   long long off, int i, int n) {
   SampleTerms s;
   const bool valid = i < n;
-  s.t = valid ? __ldg(&sample_pos[off + i].w) : 0.f;
-  const float nxt = (i + 1 < n) ? __ldg(&sample_pos[off + i + 1].w) : s.t;  // slot n inherits t_{n-1}: delta_{n-1} = 0
+  auto depth_of = [&](long long k) { return sample_t ? __ldg(sample_t + k) : __ldg(&sample_pos[k].w); };
+  s.t = valid ? depth_of(off + i) : 0.f;
+  bool has_next = i + 1 < n;
+  if (has_next && slot) has_next = __ldg(slot + off + i + 1) == __ldg(slot + off + i) + 1;
+  const float nxt = has_next ? depth_of(off + i + 1) : s.t;  // slot n inherits t_{n-1}: delta_{n-1} = 0
   s.c = valid ? __ldg(&rgbs[off + i]) : make_float4(0.f, 0.f, 0.f, 0.f);
   s.delta = nxt - s.t;
   s.edd = expf(-(s.c.w * s.delta));
@@ -58,23 +65,42 @@ __device__ __forceinline__ SampleTerms load_terms(const float4* __restrict__ sam
   return s;
 }
 
-__global__ void __launch_bounds__(256) k_composite_fwd(const float4* __restrict__ sample_pos, const float4* __restrict__ rgbs,
+// Forward: a warp owns 32 CONSECUTIVE rays.  Lanes first fetch their own ray's offsets (coalesced); three of four rays of the eval
+// workload carry no sample and are finished right there by their lane; the rays with samples are then composited one after the
+// other by the whole warp (lanes own consecutive samples), each result parked in the owning lane, and all 32 outputs leave with
+// coalesced stores.  Slot depths come from `sample_t` ([S], written by the kNN kernel next to the positions: 4 B per sample
+// instead of a 16-byte sector for one float) or, when it is null, from sample_pos.w.
+__global__ void __launch_bounds__(256) k_composite_fwd(const float4* __restrict__ sample_pos, const float* __restrict__ sample_t,
+                                                       const float4* __restrict__ rgbs,
                                                        const long long* __restrict__ ray_offset,
                                                        const int* __restrict__ ray_ids, const float* __restrict__ ray_end,
+                                                       const unsigned char* __restrict__ slot,
                                                        long long n_sel, int white_back, float* __restrict__ out_mask,
                                                        float* __restrict__ out_depth, float* __restrict__ out_rgb,
                                                        uint32_t* __restrict__ range_ord) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long sel = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  const long long sel = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * 32 + lane;
+  const bool live = sel < n_sel;
   uint32_t dmin = 0xffffffffu, dmax = 0u;
-  bool has_samples = false;  // warp-uniform
-  if (sel < n_sel) {
-    const long long off = ray_offset[sel];
-    const int n = (int)(ray_offset[sel + 1] - off);
+  long long my_off = 0;
+  int my_n = 0;
+  if (live) {
+    my_off = ray_offset[sel];
+    my_n = (int)(ray_offset[sel + 1] - my_off);
+  }
+  // result of this lane's ray; a sample-free ray: mask 0, depth 0/0 -> NaN -> +inf (clamped later), colour = background
+  float o_mask = 0.f, o_depth = __int_as_float(0x7f800000), o_r = white_back ? 1.f : 0.f, o_g = o_r, o_b = o_r;
+  if (live && my_n == 0) dmin = dmax = f2ord(ray_end[ray_ids ? ray_ids[sel] : sel]);  // all slot depths = ray_end (renderer.py:109-110)
+  uint32_t todo = __ballot_sync(0xffffffffu, live && my_n > 0);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const long long off = __shfl_sync(0xffffffffu, my_off, src);
+    const int n = __shfl_sync(0xffffffffu, my_n, src);
     float carry = 1.f, sw = 0.f, swt = 0.f, r = 0.f, g = 0.f, b = 0.f;
     for (int base = 0; base < n; base += 32) {
       const int i = base + lane;
-      const SampleTerms s = load_terms(sample_pos, rgbs, off, i, n);
+      const SampleTerms s = load_terms(sample_pos, sample_t, rgbs, slot, off, i, n);
       const float incl = warp_scan_mul(s.f, lane);
       float excl = __shfl_up_sync(0xffffffffu, incl, 1);
       if (lane == 0) excl = 1.f;
@@ -83,28 +109,27 @@ __global__ void __launch_bounds__(256) k_composite_fwd(const float4* __restrict_
       carry *= __shfl_sync(0xffffffffu, incl, 31);
       if (i < n) { dmin = min(dmin, f2ord(s.t)); dmax = max(dmax, f2ord(s.t)); }
     }
-    // 3 of 4 rays of the eval workload carry no sample: their warps skip the five sum reductions and the range reduction below
-    if (n > 0) { sw = warp_sum(sw); swt = warp_sum(swt); r = warp_sum(r); g = warp_sum(g); b = warp_sum(b); }
-    has_samples = n > 0;
-    if (lane == 0) {
-      if (n == 0) {
-        const float e = ray_end[ray_ids ? ray_ids[sel] : sel];
-        dmin = dmax = f2ord(e);
+    sw = warp_sum(sw); swt = warp_sum(swt); r = warp_sum(r); g = warp_sum(g); b = warp_sum(b);
+    if (lane == src) {
+      if (slot && __ldg(slot + off) != 0) {  // leading holes carry ray_end (renderer.py:109-110): it joins the clamp range
+        const uint32_t e = f2ord(ray_end[ray_ids ? ray_ids[sel] : sel]);
+        dmin = min(dmin, e); dmax = max(dmax, e);
       }
       float d = swt / sw;
       if (d != d) d = __int_as_float(0x7f800000);  // nan_to_num(nan -> +inf)  (renderer.py:154)
       const float bg = white_back ? 1.0f - sw : 0.f;
-      out_mask[sel] = sw;
-      out_depth[sel] = d;
-      out_rgb[sel * 3 + 0] = r + bg; out_rgb[sel * 3 + 1] = g + bg; out_rgb[sel * 3 + 2] = b + bg;
+      o_mask = sw; o_depth = d; o_r = r + bg; o_g = g + bg; o_b = b + bg;
     }
   }
-  if (has_samples) {  // otherwise lane 0 alone holds a value (ray_end of a sample-free ray) and it is the lane that publishes
+  if (live) {
+    out_mask[sel] = o_mask;
+    out_depth[sel] = o_depth;
+    out_rgb[sel * 3 + 0] = o_r; out_rgb[sel * 3 + 1] = o_g; out_rgb[sel * 3 + 2] = o_b;
+  }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      dmin = min(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
-      dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
-    }
+  for (int o = 16; o; o >>= 1) {
+    dmin = min(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+    dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
   }
   __shared__ uint32_t smin[8], smax[8];
   if (lane == 0) { smin[warp] = dmin; smax[warp] = dmax; }
@@ -133,13 +158,14 @@ __global__ void k_init_range(uint32_t* p) { p[0] = 0xffffffffu; p[1] = 0u; }
 //   dw_i        = g_rgb . c_i  - (white_back ? sum(g_rgb) : 0) + g_mask + g_depth * (t_i - D) / M   [depth term if unclamped]
 //   dL/dalpha_i = T_i * dw_i - (sum_{k>i} dw_k w_k) / f_i          (autograd of the exclusive cumprod)
 //   dL/dsigma_i = dL/dalpha_i * delta_i * exp(-sigma_i delta_i)
-__global__ void __launch_bounds__(256) k_composite_bwd(const float4* __restrict__ sample_pos, const float4* __restrict__ rgbs,
+__global__ void __launch_bounds__(256) k_composite_bwd(const float4* __restrict__ sample_pos, const float* __restrict__ sample_t,
+                                                       const float4* __restrict__ rgbs,
                                                        const long long* __restrict__ ray_offset, long long n_sel,
                                                        int white_back, const float* __restrict__ g_rgb,
                                                        const float* __restrict__ g_mask, const float* __restrict__ g_depth,
                                                        const float* __restrict__ out_mask, const float* __restrict__ out_depth,
                                                        const unsigned char* __restrict__ clamped,
-                                                       float4* __restrict__ g_rgbs) {
+                                                       const unsigned char* __restrict__ slot, float4* __restrict__ g_rgbs) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long sel = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (sel >= n_sel) return;
@@ -159,7 +185,7 @@ __global__ void __launch_bounds__(256) k_composite_bwd(const float4* __restrict_
     for (int ch = 0; ch < kDepthRes / 32; ++ch) {
       carries[ch] = carry;
       if (ch * 32 < n) {
-        const SampleTerms s = load_terms(sample_pos, rgbs, off, ch * 32 + lane, n);
+        const SampleTerms s = load_terms(sample_pos, sample_t, rgbs, slot, off, ch * 32 + lane, n);
         const float incl = warp_scan_mul(s.f, lane);
         carry *= __shfl_sync(0xffffffffu, incl, 31);
       }
@@ -170,7 +196,7 @@ __global__ void __launch_bounds__(256) k_composite_bwd(const float4* __restrict_
   for (int ch = kDepthRes / 32 - 1; ch >= 0; --ch) {
     if (ch * 32 < n) {
     const int i = ch * 32 + lane;
-    const SampleTerms s = load_terms(sample_pos, rgbs, off, i, n);
+    const SampleTerms s = load_terms(sample_pos, sample_t, rgbs, slot, off, i, n);
     const float incl = warp_scan_mul(s.f, lane);
     float excl = __shfl_up_sync(0xffffffffu, incl, 1);
     if (lane == 0) excl = 1.f;
@@ -191,9 +217,10 @@ __global__ void __launch_bounds__(256) k_composite_bwd(const float4* __restrict_
 
 }  // namespace npcd
 
-extern "C" int npcd_composite_fwd(const float* sample_pos, const float* rgbs, const long long* ray_offset, const int* ray_ids,
-                                  const float* ray_end, long long n_sel, int white_back, float* out_mask, float* out_depth,
-                                  float* out_rgb, void* range_scratch, int init_range, void* stream) {
+extern "C" int npcd_composite_fwd(const float* sample_pos, const float* sample_t, const float* rgbs, const long long* ray_offset,
+                                  const int* ray_ids, const float* ray_end, const unsigned char* slot, long long n_sel,
+                                  int white_back, float* out_mask, float* out_depth, float* out_rgb, void* range_scratch,
+                                  int init_range, void* stream) {
   using namespace npcd;
   NPCD_CHECK_ARG(ray_offset && ray_end && out_mask && out_depth && out_rgb && range_scratch, "null pointer");
   NPCD_CHECK_ARG(n_sel >= 0, "bad n_sel");
@@ -201,10 +228,10 @@ extern "C" int npcd_composite_fwd(const float* sample_pos, const float* rgbs, co
   uint32_t* rng = (uint32_t*)range_scratch;
   if (init_range) k_init_range<<<1, 1, 0, st>>>(rng);
   if (n_sel > 0) {
-    const int wpb = 8;
-    k_composite_fwd<<<(unsigned)((n_sel + wpb - 1) / wpb), wpb * 32, 0, st>>>((const float4*)sample_pos, (const float4*)rgbs,
-                                                                             ray_offset, ray_ids, ray_end, n_sel, white_back,
-                                                                             out_mask, out_depth, out_rgb, rng);
+    const int rpb = 8 * 32;  // 8 warps x 32 rays
+    k_composite_fwd<<<(unsigned)((n_sel + rpb - 1) / rpb), 256, 0, st>>>((const float4*)sample_pos, sample_t, (const float4*)rgbs,
+                                                                        ray_offset, ray_ids, ray_end, slot, n_sel, white_back,
+                                                                        out_mask, out_depth, out_rgb, rng);
   }
   return check_launch("npcd_composite_fwd");
 }
@@ -218,18 +245,18 @@ extern "C" int npcd_clamp_depth(float* depth, long long n, const void* range_scr
   return check_launch("npcd_clamp_depth");
 }
 
-extern "C" int npcd_composite_bwd(const float* sample_pos, const float* rgbs, const long long* ray_offset, long long n_sel,
-                                  int white_back, const float* g_rgb, const float* g_mask, const float* g_depth,
-                                  const float* out_mask, const float* out_depth, const unsigned char* clamped, float* g_rgbs,
-                                  void* stream) {
+extern "C" int npcd_composite_bwd(const float* sample_pos, const float* sample_t, const float* rgbs, const long long* ray_offset,
+                                  const unsigned char* slot, long long n_sel, int white_back, const float* g_rgb,
+                                  const float* g_mask, const float* g_depth, const float* out_mask, const float* out_depth,
+                                  const unsigned char* clamped, float* g_rgbs, void* stream) {
   using namespace npcd;
   NPCD_CHECK_ARG(ray_offset && out_mask && out_depth && g_rgbs, "null pointer");
   NPCD_CHECK_ARG(n_sel >= 0, "bad n_sel");
   if (n_sel == 0) return 0;
   const int wpb = 8;
   k_composite_bwd<<<(unsigned)((n_sel + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
-      (const float4*)sample_pos, (const float4*)rgbs, ray_offset, n_sel, white_back, g_rgb, g_mask, g_depth, out_mask, out_depth,
-      clamped, (float4*)g_rgbs);
+      (const float4*)sample_pos, sample_t, (const float4*)rgbs, ray_offset, n_sel, white_back, g_rgb, g_mask, g_depth, out_mask,
+      out_depth, clamped, slot, (float4*)g_rgbs);
   return check_launch("npcd_composite_bwd");
 }
 

@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(512) k_grid_build(const float* __restrict__ kp
   for (int p = tid; p < P; p += nt) {
     const float x = pts[p * 3], y = pts[p * 3 + 1], z = pts[p * 3 + 2];
     atomicAdd(&hist[cell_of(x, y, z)], 1);
+    if (is_far_sentinel(x)) continue;  // invisible point (voxel-compat mode): listed under the last cell, no occupancy, no box
     const int cx = grid_coord(x), cy = grid_coord(y), cz = grid_coord(z);
     atomicMin(&box[0], cx); atomicMin(&box[1], cy); atomicMin(&box[2], cz);
     atomicMax(&box[3], cx); atomicMax(&box[4], cy); atomicMax(&box[5], cz);
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(128) k_grid_masks(const float* __restrict__ kp
   const float r2_maybe = r_maybe * r_maybe, r2_sure = r_sure > 0.f ? r_sure * r_sure : 0.f;
   const float h = 2.0f / kFine;
   const float c3[3] = {pts[p * 3], pts[p * 3 + 1], pts[p * 3 + 2]};
+  if (is_far_sentinel(c3[0])) return;
   int lo[3], hi[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {

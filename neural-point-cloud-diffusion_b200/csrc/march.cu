@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(128) k_knn_fill(const float* __restrict__ cam,
                                                   int P, const int* __restrict__ cell_start,
                                                   const float4* __restrict__ sorted_pts, float radius,
                                                   long long capacity, int* __restrict__ nbr_idx,
-                                                  float4* __restrict__ sample_pos, int* __restrict__ sample_ray) {
+                                                  float4* __restrict__ sample_pos, float* __restrict__ sample_t, int* __restrict__ sample_ray) {
   const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long S = min(ray_offset[n_sel], capacity);
   if (s >= S) return;
@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(128) k_knn_fill(const float* __restrict__ cam,
   if (q1 == q1) { sum = __fadd_rn(sum, q1); cnt += 1.f; }
   if (q2 == q2) { sum = __fadd_rn(sum, q2); cnt += 1.f; }
   sample_pos[s] = make_float4(x, y, z, __fdiv_rn(sum, cnt));
+  if (sample_t) sample_t[s] = __fdiv_rn(sum, cnt);
   if (sample_ray) sample_ray[s] = (int)sel;
 }
 
@@ -557,7 +558,7 @@ __global__ void __launch_bounds__(kChunk) k_knn_fill_s(const float* __restrict__
                                                        int rays_per_view, int views_per_obj, int P, const int* __restrict__ cell_start,
                                                        const float4* __restrict__ sorted_pts, float radius, float T, long long capacity,
                                                        int* __restrict__ nbr_idx, float4* __restrict__ sample_pos,
-                                                       int* __restrict__ sample_ray, int rays_per_cta) {
+                                                       float* __restrict__ sample_t, int* __restrict__ sample_ray, int rays_per_cta) {
   extern __shared__ __align__(16) uint8_t smem_raw[];  // [sorted points of the chunk's object: P float4][cand_d2][range][cand_idx]
   __shared__ int off_s[kChunk + 1];
   float4* pts_s = reinterpret_cast<float4*>(smem_raw);
@@ -614,6 +615,7 @@ __global__ void __launch_bounds__(kChunk) k_knn_fill_s(const float* __restrict__
     if (q1 == q1) { sum = __fadd_rn(sum, q1); cnt += 1.f; }
     if (q2 == q2) { sum = __fadd_rn(sum, q2); cnt += 1.f; }
     sample_pos[s] = make_float4(x, y, z, __fdiv_rn(sum, cnt));
+    if (sample_t) sample_t[s] = __fdiv_rn(sum, cnt);
     if (sample_ray) sample_ray[s] = (int)sel;
   }
 }
@@ -674,7 +676,7 @@ extern "C" int npcd_knn_fill(const float* cam_centers, const float* dirs, const 
                              const float* jitter, const int* ray_ids, long long n_sel, const long long* ray_offset,
                              const unsigned* valid_bits, int rays_per_view, int views_per_obj, int n_points,
                              const int* cell_start, const float* sorted_pts, float radius, long long capacity, int* nbr_idx,
-                             float* sample_pos, int* sample_ray, int impl, void* stream) {
+                             float* sample_pos, float* sample_t, int* sample_ray, int impl, void* stream) {
   using namespace npcd;
   NPCD_CHECK_ARG(cam_centers && dirs && ray_start && ray_end && ray_offset && valid_bits && cell_start && sorted_pts, "null pointer");
   NPCD_CHECK_ARG(capacity == 0 || (nbr_idx && sample_pos), "null output with capacity > 0");
@@ -689,7 +691,8 @@ extern "C" int npcd_knn_fill(const float* cam_centers, const float* dirs, const 
     const int rpc = rays_per_cta_for(n_sel);
     k_knn_fill_s<<<(unsigned)((n_sel + rpc - 1) / rpc), kChunk, smem, (cudaStream_t)stream>>>(
         cam_centers, dirs, ray_start, ray_end, jitter, ray_ids, n_sel, ray_offset, valid_bits, rays_per_view, views_per_obj, n_points,
-        cell_start, (const float4*)sorted_pts, radius, radius_threshold(radius), capacity, nbr_idx, (float4*)sample_pos, sample_ray, rpc);
+        cell_start, (const float4*)sorted_pts, radius, radius_threshold(radius), capacity, nbr_idx, (float4*)sample_pos, sample_t,
+        sample_ray, rpc);
     return check_launch("npcd_knn_fill");
   }
   const int bs = 128;
@@ -697,7 +700,7 @@ extern "C" int npcd_knn_fill(const float* cam_centers, const float* dirs, const 
   k_knn_fill<<<grid, bs, 0, (cudaStream_t)stream>>>(cam_centers, dirs, ray_start, ray_end, jitter, ray_ids, n_sel, ray_offset,
                                                     valid_bits, rays_per_view, views_per_obj, n_points, cell_start,
                                                     (const float4*)sorted_pts, radius, capacity, nbr_idx, (float4*)sample_pos,
-                                                    sample_ray);
+                                                    sample_t, sample_ray);
   return check_launch("npcd_knn_fill");
 }
 

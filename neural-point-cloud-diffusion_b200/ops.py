@@ -121,6 +121,7 @@ class Grid:
     masks: Optional[torch.Tensor] = None  # [B, cells, 2] int64 (sure, maybe) sub-cell masks, built lazily for one radius
     mask_radius: Optional[float] = None
     kp_pos: Optional[torch.Tensor] = None  # the (detached, contiguous) points the grid was built from
+    vox: Optional["VoxelSpec"] = None      # voxel-compat mode: the grid holds the STORED points only, candidates come from vox.vox_bits
 
 
 _GRID_DIMS = None
@@ -212,20 +213,87 @@ def scan_counts(ray_count, ray_ids=None):
 def knn_fill(rays: Rays, grid: Grid, views_per_obj: int, radius: float, valid_bits, ray_offset, capacity: int, ray_ids=None,
              jitter=None, want_sample_ray: bool = False):
     """Returns nbr_idx [capacity,8] int32, sample_pos [capacity,4], sample_ray [capacity] int32 or None."""
+    nbr, pos, _, sray = knn_fill_t(rays, grid, views_per_obj, radius, valid_bits, ray_offset, capacity, ray_ids, jitter, want_sample_ray,
+                                   want_t=False)
+    return nbr, pos, sray
+
+
+def knn_fill_t(rays: Rays, grid: Grid, views_per_obj: int, radius: float, valid_bits, ray_offset, capacity: int, ray_ids=None,
+               jitter=None, want_sample_ray: bool = False, want_t: bool = True):
+    """``knn_fill`` that also returns the slot depths as a dense [capacity] array (what the compositor streams: 4 B per sample)."""
     N, R = rays.start.shape
     dev = rays.start.device
     n_sel = ray_offset.numel() - 1
     nbr = torch.empty((capacity, K_NEIGHBORS), dtype=torch.int32, device=dev)
     pos = torch.empty((capacity, 4), device=dev)
+    t = torch.empty((capacity,), device=dev) if want_t else None
     sray = torch.empty((capacity,), dtype=torch.int32, device=dev) if want_sample_ray else None
     if jitter is not None:
         jitter = jitter.contiguous().float()
     _timed("knn", lambda: call(
         "npcd_knn_fill", ptr(rays.cam), ptr(rays.dirs), ptr(rays.start), ptr(rays.end), ptr(jitter), ptr(ray_ids), n_sel,
         ptr(ray_offset), ptr(valid_bits), R, views_per_obj, grid.n_points, ptr(grid.cell_start), ptr(grid.sorted_pts),
-        float(radius), capacity, ptr(nbr), ptr(pos), ptr(sray), int(QUERY_IMPL), _stream()))
+        float(radius), capacity, ptr(nbr), ptr(pos), ptr(t), ptr(sray), int(QUERY_IMPL), _stream()))
     _count(1 if capacity and n_sel else 0)
-    return nbr, pos, sray
+    return nbr, pos, t, sray
+
+
+# ---- voxel-grid-compatible query mode (SURVEY.md section 8(a) Q1; csrc/voxel_compat.cu) ------------------------------------------
+@dataclass
+class VoxelSpec:
+    voxel_size: float       # edge of a voxel: voxel_size * voxel_scale of the reference options (0.08)
+    range_lo: float
+    n_vox: int
+    words: int
+    max_points_per_voxel: int
+    kernel_size: int
+    vox_bits: torch.Tensor  # [B, words] int32: dilated occupancy of the stored points
+
+
+def voxel_dims(voxel_size: float, range_lo: float, range_hi: float):
+    n, w = C.c_int(), C.c_int()
+    call("npcd_voxel_dims", float(voxel_size), float(range_lo), float(range_hi), C.byref(n), C.byref(w))
+    return n.value, w.value
+
+
+def voxel_select(kp_pos, voxel_size: float, range_lo: float, range_hi: float, max_points_per_voxel: int, kernel_size: int):
+    """kp_pos [B,P,3] -> (stored_pos [B,P,3]: dropped points moved to the far sentinel, VoxelSpec)."""
+    _need_cuda(kp_pos)
+    kp_pos = kp_pos.detach().contiguous().float()
+    B, P = kp_pos.shape[:2]
+    n_vox, words = voxel_dims(voxel_size, range_lo, range_hi)
+    stored = torch.empty_like(kp_pos)
+    bits = torch.empty((B, words), dtype=torch.int32, device=kp_pos.device)
+    call("npcd_voxel_select", ptr(kp_pos), B, P, float(voxel_size), float(range_lo), n_vox, int(max_points_per_voxel), int(kernel_size),
+         ptr(stored), ptr(bits), _stream())
+    _count(1 if B else 0)
+    return stored, VoxelSpec(float(voxel_size), float(range_lo), n_vox, words, int(max_points_per_voxel), int(kernel_size), bits)
+
+
+def voxel_filter(rays: Rays, vox: VoxelSpec, views_per_obj: int, max_shading_pts: int, valid_bits, jitter=None):
+    """In place on valid_bits (from ``march_count`` with no cap).  Returns (valid_bits, cand_bits [N*R,4], ray_count [N*R])."""
+    N, R = rays.start.shape
+    n_rays = N * R
+    dev = rays.start.device
+    cand = torch.empty((n_rays, 4), dtype=torch.int32, device=dev)
+    ray_count = torch.empty((n_rays,), dtype=torch.int32, device=dev)
+    if jitter is not None:
+        jitter = jitter.contiguous().float()
+    _timed("march", lambda: call(
+        "npcd_voxel_filter", ptr(rays.cam), ptr(rays.dirs), ptr(rays.start), ptr(rays.end), ptr(jitter), n_rays, R, views_per_obj,
+        ptr(vox.vox_bits), vox.n_vox, vox.voxel_size, vox.range_lo, int(max_shading_pts), ptr(valid_bits), ptr(cand), ptr(ray_count),
+        _stream()))
+    _count(1 if n_rays else 0)
+    return valid_bits, cand, ray_count
+
+
+def voxel_slots(ray_offset, ray_ids, valid_bits, cand_bits, capacity: int):
+    """slot [capacity] uint8: index of every kept sample among its ray's candidates."""
+    n_sel = ray_offset.numel() - 1
+    slot = torch.empty((capacity,), dtype=torch.uint8, device=ray_offset.device)
+    call("npcd_voxel_slots", ptr(ray_offset), ptr(ray_ids), ptr(valid_bits), ptr(cand_bits), n_sel, capacity, ptr(slot), _stream())
+    _count(1 if n_sel and capacity else 0)
+    return slot
 
 
 def subsample_valid_rays(ray_count, n_views: int, rays_per_view: int, max_keep: int, seed: int, group=None, view_offset: int = 0):
@@ -1049,9 +1117,10 @@ def field_simt_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity
 
 
 def composite_fwd(sample_pos, rgbs, ray_offset, ray_end, ray_ids=None, white_back: bool = True, range_scratch=None,
-                  init_range: bool = True, out=None):
+                  init_range: bool = True, out=None, sample_t=None, slot=None):
     """Returns mask [n], depth_raw [n], rgb [n,3], range_scratch (call clamp_depth afterwards).
-    ``out`` = (mask, depth, rgb) contiguous views to write into (chunked inference)."""
+    ``out`` = (mask, depth, rgb) contiguous views to write into (chunked inference); ``sample_t``: dense [S] slot depths (else
+    sample_pos[:, 3] is read); ``slot``: voxel-compat slot indices (holes)."""
     dev = ray_offset.device
     n = ray_offset.numel() - 1
     if out is None:
@@ -1063,8 +1132,9 @@ def composite_fwd(sample_pos, rgbs, ray_offset, ray_end, ray_ids=None, white_bac
         assert mask.numel() == n and depth.numel() == n and rgb.numel() == 3 * n
     if range_scratch is None:
         range_scratch = torch.empty(2, dtype=torch.int32, device=dev)
-    _timed("composite", lambda: call("npcd_composite_fwd", ptr(sample_pos), ptr(rgbs), ptr(ray_offset), ptr(ray_ids), ptr(ray_end), n,
-                                     int(white_back), ptr(mask), ptr(depth), ptr(rgb), ptr(range_scratch), int(init_range), _stream()))
+    _timed("composite", lambda: call("npcd_composite_fwd", ptr(sample_pos), ptr(sample_t), ptr(rgbs), ptr(ray_offset), ptr(ray_ids),
+                                     ptr(ray_end), ptr(slot), n, int(white_back), ptr(mask), ptr(depth), ptr(rgb), ptr(range_scratch),
+                                     int(init_range), _stream()))
     _count((1 if init_range else 0) + (1 if n else 0))
     return mask, depth, rgb, range_scratch
 
@@ -1087,12 +1157,13 @@ def clamp_depth(depth, range_scratch, want_clamped: bool = False):
     return clamped
 
 
-def composite_bwd(sample_pos, rgbs, ray_offset, white_back, g_rgb, g_mask, g_depth, out_mask, out_depth, clamped):
+def composite_bwd(sample_pos, rgbs, ray_offset, white_back, g_rgb, g_mask, g_depth, out_mask, out_depth, clamped, sample_t=None,
+                  slot=None):
     S = rgbs.shape[0]
     n = ray_offset.numel() - 1
     g = torch.zeros((S, 4), device=rgbs.device)
     cont = lambda t: None if t is None else t.contiguous().float()
-    call("npcd_composite_bwd", ptr(sample_pos), ptr(rgbs), ptr(ray_offset), n, int(white_back), ptr(cont(g_rgb)), ptr(cont(g_mask)),
+    call("npcd_composite_bwd", ptr(sample_pos), ptr(sample_t), ptr(rgbs), ptr(ray_offset), ptr(slot), n, int(white_back), ptr(cont(g_rgb)), ptr(cont(g_mask)),
          ptr(cont(g_depth)), ptr(out_mask), ptr(out_depth), ptr(clamped), ptr(g), _stream())
     _count(1 if n else 0)
     return g

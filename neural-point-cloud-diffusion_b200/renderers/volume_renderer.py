@@ -25,20 +25,21 @@ class _CompositeFn(torch.autograd.Function):
     """Compositing over compact per-ray sample lists; backward = ``npcd_composite_bwd``."""
 
     @staticmethod
-    def forward(ctx, rgbs, sample_pos, ray_offset, ray_end, ray_ids, white_back, group=None):
-        mask, depth, rgb, rng = ops.composite_fwd(sample_pos, rgbs, ray_offset, ray_end, ray_ids, white_back)
+    def forward(ctx, rgbs, sample_pos, ray_offset, ray_end, ray_ids, white_back, group=None, sample_t=None, slot=None):
+        mask, depth, rgb, rng = ops.composite_fwd(sample_pos, rgbs, ray_offset, ray_end, ray_ids, white_back, sample_t=sample_t, slot=slot)
         if group is not None:
             ops.range_all_reduce(rng, group)
         clamped = ops.clamp_depth(depth, rng, want_clamped=True)
-        ctx.save_for_backward(rgbs, sample_pos, ray_offset, mask, depth, clamped)
+        ctx.save_for_backward(rgbs, sample_pos, ray_offset, mask, depth, clamped, sample_t, slot)
         ctx.white_back = white_back
         return mask, depth, rgb
 
     @staticmethod
     def backward(ctx, g_mask, g_depth, g_rgb):
-        rgbs, sample_pos, ray_offset, mask, depth, clamped = ctx.saved_tensors
-        g = ops.composite_bwd(sample_pos, rgbs, ray_offset, ctx.white_back, g_rgb, g_mask, g_depth, mask, depth, clamped)
-        return g, None, None, None, None, None, None
+        rgbs, sample_pos, ray_offset, mask, depth, clamped, sample_t, slot = ctx.saved_tensors
+        g = ops.composite_bwd(sample_pos, rgbs, ray_offset, ctx.white_back, g_rgb, g_mask, g_depth, mask, depth, clamped,
+                              sample_t=sample_t, slot=slot)
+        return g, None, None, None, None, None, None, None, None
 
 
 class VolumeRenderer(nn.Module):
@@ -158,7 +159,11 @@ class VolumeRenderer(nn.Module):
             else:
                 jitter = torch.rand((N, R, ops.DEPTH_RES), device=dev)
 
-        valid_bits, ray_count = ops.march_count(rays, grid, T, radius, SR, jitter)
+        vox = grid.vox  # voxel-compat semantics (VoxelGrid.semantics == "voxelgrid"): candidates, per-voxel cap, holes
+        valid_bits, ray_count = ops.march_count(rays, grid, T, radius, SR if vox is None else ops.DEPTH_RES, jitter)
+        cand_bits = None
+        if vox is not None:
+            valid_bits, cand_bits, ray_count = ops.voxel_filter(rays, vox, T, SR, valid_bits, jitter)
 
         needs_grad = torch.is_grad_enabled() and (kp_feat.requires_grad or any(p.requires_grad for p in self.field.parameters()))
         out_rays = R
@@ -175,17 +180,19 @@ class VolumeRenderer(nn.Module):
             # single launch group with autograd support
             ray_offset = ops.scan_counts(ray_count, ray_ids)
             S = int(ray_offset[-1].item())
-            nbr, pos, _ = ops.knn_fill(rays, grid, T, radius, valid_bits, ray_offset, S, ray_ids, jitter)
+            nbr, pos, tdep, _ = ops.knn_fill_t(rays, grid, T, radius, valid_bits, ray_offset, S, ray_ids, jitter)
+            slot = ops.voxel_slots(ray_offset, ray_ids, valid_bits, cand_bits, S) if vox is not None else None
             if needs_grad:
                 rgbs = self.field.evaluate_autograd(nbr, pos, kp_pos, kp_feat, ray_offset[-1:]) if S > 0 else torch.zeros((0, 4), device=dev)
                 feat = None
             else:
                 rgbs, feat = self.field.evaluate(nbr, pos, kp_pos, kp_feat, ray_offset[-1:], S, want_feat=return_aux)
-            mask, depth, rgb = _CompositeFn.apply(rgbs, pos, ray_offset, rays.end.reshape(-1), ray_ids, self.white_back, self._group())
+            mask, depth, rgb = _CompositeFn.apply(rgbs, pos, ray_offset, rays.end.reshape(-1), ray_ids, self.white_back, self._group(),
+                                                  tdep, slot)
             self.last_stats = dict(S=S, Np=None)
             if return_aux:
                 aux = dict(neighbor_idx=nbr, sample_pos=pos, rgbs=rgbs, feat=feat, ray_offset=ray_offset, ray_count=ray_count,
-                           rays=rays, ray_ids=ray_ids)
+                           rays=rays, ray_ids=ray_ids, slot=slot)
         else:
             # inference: one scan over all rays gives the kept-sample total (the single host sync); if it fits the workspace
             # bound the whole batch is ONE launch group, otherwise rays are chunked by the measured sample density.  The depth
@@ -211,10 +218,11 @@ class VolumeRenderer(nn.Module):
                         ids = torch.arange(r0, r1, dtype=torch.int32, device=dev)
                         ray_offset = ops.scan_counts(ray_count, ids)
                         S = int(ray_offset[-1].item())
-                    nbr, pos, _ = ops.knn_fill(rays, grid, T, radius, valid_bits, ray_offset, S, ids, jitter)
+                    nbr, pos, tdep, _ = ops.knn_fill_t(rays, grid, T, radius, valid_bits, ray_offset, S, ids, jitter)
+                    slot = ops.voxel_slots(ray_offset, ids, valid_bits, cand_bits, S) if vox is not None else None
                     rgbs, _ = self.field.evaluate(nbr, pos, kp_pos, kp_feat, ray_offset[-1:], S)
                     ops.composite_fwd(pos, rgbs, ray_offset, ray_end, ids, self.white_back, range_scratch=rng_scratch,
-                                      init_range=first, out=(mask[r0:r1], depth[r0:r1], rgb[r0:r1]))
+                                      init_range=first, out=(mask[r0:r1], depth[r0:r1], rgb[r0:r1]), sample_t=tdep, slot=slot)
                     first = False
             if first:  # no rays at all
                 ops.composite_fwd(None, None, torch.zeros(1, dtype=torch.int64, device=dev), ray_end, None, self.white_back,
