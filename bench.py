@@ -497,6 +497,25 @@ def bench_train(ctx, steps, warmup):
         host_ms.append(1e3 * (time.perf_counter() - t_host))
         marks[i + 1].record()
     ctx.barrier()
+    if os.environ.get("NPCD_BENCH_PROFILE") and rank == 0:  # development aid: where does a step spend its host / device time?
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=50), file=sys.stderr)
+        print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=40, max_name_column_width=50), file=sys.stderr)
+        import cProfile
+        import pstats
+
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(10):
+            step()
+        torch.cuda.synchronize()
+        pr.disable()
+        pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(45)
     raw_steps = [marks[i].elapsed_time(marks[i + 1]) for i in range(steps)]
     per_step = sorted(raw_steps)
     ms_total = ctx.max_over_ranks(marks[0].elapsed_time(marks[steps]))

@@ -21,7 +21,7 @@ DEPTH_RES = 128
 HIDDEN = 256
 # operand scheme of the tensor-core inference kernels: "f16x3" (three fp16 products per layer) or "f16+e4m3x2" (fp16 hi x hi plus
 # two e4m3 correction products at twice the tensor rate); fields.MLP.precision overrides it per model
-DEFAULT_PRECISION = "f16x3"
+DEFAULT_PRECISION = "f16+e4m3x2"
 
 # number of kernels launched by this process through the C-ABI (bench.py reports it as gpu_launches)
 LAUNCHES = 0

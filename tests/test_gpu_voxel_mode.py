@@ -63,7 +63,8 @@ def test_voxel_mode_render_vs_oracle(kind, objs, views, res, syn, weights, camer
     np.testing.assert_array_equal(aux["slot"].cpu().numpy(), np.nonzero(mask.reshape(-1, mask.shape[-1]))[1].astype(np.uint8))
     for k in ("mask", "depth", "channels"):
         np.testing.assert_allclose(out[k].cpu().numpy(), ref[k], atol=1e-4, rtol=0, err_msg=k)
-        assert torch.equal(out[k], plain[k]), k
+        # (the plain inference path folds local_field.8 into the heads: same images to ~1e-7)
+        np.testing.assert_allclose(plain[k].cpu().numpy(), out[k].cpu().numpy(), atol=2e-6, rtol=0, err_msg=k)
     # the mode matters: the exact query sees more points / samples on the same inputs
     exact = orc.render(coords, feats, extr, K, res, weights, return_aux=True)
     assert exact["aux"]["neighbor_idx"].shape[0] != ra["neighbor_idx"].shape[0] or not np.array_equal(exact["aux"]["neighbor_idx"], ra["neighbor_idx"])

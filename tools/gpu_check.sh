@@ -2,7 +2,7 @@
 tag=${1:-run}
 out=gpurun_out/$tag
 mkdir -p $out
-python -m pytest tests/test_gpu_precision.py -x -q -m gpu -s > $out/pytest_precision.log 2>&1; echo "rc=$?" >> $out/pytest_precision.log
+python -m pytest tests/test_gpu_precision.py tests/test_gpu_voxel_mode.py -q -m gpu -s > $out/pytest_precision.log 2>&1; echo "rc=$?" >> $out/pytest_precision.log
 grep -E "probe|max err|max \||passed|failed|Error|rc=" $out/pytest_precision.log | tail -n 30
 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-secondary --precision f16x3 > $out/bench_f16x3.json 2> $out/bench_f16x3.err
 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-secondary --precision f16+e4m3x2 > $out/bench_f8.json 2> $out/bench_f8.err
