@@ -108,6 +108,7 @@ SIGNATURES = {
     "npcd_field_simt_fwd": [P, P, P, P, P, L, P, P, P, P, I, I, P],
     "npcd_tc_pack_weights": [P, I, P, I, F, P, P],
     "npcd_tc_pack_weights_batched": [P, I, P],
+    "npcd_debug_set_timeline": [P],
     "npcd_tc_pack_weights_f8": [P, I, P, I, F, P, P],
     "npcd_tc_rows_to_image_f8": [P, L, P, P],
     "npcd_tc_image_to_rows_f8": [P, L, P, P],

@@ -18,6 +18,11 @@
 //                 as soon as K-block 0 is there, so the tensor pipe only idles for one chunk per layer.
 //   warp 10     : heads mode only: bulk-copies the next tile's pre-split A operand (written by the pair kernel) into the
 //                 K-blocks the last layer's MMAs have released.
+//   warps 11..14: inference pair mode only (ncu on the version where the epilogue threads did this between their layer epilogues:
+//                 the tensor pipe was busy 48 % of the time, the 8 epilogue warps were the serial resource): one thread per row
+//                 of the NEXT tile gathers the pair's point, computes the positional encoding and stores the layer-0 operand
+//                 as soon as layer 3's MMAs release K-blocks 0 / 1; the same warps then take a third of the segmented-sum
+//                 tasks of the aggregation epilogue.
 // Pair mode packs (sample, neighbour) pairs DENSELY: a tile is a maximal run of whole samples whose pairs fit its 128 rows (greedy,
 // k_tile_walk below: ~125 used rows per tile), instead of 8 slots per sample (21 % padding at 6.3 neighbours per sample).
 // The next tile's gather + positional encoding is computed by the epilogue threads while the tensor pipe works on layers 1..2
@@ -31,6 +36,12 @@ namespace tc {
 
 constexpr int kThreadsTc = 352;
 constexpr int kThreadsTcTrainHeads = 384;  // + warp 11: stash copies (warp 10 is the first-operand loader in heads mode)
+constexpr int kThreadsTcPro = 480;         // inference pair mode: + warps 11..14, the input (gather / posenc) warps
+constexpr int kProThreads = 128;
+template <int kMode>
+constexpr int threads_for() {
+  return kMode == 0 /* MODE_PAIR */ ? kThreadsTcPro : (kMode == 4 /* MODE_HEADS_TRAIN */ ? kThreadsTcTrainHeads : kThreadsTc);
+}
 constexpr int kEpiThreads = 256;
 constexpr int kTileBytesW = 256 * 128;        // one K-block of 256 output rows
 constexpr int kStages = 3;
@@ -102,7 +113,15 @@ struct Params {
   // training stash of the heads stage (MODE_HEADS_TRAIN), per 128-sample tile
   uint8_t* hstash_x[6];      // operand images of F (local_field.8 output), C1, C2, C3 (channel_net hidden 1..3), C4, H (shape hidden)
   uint32_t* hstash_mask[5];  // sign bits of H, C1, C2, C3, C4
+  long long* timeline;       // development aid (npcd_debug_set_timeline): clock64() of CTA 0's phase boundaries, [tile][32] events
 };
+
+constexpr int kTimelineTiles = 64;
+// event e of the `it`-th tile of CTA 0 (one designated thread per role calls this; a null pointer costs one uniform branch)
+#define NPCD_TL(it, e)                                                                                        \
+  do {                                                                                                        \
+    if (P.timeline && blockIdx.x == 0 && (it) < kTimelineTiles) P.timeline[(it) * 32 + (e)] = clock64();      \
+  } while (0)
 
 // One chunk (32 accumulator columns starting at c0) of an ACT / LINEAR epilogue: y = [lrelu](acc * inv + b) -> fp16 hi/lo ->
 // K-block (c0 >> 6) of the A operand, 16-byte chunks (c0 & 63) / 8 .. +3.
@@ -162,8 +181,9 @@ constexpr bool kCluster = true;
 
 // ------------------------------------------------------------------------------------------------------------- kernel ----
 template <int kMode, bool kF8 = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_TRAIN ? kThreadsTcTrainHeads : kThreadsTc, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(threads_for<kMode>(), 1)
     k_field_tc(const __grid_constant__ Params P) {
+  constexpr bool kPro = kMode == MODE_PAIR;  // dedicated input warps (11..14)
   static_assert(!kF8 || kMode == MODE_PAIR || kMode == MODE_HEADS || kMode == MODE_PROBE, "the f8 operand scheme is inference-only");
   constexpr bool kPair = kMode == MODE_PAIR || kMode == MODE_PAIR_TRAIN;
   constexpr bool kTrainP = kMode == MODE_PAIR_TRAIN;
@@ -186,7 +206,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(bar(kBarWFull + i), 1); mbar_init(bar(kBarWEmpty + i), kCluster ? 2 : 1); }
     // heads training: a K-block is free for the next tile's first operand once the last layer's MMAs AND the stash copy are done
-    for (int i = 0; i < 4; ++i) { mbar_init(bar(kBarARdy + i), 8); mbar_init(bar(kBarA0Rdy + i), 1); mbar_init(bar(kBarAFree + i), kTrainH ? 2 : 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(bar(kBarARdy + i), 8); mbar_init(bar(kBarA0Rdy + i), kPro ? 4 : 1); mbar_init(bar(kBarAFree + i), kTrainH ? 2 : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar(kBarAccRdy + i), 1); mbar_init(bar(kBarAccFree + i), 8); }
     for (int i = 0; i < 4; ++i) mbar_init(bar(kBarStash + i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -205,6 +225,63 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
   const uint32_t cta_rank = kCluster ? cluster_ctarank() : 0u;
   const int first_cta = kCluster ? (int)(blockIdx.x & ~1u) : (int)blockIdx.x;
   const int n_pass = n_tiles > first_cta ? (n_tiles - first_cta + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  // ---- aggregation epilogue, sum phase: task = (sample of the tile, 8 of the pass's 128 columns); shared by the epilogue threads
+  //      and, in inference pair mode, the input warps (u = thread number among the n_threads that take tasks) ----
+  auto agg_sum_tasks = [&](int u, int n_threads, int pass, int buf) {
+    const float* stage = reinterpret_cast<const float*>(sA + 4 * kTileBytesA);
+    const uint8_t* samp_row = misc + kOffSampRow + buf * 128;
+    const uint8_t* samp_cnt = misc + kOffSampCnt + buf * 128;
+    const int* info = reinterpret_cast<const int*>(misc + kOffInfo) + buf * 4;
+    const int s_begin = info[0], n_samp = info[1];
+    for (int task = u; task < n_samp * 16; task += n_threads) {
+      const int sl = task >> 4, c8 = task & 15;
+      const int r0 = samp_row[sl], cnt = samp_cnt[sl];
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      // a sample has 1..8 rows: two groups of four predicated, independent loads (same summation order as a plain loop)
+#pragma unroll
+      for (int j0 = 0; j0 < kK; j0 += 4) {
+        if (j0 < cnt) {
+          float4 t0[4], t1[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int r = min(r0 + j0 + j, 127);
+            const float* rp = stage + r * 128 + ((c8 ^ (r & 7)) << 2);
+            t0[j] = *reinterpret_cast<const float4*>(rp);
+            t1[j] = *reinterpret_cast<const float4*>(rp + 64);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j0 + j < cnt) {
+              acc[0] += t0[j].x; acc[1] += t0[j].y; acc[2] += t0[j].z; acc[3] += t0[j].w;
+              acc[4] += t1[j].x; acc[5] += t1[j].y; acc[6] += t1[j].z; acc[7] += t1[j].w;
+            }
+          }
+        }
+      }
+      const long long s = (long long)s_begin + sl;
+      const int col = 128 * pass + 8 * c8;
+      uint8_t* kbp = P.img + (size_t)(s >> 7) * kImgTileBytes + (size_t)(col >> 6) * (2 * kTileBytesA);
+      if (!kF8) {
+        uint4 hi, lo;
+        split8(acc, hi, lo);
+        uint8_t* p = kbp + swz((int)(s & 127), (col & 63) >> 3);
+        *reinterpret_cast<uint4*>(p) = hi;
+        *reinterpret_cast<uint4*>(p + kTileBytesA) = lo;
+      } else {  // acc already carries kF8ActScale (the layer-3 epilogue scale and bias include it)
+        uint4 hi;
+        uint2 lo8, hi8;
+        split8_f8(acc, hi, lo8, hi8);
+        *reinterpret_cast<uint4*>(kbp + swz((int)(s & 127), (col & 63) >> 3)) = hi;
+        *reinterpret_cast<uint2*>(kbp + kTileBytesA + swz8_lo((int)(s & 127), (col & 63) >> 3)) = lo8;
+        *reinterpret_cast<uint2*>(kbp + kTileBytesA + swz8_hi((int)(s & 127), (col & 63) >> 3)) = hi8;
+      }
+    }
+  };
+  // barrier of the aggregation passes: the 256 epilogue threads (+ the 128 input-warp threads in inference pair mode)
+  auto agg_bar = [&]() {
+    if (kPro) asm volatile("bar.sync 3, 384;" ::: "memory"); else epi_bar_sync();
+  };
 
   if (warp == 0) {
     // ================================================= weight producer ==================================================
@@ -259,6 +336,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
       }
       const bool has_next = tile + (int)gridDim.x < n_tiles;
       for (int l = 0; l < n_layers; ++l, ++lc) {
+        if (lane == 0 && l < 4) NPCD_TL(pass, 16 + 3 * l);
         const uint32_t ab = lc & 1u;
         const uint32_t d_tmem = tmem_base + ab * 256u;
         mbar_wait(bar(kBarAccFree + ab), ((ph_af >> ab) & 1u) ^ 1u);  // every epilogue warp has drained this accumulator
@@ -268,13 +346,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
         // heads layer 2 (channel_net.0) reads the same operand (feat) as layer 1 (shape_net.0): nothing new to wait for
         const bool fresh_a = !(kHeads && l + P.layer_ofs == 2);
         for (int kb = 0; kb < nkb; ++kb) {
-          if (!kPair && l == 0) {
+          if ((!kPair || kPro) && l == 0) {  // first operand of a tile: the loader warp (heads) / the input warps (pair)
             mbar_wait(bar(kBarA0Rdy + kb), (ph_a0 >> kb) & 1u);
             ph_a0 ^= 1u << kb;
           } else if (fresh_a) {
             mbar_wait(bar(kBarARdy + kb), (ph_ar >> kb) & 1u);
             ph_ar ^= 1u << kb;
           }
+          if (lane == 0 && kb == 0 && l < 4) NPCD_TL(pass, 17 + 3 * l);  // first operand block of the layer is there
           const int ks_n = min(4, ksteps - kb * 4);
           // descriptor start-address field counts 16-byte units: +2 per 16-column K step, +1024 per 16 KB tile
           const uint64_t a_hi = desc_a0 + (uint64_t)(kb * 2 * (kTileBytesA >> 4)), a_lo = a_hi + (kTileBytesA >> 4);
@@ -320,6 +399,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
             if (l == n_layers - 1 && has_next && (!kPair || kb < 2)) umma_commit(bar(kBarAFree + kb));
             if (kb == nkb - 1) umma_commit(bar(kBarAccRdy + ab));
           }
+          if (lane == 0 && kb == nkb - 1 && l < 4) NPCD_TL(pass, 18 + 3 * l);  // last MMA of the layer issued
           __syncwarp();
           if (++st == kStages) { st = 0; ph_w ^= 1; }
         }
@@ -372,6 +452,164 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
           }
           __syncwarp();
         }
+      }
+    }
+  } else if (kPro && warp >= 11) {
+    // ============================ inference pair mode: input warps (one thread per row of the tile) ====================
+    // layer-0 input, 96 columns (see the column map at the epilogue threads' prologue below; the two code paths build the same
+    // operand): chunks of 8 columns, K-block 0 = chunks 0..7, K-block 1 = chunks 8..11.
+    const int pt = threadIdx.x - 352;  // 0..127 = tile row
+    const int row = pt, x7 = row & 7;
+    const uint32_t rowbase = (uint32_t)((row >> 3) * 1024 + x7 * 128);
+    float* wts_all = reinterpret_cast<float*>(misc + kOffWts);
+    uint8_t* row_samp_all = misc + kOffRowSamp;
+    uint8_t* samp_row_all = misc + kOffSampRow;
+    uint8_t* samp_cnt_all = misc + kOffSampCnt;
+    int* info_all = reinterpret_cast<int*>(misc + kOffInfo);
+    uint4 c_hi[8];
+    uint4 c_lo[8];  // f8 scheme: {lo8 (8 B), hi8 (8 B)} of the chunk
+    auto split_c = [&](const float (&y)[8], int c) {
+      if (!kF8) {
+        split8(y, c_hi[c], c_lo[c]);
+      } else {
+        const float ys[8] = {y[0] * kF8ActScale, y[1] * kF8ActScale, y[2] * kF8ActScale, y[3] * kF8ActScale,
+                             y[4] * kF8ActScale, y[5] * kF8ActScale, y[6] * kF8ActScale, y[7] * kF8ActScale};
+        uint2 lo8, hi8;
+        split8_f8(ys, c_hi[c], lo8, hi8);
+        c_lo[c] = make_uint4(lo8.x, lo8.y, hi8.x, hi8.y);
+      }
+    };
+    auto store_c = [&](int kb, int c, int src) {  // chunk c (8 columns) of K-block kb
+      uint8_t* t = sA + kb * 2 * kTileBytesA + rowbase;
+      *reinterpret_cast<uint4*>(t + ((c ^ x7) << 4)) = c_hi[src];
+      if (!kF8) {
+        *reinterpret_cast<uint4*>(t + kTileBytesA + ((c ^ x7) << 4)) = c_lo[src];
+      } else {
+        *reinterpret_cast<uint2*>(t + kTileBytesA + (((c >> 1) ^ x7) << 4) + (c & 1) * 8) = make_uint2(c_lo[src].x, c_lo[src].y);
+        *reinterpret_cast<uint2*>(t + kTileBytesA + ((((c >> 1) + 4) ^ x7) << 4) + (c & 1) * 8) = make_uint2(c_lo[src].z, c_lo[src].w);
+      }
+    };
+    auto publish_a0 = [&](int kb) {
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(kBarA0Rdy + kb));
+    };
+    // (sin, cos) of d * 2^i * pi for n consecutive octaves starting with frequency fr0, interleaved into v[0 .. 2n)
+    auto octaves = [&](float d, float fr0, int n, float* v) {
+      float fr = fr0;
+#pragma unroll
+      for (int i = 0; i < kFreqs; ++i) {
+        if (i < n) {
+          float sn, cs;
+          sincos_small(d * fr, sn, cs);
+          v[2 * i] = sn;
+          v[2 * i + 1] = cs;
+          fr *= 2.0f;
+        }
+      }
+    };
+    const float kPi = 3.14159274101257324f;
+    // input of tile `tile` into K-blocks 0 / 1; wait_free: the K-blocks still hold the previous tile's X_3 until layer 3's MMAs pass
+    auto prepare = [&](int tile, int buf, bool wait_free, uint32_t parity) {
+      const int s_begin = __ldg(P.tile_start + tile), s_end = __ldg(P.tile_start + tile + 1);
+      const int n_samp = s_end - s_begin;
+      const int base = __ldg(P.pair_off + s_begin);
+      uint8_t* row_samp = row_samp_all + buf * 128;
+      uint8_t* samp_row = samp_row_all + buf * 128;
+      uint8_t* samp_cnt = samp_cnt_all + buf * 128;
+      if (pt < n_samp) {
+        const int o = __ldg(P.pair_off + s_begin + pt) - base;
+        const int c = __ldg(P.pair_off + s_begin + pt + 1) - base - o;
+        samp_row[pt] = (uint8_t)o;
+        samp_cnt[pt] = (uint8_t)c;
+        for (int j = 0; j < c; ++j) row_samp[o + j] = (uint8_t)pt;
+      }
+      if (pt == 0) {
+        info_all[buf * 4 + 0] = s_begin;
+        info_all[buf * 4 + 1] = n_samp;
+        info_all[buf * 4 + 2] = __ldg(P.pair_off + s_end) - base;
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      const int n_rows = info_all[buf * 4 + 2];
+      int idx = -1;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      float px = 0.f, py = 0.f, pz = 0.f;
+      if (row < n_rows) {
+        const int sl = row_samp[row];
+        const long long s = (long long)s_begin + sl;
+        idx = __ldg(P.nbr_idx + s * kK + (row - samp_row[sl]));
+        x = __ldg(P.sample_pos + s);
+        px = __ldg(P.kp_pos + (size_t)idx * 3); py = __ldg(P.kp_pos + (size_t)idx * 3 + 1); pz = __ldg(P.kp_pos + (size_t)idx * 3 + 2);
+      }
+      const bool live = idx >= 0;
+      const float d3[3] = {x.x - px, x.y - py, x.z - pz};
+      const float nrm = sqrtf(d3[0] * d3[0] + d3[1] * d3[1] + d3[2] * d3[2]);
+      wts_all[buf * 128 + row] = live ? 1.0f / (nrm + 1e-5f) : 0.f;
+      // ---- K-block 0: [feat 0..31 | x: (sin, cos) of octaves 0..7 | d_x, (sin, cos)_x of octaves 8, 9, d_y, (sin, cos)_y of octaves 0..4]
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        float y[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (live) {
+          const float4 f0 = __ldg(reinterpret_cast<const float4*>(P.kp_feat + (size_t)idx * 32 + ch * 8));
+          const float4 f1 = __ldg(reinterpret_cast<const float4*>(P.kp_feat + (size_t)idx * 32 + ch * 8 + 4));
+          y[0] = f0.x; y[1] = f0.y; y[2] = f0.z; y[3] = f0.w; y[4] = f1.x; y[5] = f1.y; y[6] = f1.z; y[7] = f1.w;
+        }
+        split_c(y, ch);
+      }
+      {
+        float v[32];
+        octaves(d3[0], kPi, 8, v);
+        v[16] = d3[0];
+        octaves(d3[0], kPi * 256.0f, 2, v + 17);
+        v[21] = d3[1];
+        octaves(d3[1], kPi, 5, v + 22);
+        if (!live) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const float y[8] = {v[ch * 8], v[ch * 8 + 1], v[ch * 8 + 2], v[ch * 8 + 3], v[ch * 8 + 4], v[ch * 8 + 5], v[ch * 8 + 6], v[ch * 8 + 7]};
+          split_c(y, 4 + ch);
+        }
+      }
+      if (wait_free) mbar_wait(bar(kBarAFree + 0), parity);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) store_c(0, c, c);
+      publish_a0(0);
+      // ---- K-block 1: [(sin, cos)_y of octaves 5..9 | z: d, (sin, cos) x 10 | 0]
+      {
+        float v[32];
+        octaves(d3[1], kPi * 32.0f, 5, v);
+        v[10] = d3[2];
+        octaves(d3[2], kPi, kFreqs, v + 11);
+        v[31] = 0.f;
+        if (!live) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const float y[8] = {v[ch * 8], v[ch * 8 + 1], v[ch * 8 + 2], v[ch * 8 + 3], v[ch * 8 + 4], v[ch * 8 + 5], v[ch * 8 + 6], v[ch * 8 + 7]};
+          split_c(y, ch);
+        }
+      }
+      if (wait_free) mbar_wait(bar(kBarAFree + 1), parity);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) store_c(1, c, c);
+      publish_a0(1);
+    };
+    if ((int)blockIdx.x < n_tiles) prepare((int)blockIdx.x, 0, false, 0u);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int next = tile + (int)gridDim.x;
+      if (next < n_tiles) prepare(next, (int)((it + 1) & 1u), true, it & 1u);
+      // a third of the segmented-sum tasks of this tile's aggregation epilogue (two passes of 128 columns)
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        agg_bar();  // the epilogue threads have staged the pass
+        agg_sum_tasks(kEpiThreads + pt, kEpiThreads + kProThreads, pass, (int)(it & 1u));
+        agg_bar();
       }
     }
   } else if (warp == 11) {
@@ -446,9 +684,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
     };
 
     // ACT / LINEAR epilogue of layer l: four 32-column chunks (2 i + half), software-pipelined TMEM loads
+    int tl_it = 0;  // tile counter of this CTA (timeline)
     auto epilogue_store = [&](int l, float slope, float* feat_row) {
       const uint32_t ab = lc & 1u;
+      if (et == 0) NPCD_TL(tl_it, 2 * l);
       wait_acc(ab);
+      if (et == 0) NPCD_TL(tl_it, 2 * l + 1);
       const float inv = P.layers[l].inv_scale;
       const uint32_t t_acc = t_row + ab * 256u;
       uint32_t v[2][32];
@@ -617,9 +858,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
 
       // Iteration -1 primes the pipeline (stages the first tile's input); iteration `it` runs the four layer epilogues of tile
       // `cur` and, between them, stages the input of the tile after it.  One call site per helper keeps the code I-cache sized.
-      int cur = -1;
-      for (int it = -1;; ++it) {
+      // (kPro, inference: the input warps 11..14 stage the layer-0 input; no priming iteration, no prologue work here.)
+      int cur = kPro ? (int)blockIdx.x : -1;
+      if (kPro) tile_now = cur;
+      for (int it = kPro ? 0 : -1;; ++it) {
         const bool prime = it < 0;
+        if (kPro && cur >= n_tiles) break;
         const int target = prime ? (int)blockIdx.x : cur + (int)gridDim.x;  // tile whose layer-0 input is staged now
         const bool has_target = target < n_tiles;
         if (prime && !has_target) break;
@@ -627,9 +871,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
 #pragma unroll 1
         for (int l = 0; l < 3; ++l) {
           if (!prime) epilogue_store(l, 0.01f, nullptr);
-          if (l == 0 && has_target) prologue_compute(target, buf ^ 1);
+          if (!kPro && l == 0 && has_target) prologue_compute(target, buf ^ 1);
         }
-        if (has_target) {  // layer 3's MMAs release K-blocks 0 and 1 as they pass them
+        if (!kPro && has_target) {  // layer 3's MMAs release K-blocks 0 and 1 as they pass them
 #pragma unroll 1
           for (int kb = 0; kb < 2; ++kb) {
             if (!prime) mbar_wait(bar(kBarAFree + kb), (uint32_t)it & 1u);
@@ -642,8 +886,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
         //      two passes of 128 columns; the sums leave as the pre-split operand image the heads kernel bulk-copies.
         {
           const uint32_t ab = lc & 1u;
+          if (et == 0) NPCD_TL(tl_it, 6);
           wait_acc(ab);
-          epi_bar_sync();  // wts[] / row maps of this tile were written by other warps
+          if (et == 0) NPCD_TL(tl_it, 7);
+          if (!kPro) epi_bar_sync();  // wts[] / row maps of this tile were written by other warps of this group (kPro: by the input
+                                      // warps a tile ago, ordered by their A0Rdy arrive -> MMA -> accumulator-ready chain)
           const float inv = P.layers[3].inv_scale;
           const uint32_t t_acc = t_row + ab * 256u;
           const float* wts = wts_all + buf * 128;
@@ -667,67 +914,46 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMode == MODE_HEADS_
           // 16 lanes read chunks 2 c8 and 2 c8 + 1 of one row.
           float* stage = reinterpret_cast<float*>(sA + 4 * kTileBytesA);
           const uint64_t inv2 = pack2(inv, inv), slope2 = pack2(0.01f, 0.01f), wn2 = pack2(wn, wn);
-#pragma unroll 1
-          for (int pass = 0; pass < 2; ++pass) {
-#pragma unroll 1
-            for (int k = 0; k < 2; ++k) {
-              const int cl = 64 * half + 32 * k;  // column within the pass
-              const int c0 = 128 * pass + cl;
-              uint32_t v[32];
-              tmem_ld32_async(t_acc + c0, v);
-              tmem_wait(v);
-              uint32_t mbits = 0u;
+          // four 32-column chunks q (pass = q >> 1): the TMEM load of chunk q + 1 is in flight while chunk q is processed
+          uint32_t v[2][32];
+          tmem_ld32_async(t_acc + 64 * half, v[0]);
 #pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                const float4 b = *reinterpret_cast<const float4*>(&P.bias[3][c0 + g * 4]);
-                float y0, y1, y2, y3;
-                act2(v[g * 4 + 0], v[g * 4 + 1], inv2, b.x, b.y, slope2, y0, y1);
-                act2(v[g * 4 + 2], v[g * 4 + 3], inv2, b.z, b.w, slope2, y2, y3);
-                if (kTrain)
-                  mbits |= ((y0 > 0.f ? 1u : 0u) | (y1 > 0.f ? 2u : 0u) | (y2 > 0.f ? 4u : 0u) | (y3 > 0.f ? 8u : 0u)) << (g * 4);
-                float4 o;
-                unpack2(mul2(pack2(y0, y1), wn2), o.x, o.y);
-                unpack2(mul2(pack2(y2, y3), wn2), o.z, o.w);
-                const int c4 = (cl >> 2) + g;
-                const int pos = ((c4 >> 1) | ((c4 & 1) << 4)) ^ x7;
-                *reinterpret_cast<float4*>(stage + row * 128 + (pos << 2)) = o;
-              }
-              if (kTrain) P.stash_mask[3][((size_t)cur * 128 + row) * 8 + (c0 >> 5)] = mbits;
+          for (int q = 0; q < 4; ++q) {
+            const int pass = q >> 1;
+            const int cl = 64 * half + 32 * (q & 1);  // column within the pass
+            const int c0 = 128 * pass + cl;
+            tmem_wait(v[q & 1]);
+            if (q < 3) tmem_ld32_async(t_acc + 128 * ((q + 1) >> 1) + 64 * half + 32 * ((q + 1) & 1), v[(q + 1) & 1]);
+            uint32_t mbits = 0u;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 b = *reinterpret_cast<const float4*>(&P.bias[3][c0 + g * 4]);
+              const uint32_t* vv = v[q & 1];
+              float y0, y1, y2, y3;
+              act2(vv[g * 4 + 0], vv[g * 4 + 1], inv2, b.x, b.y, slope2, y0, y1);
+              act2(vv[g * 4 + 2], vv[g * 4 + 3], inv2, b.z, b.w, slope2, y2, y3);
+              if (kTrain)
+                mbits |= ((y0 > 0.f ? 1u : 0u) | (y1 > 0.f ? 2u : 0u) | (y2 > 0.f ? 4u : 0u) | (y3 > 0.f ? 8u : 0u)) << (g * 4);
+              float4 o;
+              unpack2(mul2(pack2(y0, y1), wn2), o.x, o.y);
+              unpack2(mul2(pack2(y2, y3), wn2), o.z, o.w);
+              const int c4 = (cl >> 2) + g;
+              const int pos = ((c4 >> 1) | ((c4 & 1) << 4)) ^ x7;
+              *reinterpret_cast<float4*>(stage + row * 128 + (pos << 2)) = o;
             }
-            if (pass == 1) release_acc(ab);
-            epi_bar_sync();
-            for (int task = et; task < n_samp * 16; task += kEpiThreads) {
-              const int sl = task >> 4, c8 = task & 15;
-              const int r0 = samp_row[sl], cnt = samp_cnt[sl];
-              float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-              for (int j = 0; j < cnt; ++j) {
-                const int r = r0 + j;
-                const float* rp = stage + r * 128 + ((c8 ^ (r & 7)) << 2);
-                const float4 t0 = *reinterpret_cast<const float4*>(rp);
-                const float4 t1 = *reinterpret_cast<const float4*>(rp + 64);
-                acc[0] += t0.x; acc[1] += t0.y; acc[2] += t0.z; acc[3] += t0.w;
-                acc[4] += t1.x; acc[5] += t1.y; acc[6] += t1.z; acc[7] += t1.w;
-              }
-              const long long s = (long long)s_begin + sl;
-              const int col = 128 * pass + 8 * c8;
-              uint8_t* kbp = P.img + (size_t)(s >> 7) * kImgTileBytes + (size_t)(col >> 6) * (2 * kTileBytesA);
-              if (!kF8) {
-                uint4 hi, lo;
-                split8(acc, hi, lo);
-                uint8_t* p = kbp + swz((int)(s & 127), (col & 63) >> 3);
-                *reinterpret_cast<uint4*>(p) = hi;
-                *reinterpret_cast<uint4*>(p + kTileBytesA) = lo;
-              } else {  // acc already carries kF8ActScale (the layer-3 epilogue scale and bias include it)
-                uint4 hi;
-                uint2 lo8, hi8;
-                split8_f8(acc, hi, lo8, hi8);
-                *reinterpret_cast<uint4*>(kbp + swz((int)(s & 127), (col & 63) >> 3)) = hi;
-                *reinterpret_cast<uint2*>(kbp + kTileBytesA + swz8_lo((int)(s & 127), (col & 63) >> 3)) = lo8;
-                *reinterpret_cast<uint2*>(kbp + kTileBytesA + swz8_hi((int)(s & 127), (col & 63) >> 3)) = hi8;
-              }
+            if (kTrain) P.stash_mask[3][((size_t)cur * 128 + row) * 8 + (c0 >> 5)] = mbits;
+            if (q & 1) {
+              if (pass == 1) release_acc(ab);
+              if (et == 0) NPCD_TL(tl_it, 8 + 4 * pass);
+              agg_bar();
+              if (et == 0) NPCD_TL(tl_it, 9 + 4 * pass);
+              agg_sum_tasks(et, kPro ? kEpiThreads + kProThreads : kEpiThreads, pass, buf);
+              if (et == 0) NPCD_TL(tl_it, 10 + 4 * pass);
+              agg_bar();  // the staging area is rewritten by the next pass / the next tile's layer-0 epilogue
+              if (et == 0) NPCD_TL(tl_it, 11 + 4 * pass);
             }
-            epi_bar_sync();  // the staging area is rewritten by the next pass / the next tile's layer-0 epilogue
           }
+          ++tl_it;
           ++lc;
         }
         if (!has_target) break;
@@ -1179,8 +1405,13 @@ void fill_layer(tc::Params& P, int i, const npcd_tc_layer& src, int epi, bool f8
   }
 }
 
+long long* g_timeline = nullptr;
+
 template <int kMode, bool kF8 = false>
-int launch_tc(const tc::Params& P, long long tiles, int num_sms, cudaStream_t st, const char* what) {
+int launch_tc(const tc::Params& P_in, long long tiles, int num_sms, cudaStream_t st, const char* what) {
+  static thread_local tc::Params P;
+  P = P_in;
+  P.timeline = kMode == tc::MODE_PAIR ? g_timeline : nullptr;
   cudaError_t e = cudaFuncSetAttribute(tc::k_field_tc<kMode, kF8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal);
   if (e != cudaSuccess) {
     set_error("%s: cannot opt in to %d bytes of shared memory: %s", what, tc::kSmemTotal, cudaGetErrorString(e));
@@ -1189,7 +1420,7 @@ int launch_tc(const tc::Params& P, long long tiles, int num_sms, cudaStream_t st
   if (num_sms <= 0) num_sms = 148;
   unsigned grid = (unsigned)(tiles < num_sms ? (tiles > 0 ? tiles : 1) : num_sms);
   if (tc::kCluster) grid = (grid + 1u) & ~1u;  // whole 2-CTA clusters
-  tc::k_field_tc<kMode, kF8><<<grid, kMode == tc::MODE_HEADS_TRAIN ? tc::kThreadsTcTrainHeads : tc::kThreadsTc, tc::kSmemTotal, st>>>(P);
+  tc::k_field_tc<kMode, kF8><<<grid, tc::threads_for<kMode>(), tc::kSmemTotal, st>>>(P);
   return check_launch(what);
 }
 }  // namespace
@@ -1269,6 +1500,12 @@ int heads_stage(const npcd_mlp_tc_weights* W, uint8_t* img, float* rgbs, float* 
   return launch_tc<kMode, kF8>(P, (capacity + 127) / 128, num_sms, st, "npcd_field_tc_fwd(heads)");
 }
 }  // namespace
+
+// development aid: the inference pair kernel's CTA 0 records clock64() at its phase boundaries into buf [64 tiles][32] (null: off)
+extern "C" int npcd_debug_set_timeline(void* buf) {
+  g_timeline = (long long*)buf;
+  return 0;
+}
 
 extern "C" int npcd_field_tc_workspace_bytes(long long capacity, size_t* bytes) {
   NPCD_CHECK_ARG(bytes && capacity >= 0 && capacity < (1ll << 27), "bad arguments (capacity must be < 2^27 samples per launch)");
