@@ -19,7 +19,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr", "--extended-lambda",
     "-I", INCLUDE, "-I", CSRC,
-]
+] + os.environ.get("NPCD_NVCC_DEFINES", "").split()  # development aid: extra -D switches (part of the build digest)
 
 
 def _nvcc() -> str:

@@ -71,6 +71,7 @@ constexpr int kOffStashBars = 2048;  // 4 mbarriers: K-block kb of the A operand
 // barrier indices
 constexpr int kBarWFull = 0, kBarWEmpty = 3, kBarARdy = 6, kBarA0Rdy = 10, kBarAFree = 14, kBarAccRdy = 18, kBarAccFree = 20;
 constexpr int kBarStash = kOffStashBars / 8;
+constexpr int kBarARdy2 = kBarStash + 4;  // second half (columns 16-31 / 48-63) of K-block 0 published (inference: split first block)
 
 struct Layer {
   const uint8_t* w;  // packed tiles: for each K-block: hi tile (32 KB) then lo tile (32 KB)
@@ -126,7 +127,8 @@ constexpr int kTimelineTiles = 64;
 // One chunk (32 accumulator columns starting at c0) of an ACT / LINEAR epilogue: y = [lrelu](acc * inv + b) -> fp16 hi/lo ->
 // K-block (c0 >> 6) of the A operand, 16-byte chunks (c0 & 63) / 8 .. +3.
 // slope = 0.01 (LeakyReLU) or 1 (linear layer: max(y, y) = y).
-template <bool kF8 = false>
+// kG0 .. kG1: the 8-column groups of the chunk to process (0 .. 4 = all; the first K-block of a layer is published in two halves)
+template <bool kF8 = false, int kG0 = 0, int kG1 = 4>
 __device__ __forceinline__ void epi_chunk_store(const Params& P, int l, float inv, float slope, const uint32_t (&v)[32], int c0,
                                                 uint8_t* sA, uint32_t rowbase, int x7, float* feat_row, uint32_t* mask_out = nullptr) {
   uint32_t mbits = 0u;
@@ -134,7 +136,7 @@ __device__ __forceinline__ void epi_chunk_store(const Params& P, int l, float in
   const int c16_0 = (c0 & 63) >> 3;
   const uint64_t inv2 = pack2(inv, inv), slope2 = pack2(slope, slope);
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
+  for (int g = kG0; g < kG1; ++g) {
     const float4 b0 = *reinterpret_cast<const float4*>(&P.bias[l][c0 + g * 8]);
     const float4 b1 = *reinterpret_cast<const float4*>(&P.bias[l][c0 + g * 8 + 4]);
     float y[8];
@@ -163,8 +165,8 @@ __device__ __forceinline__ void epi_chunk_store(const Params& P, int l, float in
       split8_f8(y, hi, lo8, hi8);
       *reinterpret_cast<uint4*>(p) = hi;
       const int c8 = c16_0 + g;  // 8-column group within the K-block
-      uint8_t* q = kb_base + kTileBytesA + ((((c8 >> 1)) ^ x7) << 4) + (c8 & 1) * 8;
-      uint8_t* r = kb_base + kTileBytesA + ((((c8 >> 1) + 4) ^ x7) << 4) + (c8 & 1) * 8;
+      uint8_t* q = kb_base + kTileBytesA + ((f8_chunk(c8) ^ x7) << 4) + (c8 & 1) * 8;
+      uint8_t* r = kb_base + kTileBytesA + (((f8_chunk(c8) + 4) ^ x7) << 4) + (c8 & 1) * 8;
       *reinterpret_cast<uint2*>(q) = lo8;
       *reinterpret_cast<uint2*>(r) = hi8;
     }
@@ -177,13 +179,24 @@ __device__ __forceinline__ void epi_chunk_store(const Params& P, int l, float in
 // cluster walk the same weight schedule, so CTA 0's producer issues ONE multicast bulk copy per ring stage that lands in both shared
 // memories (and completes both full-barriers); a stage is reused once BOTH CTAs' MMAs have drained it (commit multicast to both
 // empty-barriers, count 2).  A CTA that has one tile fewer than its partner keeps consuming the ring without issuing MMAs.
-constexpr bool kCluster = true;
+#ifndef NPCD_TC_CLUSTER
+#define NPCD_TC_CLUSTER 1
+#endif
+constexpr bool kCluster = NPCD_TC_CLUSTER != 0;
+#if NPCD_TC_CLUSTER
+#define NPCD_TC_CLUSTER_DIMS __cluster_dims__(2, 1, 1)
+#else
+#define NPCD_TC_CLUSTER_DIMS
+#endif
 
 // ------------------------------------------------------------------------------------------------------------- kernel ----
 template <int kMode, bool kF8 = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(threads_for<kMode>(), 1)
+__global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
     k_field_tc(const __grid_constant__ Params P) {
   constexpr bool kPro = kMode == MODE_PAIR;  // dedicated input warps (11..14)
+  // inference: the epilogues publish K-block 0 of their output in two halves, so the next layer's MMAs start after 16 values per
+  // thread instead of 32 (timeline of CTA 0: the first-block latency was ~1450 of the ~7100 cycles a layer takes)
+  constexpr bool kSplit0 = kMode == MODE_PAIR || kMode == MODE_HEADS;
   static_assert(!kF8 || kMode == MODE_PAIR || kMode == MODE_HEADS || kMode == MODE_PROBE, "the f8 operand scheme is inference-only");
   constexpr bool kPair = kMode == MODE_PAIR || kMode == MODE_PAIR_TRAIN;
   constexpr bool kTrainP = kMode == MODE_PAIR_TRAIN;
@@ -209,6 +222,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(threads_for<kMode>()
     for (int i = 0; i < 4; ++i) { mbar_init(bar(kBarARdy + i), 8); mbar_init(bar(kBarA0Rdy + i), kPro ? 4 : 1); mbar_init(bar(kBarAFree + i), kTrainH ? 2 : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar(kBarAccRdy + i), 1); mbar_init(bar(kBarAccFree + i), 8); }
     for (int i = 0; i < 4; ++i) mbar_init(bar(kBarStash + i), 1);
+    mbar_init(bar(kBarARdy2), 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
@@ -313,6 +327,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(threads_for<kMode>()
     int st = 0;
     uint32_t ph_w = 0;
     uint32_t ph_ar = 0, ph_a0 = 0;  // one parity bit per K-block
+    uint32_t ph_ar2 = 0;            // second half of K-block 0 (kSplit0)
     uint32_t ph_af = 0;             // acc_free parity bits (bit b = accumulator b)
     uint32_t lc = 0;                // running layer counter: layer lc accumulates into TMEM columns (lc & 1) * 256
     const uint64_t desc_a0 = make_desc(smem_u32(sA));
@@ -357,6 +372,56 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(threads_for<kMode>()
           const int ks_n = min(4, ksteps - kb * 4);
           // descriptor start-address field counts 16-byte units: +2 per 16-column K step, +1024 per 16 KB tile
           const uint64_t a_hi = desc_a0 + (uint64_t)(kb * 2 * (kTileBytesA >> 4)), a_lo = a_hi + (kTileBytesA >> 4);
+          if (kSplit0 && kb == 0 && fresh_a && l > 0) {
+            // K-block 0 of an epilogue-produced operand arrives in two halves: columns {0-15, 32-47} (K16 steps 0, 2 of the fp16
+            // tile; the first K32 step of either half of the 8-bit tile), then {16-31, 48-63} (steps 1, 3; the second K32 steps).
+            // Both weight stages of the block are held until the second half has been issued.
+            const int st2 = st + 1 == kStages ? 0 : st + 1;
+            const uint32_t ph_w2 = st + 1 == kStages ? ph_w ^ 1u : ph_w;
+            mbar_wait(bar(kBarWFull + st), ph_w);
+            mbar_wait(bar(kBarWFull + st2), ph_w2);
+            tc_fence_after();
+            const uint64_t b = desc_w0 + (uint64_t)(st * (kTileBytesW >> 4)), b2 = desc_w0 + (uint64_t)(st2 * (kTileBytesW >> 4));
+            if (elect_one()) {
+              umma_f16(d_tmem, a_hi, b, kIdesc, 0u);
+              umma_f16(d_tmem, a_hi + 4, b + 4, kIdesc, 1u);
+              if (!kF8) {
+                umma_f16(d_tmem, a_lo, b, kIdesc, 1u);
+                umma_f16(d_tmem, a_lo + 4, b + 4, kIdesc, 1u);
+                umma_f16(d_tmem, a_hi, b2, kIdesc, 1u);
+                umma_f16(d_tmem, a_hi + 4, b2 + 4, kIdesc, 1u);
+              } else {
+                umma_f8(d_tmem, a_lo, b2, kIdesc, 1u);
+                umma_f8(d_tmem, a_lo + 4, b2 + 4, kIdesc, 1u);
+              }
+            }
+            __syncwarp();
+            mbar_wait(bar(kBarARdy2), ph_ar2);
+            ph_ar2 ^= 1u;
+            tc_fence_after();
+            if (elect_one()) {
+              umma_f16(d_tmem, a_hi + 2, b + 2, kIdesc, 1u);
+              umma_f16(d_tmem, a_hi + 6, b + 6, kIdesc, 1u);
+              if (!kF8) {
+                umma_f16(d_tmem, a_lo + 2, b + 2, kIdesc, 1u);
+                umma_f16(d_tmem, a_lo + 6, b + 6, kIdesc, 1u);
+              }
+              if (kCluster) umma_commit_mc(bar(kBarWEmpty + st), 0x3); else umma_commit(bar(kBarWEmpty + st));
+              if (!kF8) {
+                umma_f16(d_tmem, a_hi + 2, b2 + 2, kIdesc, 1u);
+                umma_f16(d_tmem, a_hi + 6, b2 + 6, kIdesc, 1u);
+              } else {
+                umma_f8(d_tmem, a_lo + 2, b2 + 2, kIdesc, 1u);
+                umma_f8(d_tmem, a_lo + 6, b2 + 6, kIdesc, 1u);
+              }
+              if (kCluster) umma_commit_mc(bar(kBarWEmpty + st2), 0x3); else umma_commit(bar(kBarWEmpty + st2));
+              if (l == n_layers - 1 && has_next && (!kPair || kb < 2)) umma_commit(bar(kBarAFree + kb));
+            }
+            __syncwarp();
+            for (int q = 0; q < 2; ++q)
+              if (++st == kStages) { st = 0; ph_w ^= 1; }
+            continue;
+          }
           // stage "hi": A_hi*W_hi + A_lo*W_hi
           mbar_wait(bar(kBarWFull + st), ph_w);
           tc_fence_after();
@@ -485,8 +550,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(threads_for<kMode>()
       if (!kF8) {
         *reinterpret_cast<uint4*>(t + kTileBytesA + ((c ^ x7) << 4)) = c_lo[src];
       } else {
-        *reinterpret_cast<uint2*>(t + kTileBytesA + (((c >> 1) ^ x7) << 4) + (c & 1) * 8) = make_uint2(c_lo[src].x, c_lo[src].y);
-        *reinterpret_cast<uint2*>(t + kTileBytesA + ((((c >> 1) + 4) ^ x7) << 4) + (c & 1) * 8) = make_uint2(c_lo[src].z, c_lo[src].w);
+        *reinterpret_cast<uint2*>(t + kTileBytesA + ((f8_chunk(c, kb == 0) ^ x7) << 4) + (c & 1) * 8) = make_uint2(c_lo[src].x, c_lo[src].y);
+        *reinterpret_cast<uint2*>(t + kTileBytesA + (((f8_chunk(c, kb == 0) + 4) ^ x7) << 4) + (c & 1) * 8) = make_uint2(c_lo[src].z, c_lo[src].w);
       }
     };
     auto publish_a0 = [&](int kb) {
@@ -702,9 +767,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(threads_for<kMode>()
         uint32_t* mptr = nullptr;
         if (kTrainP) mptr = P.stash_mask[l] + ((size_t)tile_now * 128 + row) * 8 + (2 * i + half);
         if (kTrainH && l >= 2) mptr = P.hstash_mask[l - 1] + ((size_t)tile_now * 128 + row) * 8 + (2 * i + half);
-        epi_chunk_store<kF8>(P, l, inv, slope, v[i & 1], (2 * i + half) * 32, sA, rowbase, x7, feat_row, mptr);
-        if (i == 3) release_acc(ab);
-        publish(kBarARdy + i);
+        if (kSplit0 && i == 0) {
+          epi_chunk_store<kF8, 0, 2>(P, l, inv, slope, v[0], half * 32, sA, rowbase, x7, feat_row, nullptr);
+          publish(kBarARdy + 0);
+          epi_chunk_store<kF8, 2, 4>(P, l, inv, slope, v[0], half * 32, sA, rowbase, x7, feat_row, nullptr);
+          publish(kBarARdy2);
+        } else {
+          epi_chunk_store<kF8>(P, l, inv, slope, v[i & 1], (2 * i + half) * 32, sA, rowbase, x7, feat_row, mptr);
+          if (i == 3) release_acc(ab);
+          publish(kBarARdy + i);
+        }
         if (kTrain) sd_pending |= 1u << i;
         if (i < 3) tmem_wait(v[(i + 1) & 1]);
       }
@@ -737,8 +809,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(threads_for<kMode>()
         if (!kF8) {
           *reinterpret_cast<uint4*>(t + kTileBytesA + ((c ^ x7) << 4)) = pre_lo[src];
         } else {
-          *reinterpret_cast<uint2*>(t + kTileBytesA + (((c >> 1) ^ x7) << 4) + (c & 1) * 8) = make_uint2(pre_lo[src].x, pre_lo[src].y);
-          *reinterpret_cast<uint2*>(t + kTileBytesA + ((((c >> 1) + 4) ^ x7) << 4) + (c & 1) * 8) = make_uint2(pre_lo[src].z, pre_lo[src].w);
+          *reinterpret_cast<uint2*>(t + kTileBytesA + ((f8_chunk(c, kb == 0) ^ x7) << 4) + (c & 1) * 8) = make_uint2(pre_lo[src].x, pre_lo[src].y);
+          *reinterpret_cast<uint2*>(t + kTileBytesA + (((f8_chunk(c, kb == 0) + 4) ^ x7) << 4) + (c & 1) * 8) = make_uint2(pre_lo[src].z, pre_lo[src].w);
         }
       };
 
@@ -1090,7 +1162,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(threads_for<kMode>()
 // MMA descriptors expect), multiplied by `scale` (a power of two).  perm[k'] = source column of packed column k' (or -1 = 0).
 // format 0: fp16 hi tile + fp16 lo tile; format 1 (f16 + e4m3 x 2 scheme, tc_ptx.cuh): fp16 tile of v * 2^13 + one 8-bit tile whose
 // row n is [Whi8 = e4m3(v * 2^5) of the 64 columns | Wlo8 = e4m3((v * 2^13 - W16) * 2^4) of the 64 columns]
-__device__ __forceinline__ void pack_weight_element(uint8_t* tile, int n, int kk, float v, int format) {
+__device__ __forceinline__ void pack_weight_element(uint8_t* tile, int n, int kk, float v, int format, bool full_block) {
   const size_t off = (size_t)(n >> 3) * 1024 + (n & 7) * 128 + (((kk >> 3) ^ (n & 7)) << 4) + (kk & 7) * 2;
   if (format == 0) {
     const __half hi = __float2half_rn(v);
@@ -1104,8 +1176,8 @@ __device__ __forceinline__ void pack_weight_element(uint8_t* tile, int n, int kk
     const uint32_t w8 = cvt_e4m3x2_f32(v * 32.0f, (vs - __half2float(hi)) * 16.0f);  // byte 0 = Whi8, byte 1 = Wlo8
     const int c8 = kk >> 3;
     uint8_t* t8 = tile + kTileBytesW;
-    t8[(size_t)(n >> 3) * 1024 + (n & 7) * 128 + (((c8 >> 1) ^ (n & 7)) << 4) + (c8 & 1) * 8 + (kk & 7)] = (uint8_t)(w8 & 0xffu);
-    t8[(size_t)(n >> 3) * 1024 + (n & 7) * 128 + ((((c8 >> 1) + 4) ^ (n & 7)) << 4) + (c8 & 1) * 8 + (kk & 7)] = (uint8_t)(w8 >> 8);
+    t8[swz8_lo(n, c8, full_block) + (kk & 7)] = (uint8_t)(w8 & 0xffu);
+    t8[swz8_hi(n, c8, full_block) + (kk & 7)] = (uint8_t)(w8 >> 8);
   }
 }
 
@@ -1116,7 +1188,7 @@ __global__ void k_pack_weights(const float* __restrict__ w, int k_in, const int*
   const int n = idx / k_pad, kp = idx % k_pad;
   const int src = perm ? perm[kp] : (kp < k_in ? kp : -1);
   const float v = src >= 0 ? w[(size_t)n * k_in + src] * scale : 0.f;
-  pack_weight_element(out + (size_t)(kp >> 6) * 2 * kTileBytesW, n, kp & 63, v, format);
+  pack_weight_element(out + (size_t)(kp >> 6) * 2 * kTileBytesW, n, kp & 63, v, format, (kp | 63) < k_pad);
 }
 
 // Batched variant: every weight matrix of a training step (10 forward layers, 4 + 6 transposed dgrad operands) in ONE launch;
@@ -1132,7 +1204,7 @@ __global__ void __launch_bounds__(256) k_pack_weights_batched(const __grid_const
   const int src = job.perm ? job.perm[kp] : (kp < job.k_in ? kp : -1);
   float v = 0.f;
   if (src >= 0 && n < job.n_rows) v = (job.transpose ? job.w[(size_t)src * job.ld + n] : job.w[(size_t)n * job.ld + src]) * job.scale;
-  pack_weight_element((uint8_t*)job.out + (size_t)(kp >> 6) * 2 * kTileBytesW, n, kp & 63, v, job.format);
+  pack_weight_element((uint8_t*)job.out + (size_t)(kp >> 6) * 2 * kTileBytesW, n, kp & 63, v, job.format, (kp | 63) < job.k_pad);
 }
 
 // fp32 rows [n,256] <-> the pre-split operand image (per 128-row tile: 4 K-blocks x (hi 16 KB, lo 16 KB), SWIZZLE_128B)

@@ -272,13 +272,24 @@ __device__ __forceinline__ void split8_f8(const float (&y)[8], uint4& hi, uint2&
   lo8 = make_uint2(l[0] | (l[1] << 16), l[2] | (l[3] << 16));
   hi8 = make_uint2(g[0] | (g[1] << 16), g[2] | (g[3] << 16));
 }
-// byte offsets inside the 8-bit tile of a K-block (128 rows x 128 B, SWIZZLE_128B): lo8 of the 8 columns [8 c8, 8 c8 + 8) of `row`
-// (c8 = 0..7); the matching hi8 bytes sit 64 B further along the (unswizzled) row, i.e. at chunk (c8 >> 1) + 4
-__host__ __device__ __forceinline__ uint32_t swz8_lo(int row, int c8) {
-  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (((c8 >> 1) ^ (row & 7)) << 4) + (c8 & 1) * 8);
+// 16-byte chunk (within a 64-byte half of an 8-bit tile row) that holds the 8 columns [8 c8, 8 c8 + 8), c8 = 0..7.  The two middle
+// 16-column groups are swapped -- chunks = columns {0-15, 32-47, 16-31, 48-63} -- so that the FIRST K = 32 step of a half covers the
+// first 16 columns of BOTH epilogue threads of a row (they own columns 0-31 and 32-63 of a K-block): the next layer's MMAs can
+// start on K-block 0 when every thread has produced 16 values instead of 32.  Activations and weights use the same map, so the
+// dot products are unchanged.
+// (A K-block that holds fewer than 64 columns -- the second block of the 96-column layer-0 input -- keeps the identity map,
+// `full` = false, so that its 32 columns still sit in the first K = 32 step.)
+__host__ __device__ __forceinline__ int f8_chunk(int c8, bool full = true) {
+  const int g = c8 >> 1;
+  return full ? (((g & 1) << 1) | (g >> 1)) : g;
 }
-__host__ __device__ __forceinline__ uint32_t swz8_hi(int row, int c8) {
-  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((c8 >> 1) + 4) ^ (row & 7)) << 4) + (c8 & 1) * 8);
+// byte offsets inside the 8-bit tile of a K-block (128 rows x 128 B, SWIZZLE_128B): lo8 of the 8 columns [8 c8, 8 c8 + 8) of `row`;
+// the matching hi8 bytes sit in the second 64-byte half of the (unswizzled) row, i.e. at chunk f8_chunk(c8) + 4
+__host__ __device__ __forceinline__ uint32_t swz8_lo(int row, int c8, bool full = true) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((f8_chunk(c8, full) ^ (row & 7)) << 4) + (c8 & 1) * 8);
+}
+__host__ __device__ __forceinline__ uint32_t swz8_hi(int row, int c8, bool full = true) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (((f8_chunk(c8, full) + 4) ^ (row & 7)) << 4) + (c8 & 1) * 8);
 }
 
 }  // namespace tc

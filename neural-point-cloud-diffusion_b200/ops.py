@@ -52,6 +52,14 @@ def _stream():
 # Grow-only pool for the large per-step training buffers (stash ~8 KB per pair, workspace ~1 KB per sample): their sizes follow the
 # data-dependent sample count, and re-allocating a slightly larger block every step would send the caching allocator to cudaMalloc.
 _POOL = {}
+POOL_HEADROOM = 3.0
+POOL_MAX_BYTES = 24 << 30
+
+
+def release_pools():
+    """Drops every pooled training buffer (stash / workspace / weight-gradient scratch): call between training and inference when the
+    memory matters.  Buffers still referenced by a live autograd graph stay alive until that graph is freed."""
+    _POOL.clear()
 
 
 def _pool_acquire(tag: str, nbytes: int, dev):
@@ -61,8 +69,9 @@ def _pool_acquire(tag: str, nbytes: int, dev):
             return free.pop(i)
     free.clear()  # every pooled block is too small: drop them, allocate with headroom
     # the kept-sample count of a training step has a fat tail (110 k .. 236 k measured on configs[2], it follows how many of the 112
-    # random pixels land on the object); 2x headroom makes a regrowth (a cudaMalloc of ~10 GB: 100-190 ms measured) a rare event
-    return torch.empty(int(nbytes * 2.0) + 4096, dtype=torch.uint8, device=dev)
+    # random pixels land on the object); generous headroom makes a regrowth (a cudaMalloc of several GB: 40-190 ms measured) a rare
+    # event -- POOL_HEADROOM x the first request, capped at POOL_MAX_BYTES per block
+    return torch.empty(min(int(nbytes * POOL_HEADROOM), max(int(nbytes * 1.25), POOL_MAX_BYTES)) + 4096, dtype=torch.uint8, device=dev)
 
 
 def _pool_release(tag: str, buf):
