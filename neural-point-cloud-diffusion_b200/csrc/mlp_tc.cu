@@ -123,6 +123,10 @@ constexpr int kTimelineTiles = 64;
   do {                                                                                                        \
     if (P.timeline && blockIdx.x == 0 && (it) < kTimelineTiles) P.timeline[(it) * 32 + (e)] = clock64();      \
   } while (0)
+#define NPCD_TLV(it, e, val)                                                                                  \
+  do {                                                                                                        \
+    if (P.timeline && blockIdx.x == 0 && (it) < kTimelineTiles) P.timeline[(it) * 32 + (e)] = (val);          \
+  } while (0)
 
 // One chunk (32 accumulator columns starting at c0) of an ACT / LINEAR epilogue: y = [lrelu](acc * inv + b) -> fp16 hi/lo ->
 // K-block (c0 >> 6) of the A operand, 16-byte chunks (c0 & 63) / 8 .. +3.
@@ -350,11 +354,21 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
         continue;
       }
       const bool has_next = tile + (int)gridDim.x < n_tiles;
+      long long tw_w = 0, tw_a = 0, tw_f = 0;  // timeline: cycles this tile's issue loop waited for weights / operands / accumulators
+      auto timed_wait = [&](uint32_t b, uint32_t par, long long& acc) {
+        if (P.timeline) {
+          const long long t0 = clock64();
+          mbar_wait(b, par);
+          acc += clock64() - t0;
+        } else {
+          mbar_wait(b, par);
+        }
+      };
       for (int l = 0; l < n_layers; ++l, ++lc) {
         if (lane == 0 && l < 4) NPCD_TL(pass, 16 + 3 * l);
         const uint32_t ab = lc & 1u;
         const uint32_t d_tmem = tmem_base + ab * 256u;
-        mbar_wait(bar(kBarAccFree + ab), ((ph_af >> ab) & 1u) ^ 1u);  // every epilogue warp has drained this accumulator
+        timed_wait(bar(kBarAccFree + ab), ((ph_af >> ab) & 1u) ^ 1u, tw_f);  // every epilogue warp has drained this accumulator
         ph_af ^= 1u << ab;
         const int ksteps = P.layers[l].ksteps;
         const int nkb = (ksteps + 3) >> 2;
@@ -362,10 +376,10 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
         const bool fresh_a = !(kHeads && l + P.layer_ofs == 2);
         for (int kb = 0; kb < nkb; ++kb) {
           if ((!kPair || kPro) && l == 0) {  // first operand of a tile: the loader warp (heads) / the input warps (pair)
-            mbar_wait(bar(kBarA0Rdy + kb), (ph_a0 >> kb) & 1u);
+            timed_wait(bar(kBarA0Rdy + kb), (ph_a0 >> kb) & 1u, tw_a);
             ph_a0 ^= 1u << kb;
           } else if (fresh_a) {
-            mbar_wait(bar(kBarARdy + kb), (ph_ar >> kb) & 1u);
+            timed_wait(bar(kBarARdy + kb), (ph_ar >> kb) & 1u, tw_a);
             ph_ar ^= 1u << kb;
           }
           if (lane == 0 && kb == 0 && l < 4) NPCD_TL(pass, 17 + 3 * l);  // first operand block of the layer is there
@@ -378,8 +392,8 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
             // Both weight stages of the block are held until the second half has been issued.
             const int st2 = st + 1 == kStages ? 0 : st + 1;
             const uint32_t ph_w2 = st + 1 == kStages ? ph_w ^ 1u : ph_w;
-            mbar_wait(bar(kBarWFull + st), ph_w);
-            mbar_wait(bar(kBarWFull + st2), ph_w2);
+            timed_wait(bar(kBarWFull + st), ph_w, tw_w);
+            timed_wait(bar(kBarWFull + st2), ph_w2, tw_w);
             tc_fence_after();
             const uint64_t b = desc_w0 + (uint64_t)(st * (kTileBytesW >> 4)), b2 = desc_w0 + (uint64_t)(st2 * (kTileBytesW >> 4));
             if (elect_one()) {
@@ -396,7 +410,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
               }
             }
             __syncwarp();
-            mbar_wait(bar(kBarARdy2), ph_ar2);
+            timed_wait(bar(kBarARdy2), ph_ar2, tw_a);
             ph_ar2 ^= 1u;
             tc_fence_after();
             if (elect_one()) {
@@ -423,7 +437,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
             continue;
           }
           // stage "hi": A_hi*W_hi + A_lo*W_hi
-          mbar_wait(bar(kBarWFull + st), ph_w);
+          timed_wait(bar(kBarWFull + st), ph_w, tw_w);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t b = desc_w0 + (uint64_t)(st * (kTileBytesW >> 4));
@@ -440,7 +454,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
           __syncwarp();
           if (++st == kStages) { st = 0; ph_w ^= 1; }
           // stage "lo": A_hi*W_lo
-          mbar_wait(bar(kBarWFull + st), ph_w);
+          timed_wait(bar(kBarWFull + st), ph_w, tw_w);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t b = desc_w0 + (uint64_t)(st * (kTileBytesW >> 4));
@@ -469,6 +483,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
           if (++st == kStages) { st = 0; ph_w ^= 1; }
         }
       }
+      if (lane == 0) { NPCD_TLV(pass, 28, tw_w); NPCD_TLV(pass, 29, tw_a); NPCD_TLV(pass, 30, tw_f); }
     }
   } else if (warp == 10) {
     // ======================================== heads / probe: first-operand loader =======================================

@@ -56,9 +56,25 @@ class MLP(Module):
                 "measured within the 1e-4 parity bar, DESIGN.md section 5)")
 
     # ---- weights packed for the kernels, re-packed whenever a parameter changes (optimizer step, load_state_dict) ----
+    def invalidate_packed_weights(self):
+        """Forces a re-pack on the next evaluation.  The cache key is (storage address, autograd version counter) per parameter;
+        writes through ``param.data`` (EMA-style ``param.data.copy_``, manual weight surgery) do not bump the version counter, so
+        call this after them -- or set ``check_weights = "fingerprint"`` to add max|w| per tensor (one small multi-tensor launch and
+        a device->host read per evaluation) to the key.  ``load_state_dict`` invalidates on its own."""
+        self._packed = None
+        self._packed_key = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self.invalidate_packed_weights()
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    check_weights = "version"
+
     def packed_weights(self, for_training: bool = False):
         params = list(self.parameters())
         key = (self.mlp_impl,) + tuple((p.data_ptr(), p._version) for p in params)
+        if self.check_weights == "fingerprint":
+            key += tuple(torch.stack(torch._foreach_norm([p.detach() for p in params], float("inf"))).tolist())
         if self._packed is None or key != self._packed_key:
             if self.mlp_impl == "tc":  # training: the transposed operands of the backward kernels ride in the same pack launch
                 self._packed = ops.PackedTcWeights(self.aggregator.local_field, self.shape_net, self.channel_net, self.aggregator.in_dim,

@@ -593,8 +593,23 @@ def _pair_perm_tensor(dev):
 def _error_flag(dev):
     t = _FLAG_CACHE.get(dev)
     if t is None:
-        t = _FLAG_CACHE[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+        t = _FLAG_CACHE[dev] = torch.zeros(1, dtype=torch.int64, device=dev)  # the kernels write the low 32 bits
     return t
+
+
+def read_count(count_dev):
+    """The renderer's one host sync: the kept-sample total (``ray_offset[-1:]``) -- and, in the same transfer, the device-side
+    error flag of the tensor-core kernels (they abort by setting it when their shared memory is not 1024-byte aligned; a set flag
+    means an EARLIER launch on this device returned nothing but uninitialised memory)."""
+    flag = _FLAG_CACHE.get(count_dev.device)
+    if flag is None:
+        return int(count_dev.item())
+    n, f = torch.cat([count_dev.reshape(1), flag]).tolist()
+    if f != 0:
+        flag.zero_()
+        raise RuntimeError("npcd_b200: a tensor-core field kernel aborted (dynamic shared memory not 1024-byte aligned); its outputs "
+                           "were never written")
+    return int(n)
 
 
 # inference: fold local_field.8 into the layers that consume it (tests flip this to compare both heads stages)

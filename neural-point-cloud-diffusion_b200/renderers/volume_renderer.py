@@ -179,7 +179,7 @@ class VolumeRenderer(nn.Module):
         if needs_grad or sample or return_aux:
             # single launch group with autograd support
             ray_offset = ops.scan_counts(ray_count, ray_ids)
-            S = int(ray_offset[-1].item())
+            S = ops.read_count(ray_offset[-1:])
             nbr, pos, tdep, _ = ops.knn_fill_t(rays, grid, T, radius, valid_bits, ray_offset, S, ray_ids, jitter)
             slot = ops.voxel_slots(ray_offset, ray_ids, valid_bits, cand_bits, S) if vox is not None else None
             if needs_grad:
@@ -204,7 +204,7 @@ class VolumeRenderer(nn.Module):
             S_total = 0
             if n_rays > 0:
                 ray_offset = ops.scan_counts(ray_count)
-                S_total = int(ray_offset[-1].item())
+                S_total = ops.read_count(ray_offset[-1:])
                 cap = int(self.max_samples_per_chunk)
                 if S_total <= cap:
                     chunks = [(0, n_rays, ray_offset, S_total)]
@@ -217,7 +217,7 @@ class VolumeRenderer(nn.Module):
                     if ray_offset is None:
                         ids = torch.arange(r0, r1, dtype=torch.int32, device=dev)
                         ray_offset = ops.scan_counts(ray_count, ids)
-                        S = int(ray_offset[-1].item())
+                        S = ops.read_count(ray_offset[-1:])
                     nbr, pos, tdep, _ = ops.knn_fill_t(rays, grid, T, radius, valid_bits, ray_offset, S, ids, jitter)
                     slot = ops.voxel_slots(ray_offset, ids, valid_bits, cand_bits, S) if vox is not None else None
                     rgbs, _ = self.field.evaluate(nbr, pos, kp_pos, kp_feat, ray_offset[-1:], S)

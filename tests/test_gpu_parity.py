@@ -471,6 +471,15 @@ def test_render_vs_golden_full_view(syn, model, weights, torch_cuda):
     ok = ~bad.reshape(-1)
     for k in ("mask", "depth"):
         np.testing.assert_allclose(out[k].cpu().numpy().reshape(-1)[ok], g[k].reshape(-1)[ok], atol=IMG_TOL, rtol=0)
+    # WHICH rays may differ: only those that hold a (sample, point) pair whose float64 distance lies within the error of the
+    # reference's matmul-form cdist (1.6e-5) of the radius -- there the reference's fp32 query itself is
+    # on the wrong side of r for some pairs, ours (direct differences, = the float64 answer) is not
+    o, d = orc.generate_rays(extr.reshape(-1, 4, 4), intr.reshape(-1, 3, 3), res)
+    s0, e0 = orc.get_ray_limits(o.reshape(1, 1, -1, 3), d.reshape(1, 1, -1, 3))
+    x = orc.sample_positions(o.reshape(1, 1, -1, 3), d.reshape(1, 1, -1, 3), orc.sample_depths(s0, e0))[0, 0]  # [R, 128, 3]
+    for ray in np.nonzero(bad.reshape(-1))[0]:
+        dist = np.linalg.norm(x[ray].astype(np.float64)[:, None, :] - coords[0].astype(np.float64)[None, :, :], axis=-1)
+        assert np.abs(dist - 0.08).min() < 3e-5, (int(ray), float(np.abs(dist - 0.08).min()))
     img = lambda a: np.clip(a.reshape(res, res, 3), 0, 1)
     white = np.ones((res, res, 3), np.float32)
     assert abs(psnr(img(ch), white) - psnr(img(g["channels"]), white)) < 0.01  # PSNR within 0.01 dB
@@ -498,14 +507,26 @@ def test_train_mode_forward_backward_vs_golden(syn, model, weights, torch_cuda):
         loss = ((out["channels"] - _t(torch, target)) ** 2).mean()
         assert abs(loss.item() - float(g["loss"])) < 1e-5
         loss.backward()
+        # Bars on this SMALL case (two objects x two views, a few thousand samples): a LeakyReLU pre-activation that rounds to the
+        # other side of zero flips that unit's derivative, so two fp32 implementations differ by up to ~5e-3 of the gradient NORM
+        # here (the CPU oracle vs the reference shows the same, tests/test_oracle_vs_golden.py); norm-relative + cosine per tensor,
+        # no max-scaled absolute tolerance.  The benchmark-sized step is held to 1e-3 / 0.99999 in tests/test_gpu_configs.py.
+        def close(name, got, ref, full_norm=None):
+            got, ref = got.astype(np.float64).reshape(-1), ref.astype(np.float64).reshape(-1)
+            rel = np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-300)
+            cos = float(got @ ref) / max(np.linalg.norm(got) * np.linalg.norm(ref), 1e-300)
+            assert rel <= GRAD_TOL and cos >= 0.9999, (name, rel, cos)
+            if full_norm is not None:
+                assert abs(full_norm[0] - full_norm[1]) <= GRAD_TOL * full_norm[1] + 1e-12, (name, full_norm)
+
         gf = ft.grad.cpu().numpy()
-        np.testing.assert_allclose(gf, g["grad_feats"], atol=GRAD_TOL * np.abs(g["grad_feats"]).max(), rtol=0)
+        close("grad_feats", gf, g["grad_feats"])
         own = dict(model.named_parameters())
         for k in weights:
             gr = own[k].grad.cpu().numpy()
-            refg = g["grad__" + k]
+            refg = g["grad__" + k]  # tensors above 4096 entries are stored as every 61st entry + the norm of the whole tensor
             got = gr if gr.size <= 4096 else gr.reshape(-1)[::61]
-            np.testing.assert_allclose(got.reshape(refg.shape), refg, atol=GRAD_TOL * max(np.abs(refg).max(), 1e-12), rtol=0, err_msg=k)
+            close(k, got.reshape(refg.shape), refg, (float(np.sqrt((gr.astype(np.float64) ** 2).sum())), float(g["gradnorm__" + k])))
     finally:
         model.eval()
 

@@ -40,6 +40,8 @@ base = T[sel, 0:1]
 rel = T[sel] - base
 period = np.diff(T[sel, 0]).mean()
 print(f"precision {prec}: tile period {period:.0f} cycles (CTA 0, tiles 8..59)")
+print(f"  issue loop waited per tile (median): weights {np.median(T[sel, 28]):.0f}, operands {np.median(T[sel, 29]):.0f}, "
+      f"accumulator-free {np.median(T[sel, 30]):.0f} cycles")
 order = sorted(names, key=lambda e: np.median(rel[:, e]))
 for e in order:
     print(f"  {np.median(rel[:, e]):9.0f}  {names[e]}")
