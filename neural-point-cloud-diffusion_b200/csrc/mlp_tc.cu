@@ -70,6 +70,24 @@ constexpr int kOffStashBars = 2048;  // 4 mbarriers: K-block kb of the A operand
 
 // barrier indices
 constexpr int kBarWFull = 0, kBarWEmpty = 3, kBarARdy = 6, kBarA0Rdy = 10, kBarAFree = 14, kBarAccRdy = 18, kBarAccFree = 20;
+// 2-SM mode (cta_group::2, inference pair / heads kernels): the leader CTA of a pair issues every MMA for both CTAs' tiles
+// (M = 256) and each CTA holds HALF of every weight tile, so the 96 KB weight area is a ring of SIX 16 KB half-tiles.
+// Why: the timeline of the 1-SM version showed a layer's 32 MMAs taking ~5900 cycles instead of 4096 -- shared-memory bandwidth:
+// 96 B/clk of MMA operand reads (4 KB of A + 8 KB of B per 128 cycles) + 64 B/clk of weight refill + the epilogue's stores exceed
+// the 128 B/clk an SM has.  With half of B per CTA the MMAs read 64 B/clk and the refill writes 32 B/clk.
+#ifndef NPCD_TC_CLUSTER
+#define NPCD_TC_CLUSTER 1
+#endif
+#ifndef NPCD_TC_2SM
+#define NPCD_TC_2SM 1
+#endif
+template <int kMode>
+constexpr bool two_sm() {
+  return NPCD_TC_2SM != 0 && NPCD_TC_CLUSTER != 0 && (kMode == 0 /* MODE_PAIR */ || kMode == 1 /* MODE_HEADS */);
+}
+constexpr int kStages2 = 6;
+constexpr int kOffBars2 = 2176;  // 2-SM barrier block in the misc area
+constexpr int kBar2WFull = kOffBars2 / 8, kBar2WEmpty = kBar2WFull + 6, kBar2WPeer = kBar2WFull + 12, kBar2A0Peer = kBar2WFull + 18;
 constexpr int kBarStash = kOffStashBars / 8;
 constexpr int kBarARdy2 = kBarStash + 4;  // second half (columns 16-31 / 48-63) of K-block 0 published (inference: split first block)
 
@@ -207,6 +225,11 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
   constexpr bool kTrainH = kMode == MODE_HEADS_TRAIN;
   constexpr bool kTrain = kTrainP || kTrainH;
   constexpr bool kHeads = kMode == MODE_HEADS || kMode == MODE_HEADS_TRAIN;
+  constexpr bool k2 = two_sm<kMode>();
+  constexpr int kSt = k2 ? kStages2 : kStages;                       // weight-ring stages
+  constexpr int kStageBytes = k2 ? kTileBytesW / 2 : kTileBytesW;    // 2-SM: this CTA's half (128 of the 256 output rows) of a tile
+  constexpr int kWF = k2 ? kBar2WFull : kBarWFull, kWE = k2 ? kBar2WEmpty : kBarWEmpty;
+  constexpr uint32_t kIdescMma = k2 ? make_idesc(256, 256) : kIdesc;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sW = smem + kSmemA;
@@ -221,15 +244,27 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
     return;
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(bar(kBarWFull + i), 1); mbar_init(bar(kBarWEmpty + i), kCluster ? 2 : 1); }
+    // 2-SM: the leader's issuer waits for the warps of BOTH CTAs (counts double, the peer arrives remotely); weight-full barriers are
+    // local (each CTA's producer loads its half) + a relay barrier in the leader that the peer arrives on when its half has landed
+    for (int i = 0; i < kSt; ++i) { mbar_init(bar(kWF + i), 1); mbar_init(bar(kWE + i), (kCluster && !k2) ? 2 : 1); }
+    if (k2) {
+      for (int i = 0; i < kSt; ++i) mbar_init(bar(kBar2WPeer + i), 1);
+      for (int i = 0; i < 4; ++i) mbar_init(bar(kBar2A0Peer + i), 1);
+    }
     // heads training: a K-block is free for the next tile's first operand once the last layer's MMAs AND the stash copy are done
-    for (int i = 0; i < 4; ++i) { mbar_init(bar(kBarARdy + i), 8); mbar_init(bar(kBarA0Rdy + i), kPro ? 4 : 1); mbar_init(bar(kBarAFree + i), kTrainH ? 2 : 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar(kBarAccRdy + i), 1); mbar_init(bar(kBarAccFree + i), 8); }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bar(kBarARdy + i), k2 ? 16 : 8);
+      mbar_init(bar(kBarA0Rdy + i), kPro ? (k2 ? 8 : 4) : 1);
+      mbar_init(bar(kBarAFree + i), kTrainH ? 2 : 1);
+    }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(kBarAccRdy + i), 1); mbar_init(bar(kBarAccFree + i), k2 ? 16 : 8); }
     for (int i = 0; i < 4; ++i) mbar_init(bar(kBarStash + i), 1);
-    mbar_init(bar(kBarARdy2), 8);
+    mbar_init(bar(kBarARdy2), k2 ? 16 : 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  if (warp == 1) {
+    if (k2) tmem_alloc_2sm(smem_u32(tmem_slot), kTmemCols); else tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
   if (kCluster) cluster_sync_all();  // the partner's barriers are initialised before anything is multicast into them
@@ -243,6 +278,12 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
   const uint32_t cta_rank = kCluster ? cluster_ctarank() : 0u;
   const int first_cta = kCluster ? (int)(blockIdx.x & ~1u) : (int)blockIdx.x;
   const int n_pass = n_tiles > first_cta ? (n_tiles - first_cta + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  // 2-SM: both CTAs walk n_pass passes in lockstep; a CTA whose tile number runs past n_tiles processes a PHANTOM tile (no
+  // samples, nothing stored) so that every barrier of the pair still gets its arrivals.
+  // arrive on a barrier the MMA issuer waits on: 2-SM -> always the leader's copy (remote arrive from the peer)
+  auto arrive_issuer = [&](int idx) {
+    if (!k2 || cta_rank == 0u) mbar_arrive(bar(idx)); else mbar_arrive_remote(bar(idx), 0u);
+  };
 
   // ---- aggregation epilogue, sum phase: task = (sample of the tile, 8 of the pass's 128 columns); shared by the epilogue threads
   //      and, in inference pair mode, the input warps (u = thread number among the n_threads that take tasks) ----
@@ -311,16 +352,19 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
         const int nkb = (P.layers[l].ksteps + 3) >> 2;
         const uint8_t* src = P.layers[l].w;
         for (int t = 0; t < 2 * nkb; ++t) {
-          mbar_wait(bar(kBarWEmpty + st), ph ^ 1);  // cluster: both CTAs have drained this stage
+          mbar_wait(bar(kWE + st), ph ^ 1);  // cluster: both CTAs have drained this stage
           if (elect_one()) {
-            mbar_expect_tx(bar(kBarWFull + st), kTileBytesW);
-            if (!kCluster)
+            mbar_expect_tx(bar(kWF + st), kStageBytes);
+            if (k2)  // this CTA's half of the tile: output rows [128 rank, 128 rank + 128)
+              bulk_g2s(smem_u32(sW + st * kStageBytes), src + (size_t)t * kTileBytesW + (size_t)cta_rank * kStageBytes, kStageBytes,
+                       bar(kWF + st));
+            else if (!kCluster)
               bulk_g2s(smem_u32(sW + st * kTileBytesW), src + (size_t)t * kTileBytesW, kTileBytesW, bar(kBarWFull + st));
             else if (cta_rank == 0)
               bulk_g2s_mc(smem_u32(sW + st * kTileBytesW), src + (size_t)t * kTileBytesW, kTileBytesW, bar(kBarWFull + st), 0x3);
           }
           __syncwarp();
-          if (++st == kStages) { st = 0; ph ^= 1; }
+          if (++st == kSt) { st = 0; ph ^= 1; }
         }
       }
     }
@@ -336,8 +380,21 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
     uint32_t lc = 0;                // running layer counter: layer lc accumulates into TMEM columns (lc & 1) * 256
     const uint64_t desc_a0 = make_desc(smem_u32(sA));
     const uint64_t desc_w0 = make_desc(smem_u32(sW));
+    if (k2 && cta_rank != 0u) {
+      // 2-SM, peer CTA: no MMAs are issued here; tell the leader when this CTA's half of every weight stage has landed
+      for (int pass = 0; pass < n_pass; ++pass)
+        for (int l = 0; l < n_layers; ++l) {
+          const int nkb = (P.layers[l].ksteps + 3) >> 2;
+          for (int t = 0; t < 2 * nkb; ++t) {
+            mbar_wait(bar(kWF + st), ph_w);
+            if (elect_one()) mbar_arrive_remote(bar(kBar2WPeer + st), 0u);
+            __syncwarp();
+            if (++st == kSt) { st = 0; ph_w ^= 1; }
+          }
+        }
+    } else
     for (int pass = 0, tile = blockIdx.x; pass < n_pass; ++pass, tile += gridDim.x) {
-      if (tile >= n_tiles) {
+      if (!k2 && tile >= n_tiles) {
         // the partner CTA still has a tile: keep the shared weight ring turning (no MMAs here, plain arrives on both empty-barriers)
         for (int l = 0; l < n_layers; ++l) {
           const int nkb = (P.layers[l].ksteps + 3) >> 2;
@@ -353,15 +410,30 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
         }
         continue;
       }
-      const bool has_next = tile + (int)gridDim.x < n_tiles;
+      // (2-SM: the waiters of both CTAs go on as long as the PAIR has another pass)
+      const bool has_next = k2 ? pass + 1 < n_pass : tile + (int)gridDim.x < n_tiles;
+      auto mma16 = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t accumulate) {
+        if (k2) umma_f16_2sm(d, a, b, kIdescMma, accumulate); else umma_f16(d, a, b, kIdescMma, accumulate);
+      };
+      auto mma8 = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t accumulate) {
+        if (k2) umma_f8_2sm(d, a, b, kIdescMma, accumulate); else umma_f8(d, a, b, kIdescMma, accumulate);
+      };
+      auto commit_stage = [&](int stage) {  // the weight stage may be refilled once the MMAs issued so far have completed
+        if (k2) umma_commit_2sm(bar(kWE + stage));
+        else if (kCluster) umma_commit_mc(bar(kBarWEmpty + stage), 0x3);
+        else umma_commit(bar(kBarWEmpty + stage));
+      };
+      auto commit_cta = [&](int idx) {  // barriers the warps of each CTA wait on locally (2-SM: both CTAs' copies)
+        if (k2) umma_commit_2sm(bar(idx)); else umma_commit(bar(idx));
+      };
       long long tw_w = 0, tw_a = 0, tw_f = 0;  // timeline: cycles this tile's issue loop waited for weights / operands / accumulators
       auto timed_wait = [&](uint32_t b, uint32_t par, long long& acc) {
         if (P.timeline) {
           const long long t0 = clock64();
-          mbar_wait(b, par);
+          if (k2) mbar_wait_cluster(b, par); else mbar_wait(b, par);
           acc += clock64() - t0;
         } else {
-          mbar_wait(b, par);
+          if (k2) mbar_wait_cluster(b, par); else mbar_wait(b, par);
         }
       };
       for (int l = 0; l < n_layers; ++l, ++lc) {
@@ -377,6 +449,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
         for (int kb = 0; kb < nkb; ++kb) {
           if ((!kPair || kPro) && l == 0) {  // first operand of a tile: the loader warp (heads) / the input warps (pair)
             timed_wait(bar(kBarA0Rdy + kb), (ph_a0 >> kb) & 1u, tw_a);
+            if (k2 && !kPro) timed_wait(bar(kBar2A0Peer + kb), (ph_a0 >> kb) & 1u, tw_a);  // the peer's loader relays its copy
             ph_a0 ^= 1u << kb;
           } else if (fresh_a) {
             timed_wait(bar(kBarARdy + kb), (ph_ar >> kb) & 1u, tw_a);
@@ -390,23 +463,27 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
             // K-block 0 of an epilogue-produced operand arrives in two halves: columns {0-15, 32-47} (K16 steps 0, 2 of the fp16
             // tile; the first K32 step of either half of the 8-bit tile), then {16-31, 48-63} (steps 1, 3; the second K32 steps).
             // Both weight stages of the block are held until the second half has been issued.
-            const int st2 = st + 1 == kStages ? 0 : st + 1;
-            const uint32_t ph_w2 = st + 1 == kStages ? ph_w ^ 1u : ph_w;
-            timed_wait(bar(kBarWFull + st), ph_w, tw_w);
-            timed_wait(bar(kBarWFull + st2), ph_w2, tw_w);
+            const int st2 = st + 1 == kSt ? 0 : st + 1;
+            const uint32_t ph_w2 = st + 1 == kSt ? ph_w ^ 1u : ph_w;
+            timed_wait(bar(kWF + st), ph_w, tw_w);
+            timed_wait(bar(kWF + st2), ph_w2, tw_w);
+            if (k2) {
+              timed_wait(bar(kBar2WPeer + st), ph_w, tw_w);
+              timed_wait(bar(kBar2WPeer + st2), ph_w2, tw_w);
+            }
             tc_fence_after();
-            const uint64_t b = desc_w0 + (uint64_t)(st * (kTileBytesW >> 4)), b2 = desc_w0 + (uint64_t)(st2 * (kTileBytesW >> 4));
+            const uint64_t b = desc_w0 + (uint64_t)(st * (kStageBytes >> 4)), b2 = desc_w0 + (uint64_t)(st2 * (kStageBytes >> 4));
             if (elect_one()) {
-              umma_f16(d_tmem, a_hi, b, kIdesc, 0u);
-              umma_f16(d_tmem, a_hi + 4, b + 4, kIdesc, 1u);
+              mma16(d_tmem, a_hi, b, 0u);
+              mma16(d_tmem, a_hi + 4, b + 4, 1u);
               if (!kF8) {
-                umma_f16(d_tmem, a_lo, b, kIdesc, 1u);
-                umma_f16(d_tmem, a_lo + 4, b + 4, kIdesc, 1u);
-                umma_f16(d_tmem, a_hi, b2, kIdesc, 1u);
-                umma_f16(d_tmem, a_hi + 4, b2 + 4, kIdesc, 1u);
+                mma16(d_tmem, a_lo, b, 1u);
+                mma16(d_tmem, a_lo + 4, b + 4, 1u);
+                mma16(d_tmem, a_hi, b2, 1u);
+                mma16(d_tmem, a_hi + 4, b2 + 4, 1u);
               } else {
-                umma_f8(d_tmem, a_lo, b2, kIdesc, 1u);
-                umma_f8(d_tmem, a_lo + 4, b2 + 4, kIdesc, 1u);
+                mma8(d_tmem, a_lo, b2, 1u);
+                mma8(d_tmem, a_lo + 4, b2 + 4, 1u);
               }
             }
             __syncwarp();
@@ -414,73 +491,75 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
             ph_ar2 ^= 1u;
             tc_fence_after();
             if (elect_one()) {
-              umma_f16(d_tmem, a_hi + 2, b + 2, kIdesc, 1u);
-              umma_f16(d_tmem, a_hi + 6, b + 6, kIdesc, 1u);
+              mma16(d_tmem, a_hi + 2, b + 2, 1u);
+              mma16(d_tmem, a_hi + 6, b + 6, 1u);
               if (!kF8) {
-                umma_f16(d_tmem, a_lo + 2, b + 2, kIdesc, 1u);
-                umma_f16(d_tmem, a_lo + 6, b + 6, kIdesc, 1u);
+                mma16(d_tmem, a_lo + 2, b + 2, 1u);
+                mma16(d_tmem, a_lo + 6, b + 6, 1u);
               }
-              if (kCluster) umma_commit_mc(bar(kBarWEmpty + st), 0x3); else umma_commit(bar(kBarWEmpty + st));
+              commit_stage(st);
               if (!kF8) {
-                umma_f16(d_tmem, a_hi + 2, b2 + 2, kIdesc, 1u);
-                umma_f16(d_tmem, a_hi + 6, b2 + 6, kIdesc, 1u);
+                mma16(d_tmem, a_hi + 2, b2 + 2, 1u);
+                mma16(d_tmem, a_hi + 6, b2 + 6, 1u);
               } else {
-                umma_f8(d_tmem, a_lo + 2, b2 + 2, kIdesc, 1u);
-                umma_f8(d_tmem, a_lo + 6, b2 + 6, kIdesc, 1u);
+                mma8(d_tmem, a_lo + 2, b2 + 2, 1u);
+                mma8(d_tmem, a_lo + 6, b2 + 6, 1u);
               }
-              if (kCluster) umma_commit_mc(bar(kBarWEmpty + st2), 0x3); else umma_commit(bar(kBarWEmpty + st2));
-              if (l == n_layers - 1 && has_next && (!kPair || kb < 2)) umma_commit(bar(kBarAFree + kb));
+              commit_stage(st2);
+              if (l == n_layers - 1 && has_next && (!kPair || kb < 2)) commit_cta(kBarAFree + kb);
             }
             __syncwarp();
             for (int q = 0; q < 2; ++q)
-              if (++st == kStages) { st = 0; ph_w ^= 1; }
+              if (++st == kSt) { st = 0; ph_w ^= 1; }
             continue;
           }
           // stage "hi": A_hi*W_hi + A_lo*W_hi
-          timed_wait(bar(kBarWFull + st), ph_w, tw_w);
+          timed_wait(bar(kWF + st), ph_w, tw_w);
+          if (k2) timed_wait(bar(kBar2WPeer + st), ph_w, tw_w);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t b = desc_w0 + (uint64_t)(st * (kTileBytesW >> 4));
+            const uint64_t b = desc_w0 + (uint64_t)(st * (kStageBytes >> 4));
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              if (ks < ks_n) umma_f16(d_tmem, a_hi + 2 * ks, b + 2 * ks, kIdesc, (kb | ks) != 0);
+              if (ks < ks_n) mma16(d_tmem, a_hi + 2 * ks, b + 2 * ks, (kb | ks) != 0);
             if (!kF8) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                if (ks < ks_n) umma_f16(d_tmem, a_lo + 2 * ks, b + 2 * ks, kIdesc, 1u);
+                if (ks < ks_n) mma16(d_tmem, a_lo + 2 * ks, b + 2 * ks, 1u);
             }
-            if (kCluster) umma_commit_mc(bar(kBarWEmpty + st), 0x3); else umma_commit(bar(kBarWEmpty + st));
+            commit_stage(st);
           }
           __syncwarp();
-          if (++st == kStages) { st = 0; ph_w ^= 1; }
+          if (++st == kSt) { st = 0; ph_w ^= 1; }
           // stage "lo": A_hi*W_lo
-          timed_wait(bar(kBarWFull + st), ph_w, tw_w);
+          timed_wait(bar(kWF + st), ph_w, tw_w);
+          if (k2) timed_wait(bar(kBar2WPeer + st), ph_w, tw_w);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t b = desc_w0 + (uint64_t)(st * (kTileBytesW >> 4));
+            const uint64_t b = desc_w0 + (uint64_t)(st * (kStageBytes >> 4));
             if (!kF8) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                if (ks < ks_n) umma_f16(d_tmem, a_hi + 2 * ks, b + 2 * ks, kIdesc, 1u);
+                if (ks < ks_n) mma16(d_tmem, a_hi + 2 * ks, b + 2 * ks, 1u);
             } else {
               // the 8-bit tile: row = [lo8 of the 64 columns | hi8 of the 64 columns] against [Whi8 | Wlo8]; a K = 32 step
               // covers two fp16 K-steps, so a K-block with ks_n fp16 steps takes ks_n / 2 steps in each 64-byte half
 #pragma unroll
               for (int k8 = 0; k8 < 2; ++k8)
-                if (2 * k8 < ks_n) umma_f8(d_tmem, a_lo + 2 * k8, b + 2 * k8, kIdesc, 1u);
+                if (2 * k8 < ks_n) mma8(d_tmem, a_lo + 2 * k8, b + 2 * k8, 1u);
 #pragma unroll
               for (int k8 = 0; k8 < 2; ++k8)
-                if (2 * k8 < ks_n) umma_f8(d_tmem, a_lo + 4 + 2 * k8, b + 4 + 2 * k8, kIdesc, 1u);
+                if (2 * k8 < ks_n) mma8(d_tmem, a_lo + 4 + 2 * k8, b + 4 + 2 * k8, 1u);
             }
-            if (kCluster) umma_commit_mc(bar(kBarWEmpty + st), 0x3); else umma_commit(bar(kBarWEmpty + st));
+            commit_stage(st);
             // this K-block may take the next tile's first operand (arrive only where somebody waits: pair mode restages
             // K-blocks 0..1, and the last tile of a CTA has no successor)
-            if (l == n_layers - 1 && has_next && (!kPair || kb < 2)) umma_commit(bar(kBarAFree + kb));
-            if (kb == nkb - 1) umma_commit(bar(kBarAccRdy + ab));
+            if (l == n_layers - 1 && has_next && (!kPair || kb < 2)) commit_cta(kBarAFree + kb);
+            if (kb == nkb - 1) commit_cta(kBarAccRdy + ab);
           }
           if (lane == 0 && kb == nkb - 1 && l < 4) NPCD_TL(pass, 18 + 3 * l);  // last MMA of the layer issued
           __syncwarp();
-          if (++st == kStages) { st = 0; ph_w ^= 1; }
+          if (++st == kSt) { st = 0; ph_w ^= 1; }
         }
       }
       if (lane == 0) { NPCD_TLV(pass, 28, tw_w); NPCD_TLV(pass, 29, tw_a); NPCD_TLV(pass, 30, tw_f); }
@@ -522,15 +601,27 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
       __syncwarp();
     } else if (!kPair) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int n_it = k2 ? n_pass : (n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0);
+      for (int tile = blockIdx.x; (int)it < n_it; tile += gridDim.x, ++it) {
         for (int kb = 0; kb < 4; ++kb) {
           if (it > 0) mbar_wait(bar(kBarAFree + kb), (it - 1) & 1u);
           if (elect_one()) {
-            mbar_expect_tx(bar(kBarA0Rdy + kb), 2 * kTileBytesA);
-            bulk_g2s(smem_u32(sA + kb * 2 * kTileBytesA), P.img + (size_t)tile * kImgTileBytes + (size_t)kb * 2 * kTileBytesA,
-                     2 * kTileBytesA, bar(kBarA0Rdy + kb));
+            if (tile < n_tiles) {
+              mbar_expect_tx(bar(kBarA0Rdy + kb), 2 * kTileBytesA);
+              bulk_g2s(smem_u32(sA + kb * 2 * kTileBytesA), P.img + (size_t)tile * kImgTileBytes + (size_t)kb * 2 * kTileBytesA,
+                       2 * kTileBytesA, bar(kBarA0Rdy + kb));
+            } else {
+              mbar_arrive(bar(kBarA0Rdy + kb));  // phantom tile of the 2-SM pair: whatever the K-block holds is multiplied, nothing is stored
+            }
           }
           __syncwarp();
+        }
+        if (k2 && cta_rank != 0u) {  // the leader's issuer must know that THIS CTA's operand has landed too
+          for (int kb = 0; kb < 4; ++kb) {
+            mbar_wait(bar(kBarA0Rdy + kb), it & 1u);
+            if (elect_one()) mbar_arrive_remote(bar(kBar2A0Peer + kb), 0u);
+            __syncwarp();
+          }
         }
       }
     }
@@ -572,7 +663,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
     auto publish_a0 = [&](int kb) {
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(kBarA0Rdy + kb));
+      if (lane == 0) arrive_issuer(kBarA0Rdy + kb);
     };
     // (sin, cos) of d * 2^i * pi for n consecutive octaves starting with frequency fr0, interleaved into v[0 .. 2n)
     auto octaves = [&](float d, float fr0, int n, float* v) {
@@ -591,7 +682,8 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
     const float kPi = 3.14159274101257324f;
     // input of tile `tile` into K-blocks 0 / 1; wait_free: the K-blocks still hold the previous tile's X_3 until layer 3's MMAs pass
     auto prepare = [&](int tile, int buf, bool wait_free, uint32_t parity) {
-      const int s_begin = __ldg(P.tile_start + tile), s_end = __ldg(P.tile_start + tile + 1);
+      const bool phantom = tile >= n_tiles;  // 2-SM pair with an odd tile count: an all-padding tile
+      const int s_begin = phantom ? 0 : __ldg(P.tile_start + tile), s_end = phantom ? 0 : __ldg(P.tile_start + tile + 1);
       const int n_samp = s_end - s_begin;
       const int base = __ldg(P.pair_off + s_begin);
       uint8_t* row_samp = row_samp_all + buf * 128;
@@ -679,11 +771,12 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
       for (int c = 0; c < 4; ++c) store_c(1, c, c);
       publish_a0(1);
     };
-    if ((int)blockIdx.x < n_tiles) prepare((int)blockIdx.x, 0, false, 0u);
+    const int n_it = k2 ? n_pass : (n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0);
+    if (n_it > 0) prepare((int)blockIdx.x, 0, false, 0u);
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; (int)it < n_it; tile += gridDim.x, ++it) {
       const int next = tile + (int)gridDim.x;
-      if (next < n_tiles) prepare(next, (int)((it + 1) & 1u), true, it & 1u);
+      if ((int)it + 1 < n_it) prepare(next, (int)((it + 1) & 1u), true, it & 1u);
       // a third of the segmented-sum tasks of this tile's aggregation epilogue (two passes of 128 columns)
 #pragma unroll 1
       for (int pass = 0; pass < 2; ++pass) {
@@ -739,7 +832,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(barrier_index));
+      if (lane == 0) arrive_issuer(barrier_index);
     };
     auto wait_acc = [&](uint32_t ab) {
       mbar_wait(bar(kBarAccRdy + ab), (ph_acc >> ab) & 1u);
@@ -749,7 +842,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
     auto release_acc = [&](uint32_t ab) {
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(kBarAccFree + ab));
+      if (lane == 0) arrive_issuer(kBarAccFree + ab);
     };
 
     // training: K-block kb may only be overwritten once the stash warp has copied its previous contents out
@@ -950,7 +1043,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
       if (kPro) tile_now = cur;
       for (int it = kPro ? 0 : -1;; ++it) {
         const bool prime = it < 0;
-        if (kPro && cur >= n_tiles) break;
+        if (kPro && (k2 ? it >= n_pass : cur >= n_tiles)) break;  // (2-SM: phantom tiles keep the pair in lockstep)
         const int target = prime ? (int)blockIdx.x : cur + (int)gridDim.x;  // tile whose layer-0 input is staged now
         const bool has_target = target < n_tiles;
         if (prime && !has_target) break;
@@ -1043,7 +1136,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
           ++tl_it;
           ++lc;
         }
-        if (!has_target) break;
+        if (!has_target && !k2) break;
         cur = target;
         tile_now = cur;
       }
@@ -1112,7 +1205,9 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
         ++lc;
       };
 
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int n_it = k2 ? n_pass : (n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0);
+      int tile = blockIdx.x;
+      for (int it = 0; it < n_it; ++it, tile += gridDim.x) {  // (2-SM: a tile number past n_tiles is a phantom tile, s >= S)
         const long long s = (long long)tile * 128 + row;
         tile_now = tile;
         if (kMode == MODE_PROBE) {
@@ -1169,7 +1264,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
   if (kCluster) cluster_sync_all();  // the partner may still multicast into / signal this CTA's shared memory until it is done too
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (k2) tmem_dealloc_2sm(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
