@@ -65,8 +65,10 @@ constexpr int kOffWts = 256;      // float[2][128] raw inverse-distance weights 
 constexpr int kOffRowSamp = 1280; // u8[2][128] row -> sample-in-tile                      (pair)
 constexpr int kOffSampRow = 1536; // u8[2][128] sample-in-tile -> first row                (pair)
 constexpr int kOffSampCnt = 1792; // u8[2][128] sample-in-tile -> rows                     (pair)
-constexpr int kOffPart = 256;     // float[128][4] cross-half partial dot products         (heads; aliases the pair arrays)
-constexpr int kOffStashBars = 2048;  // 4 mbarriers: K-block kb of the A operand has been copied to the training stash
+constexpr int kOffPart = 256;     // float[128][4] cross-half partial dot products, 2048 B  (heads; aliases the pair arrays)
+// (the heads' partial-product array ends at 2304: every barrier placed after the first block must sit beyond it -- with the stash
+// barriers at 2048 the dot epilogues of rows 112..113 used to write their partial sums over them)
+constexpr int kOffStashBars = 2304;  // 4 mbarriers: K-block kb of the A operand has been copied to the training stash (+ kBarARdy2)
 
 // barrier indices
 constexpr int kBarWFull = 0, kBarWEmpty = 3, kBarARdy = 6, kBarA0Rdy = 10, kBarAFree = 14, kBarAccRdy = 18, kBarAccFree = 20;
@@ -86,7 +88,9 @@ constexpr bool two_sm() {
   return NPCD_TC_2SM != 0 && NPCD_TC_CLUSTER != 0 && (kMode == 0 /* MODE_PAIR */ || kMode == 1 /* MODE_HEADS */);
 }
 constexpr int kStages2 = 6;
-constexpr int kOffBars2 = 2176;  // 2-SM barrier block in the misc area
+constexpr int kOffBars2 = 2368;  // 2-SM barrier block in the misc area (22 barriers, ends at 2544 of the 3072 bytes)
+static_assert(kOffPart + 128 * 4 * 4 <= kOffStashBars && kOffStashBars + 5 * 8 <= kOffBars2 && kOffBars2 + 22 * 8 <= kSmemMisc,
+              "misc shared-memory layout");
 constexpr int kBar2WFull = kOffBars2 / 8, kBar2WEmpty = kBar2WFull + 6, kBar2WPeer = kBar2WFull + 12, kBar2A0Peer = kBar2WFull + 18;
 constexpr int kBarStash = kOffStashBars / 8;
 constexpr int kBarARdy2 = kBarStash + 4;  // second half (columns 16-31 / 48-63) of K-block 0 published (inference: split first block)
