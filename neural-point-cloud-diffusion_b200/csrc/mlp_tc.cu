@@ -74,14 +74,18 @@ constexpr int kOffStashBars = 2304;  // 4 mbarriers: K-block kb of the A operand
 constexpr int kBarWFull = 0, kBarWEmpty = 3, kBarARdy = 6, kBarA0Rdy = 10, kBarAFree = 14, kBarAccRdy = 18, kBarAccFree = 20;
 // 2-SM mode (cta_group::2, inference pair / heads kernels): the leader CTA of a pair issues every MMA for both CTAs' tiles
 // (M = 256) and each CTA holds HALF of every weight tile, so the 96 KB weight area is a ring of SIX 16 KB half-tiles.
-// Why: the timeline of the 1-SM version showed a layer's 32 MMAs taking ~5900 cycles instead of 4096 -- shared-memory bandwidth:
+// Why: the timeline of the 1-SM version shows a layer's 32 MMAs taking ~5600 cycles instead of 4096 -- shared-memory bandwidth:
 // 96 B/clk of MMA operand reads (4 KB of A + 8 KB of B per 128 cycles) + 64 B/clk of weight refill + the epilogue's stores exceed
 // the 128 B/clk an SM has.  With half of B per CTA the MMAs read 64 B/clk and the refill writes 32 B/clk.
+// MEASURED (B200, round 2, profiles/r2_two_sm_experiment.md): bit-identical results, but NOT faster yet -- 153.5 ms per 251-view
+// step against 141.9 ms for the 1-SM kernel: the cross-CTA hand-offs (remote arrives of the peer's epilogue / input warps, the
+// relay of the peer's weight-full barrier) lengthen the epilogue -> MMA chain by more than the MMA phase gains (with cluster-scope
+// release / acquire on those hand-offs it was 174 ms).  Build switch, OFF by default.
 #ifndef NPCD_TC_CLUSTER
 #define NPCD_TC_CLUSTER 1
 #endif
 #ifndef NPCD_TC_2SM
-#define NPCD_TC_2SM 1
+#define NPCD_TC_2SM 0
 #endif
 template <int kMode>
 constexpr bool two_sm() {
@@ -286,7 +290,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
   // samples, nothing stored) so that every barrier of the pair still gets its arrivals.
   // arrive on a barrier the MMA issuer waits on: 2-SM -> always the leader's copy (remote arrive from the peer)
   auto arrive_issuer = [&](int idx) {
-    if (!k2 || cta_rank == 0u) mbar_arrive(bar(idx)); else mbar_arrive_remote(bar(idx), 0u);
+    if (!k2 || cta_rank == 0u) mbar_arrive(bar(idx)); else mbar_arrive_remote_lite(bar(idx), 0u);
   };
 
   // ---- aggregation epilogue, sum phase: task = (sample of the tile, 8 of the pass's 128 columns); shared by the epilogue threads
@@ -391,7 +395,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
           const int nkb = (P.layers[l].ksteps + 3) >> 2;
           for (int t = 0; t < 2 * nkb; ++t) {
             mbar_wait(bar(kWF + st), ph_w);
-            if (elect_one()) mbar_arrive_remote(bar(kBar2WPeer + st), 0u);
+            if (elect_one()) mbar_arrive_remote_lite(bar(kBar2WPeer + st), 0u);
             __syncwarp();
             if (++st == kSt) { st = 0; ph_w ^= 1; }
           }
@@ -434,10 +438,10 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
       auto timed_wait = [&](uint32_t b, uint32_t par, long long& acc) {
         if (P.timeline) {
           const long long t0 = clock64();
-          if (k2) mbar_wait_cluster(b, par); else mbar_wait(b, par);
+          mbar_wait(b, par);
           acc += clock64() - t0;
         } else {
-          if (k2) mbar_wait_cluster(b, par); else mbar_wait(b, par);
+          mbar_wait(b, par);
         }
       };
       for (int l = 0; l < n_layers; ++l, ++lc) {
@@ -623,7 +627,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
         if (k2 && cta_rank != 0u) {  // the leader's issuer must know that THIS CTA's operand has landed too
           for (int kb = 0; kb < 4; ++kb) {
             mbar_wait(bar(kBarA0Rdy + kb), it & 1u);
-            if (elect_one()) mbar_arrive_remote(bar(kBar2A0Peer + kb), 0u);
+            if (elect_one()) mbar_arrive_remote_lite(bar(kBar2A0Peer + kb), 0u);
             __syncwarp();
           }
         }

@@ -87,6 +87,13 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(bar), "r"(cta));
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
 }
+// the same with the default (CTA-scope release) semantics -- the form CUTLASS's ClusterBarrier::arrive(cta_id) uses for the
+// epilogue -> MMA signals of 2-SM kernels; the cluster-scope release above costs a cluster-wide fence per arrive
+__device__ __forceinline__ void mbar_arrive_remote_lite(uint32_t bar, uint32_t cta) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(bar), "r"(cta));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
 // shared -> global bulk copy (bulk async-group completion): the training stash writes
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
