@@ -46,7 +46,12 @@ def _count(n):
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    """Raw handle of torch's current stream (every C-ABI call launches on it).  `torch.cuda.current_stream().cuda_stream` builds a
+    Stream object per call (~20 us measured, ~300 calls per training step); the raw getter is a plain C call."""
+    try:
+        return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
+    except AttributeError:  # private API moved: fall back to the public one
+        return torch.cuda.current_stream().cuda_stream
 
 
 # Grow-only pool for the large per-step training buffers (stash ~8 KB per pair, workspace ~1 KB per sample): their sizes follow the
