@@ -76,6 +76,12 @@ class MLP(Module):
         if self.check_weights == "fingerprint":
             key += tuple(torch.stack(torch._foreach_norm([p.detach() for p in params], float("inf"))).tolist())
         if self._packed is None or key != self._packed_key:
+            if (self.mlp_impl == "tc" and for_training and isinstance(self._packed, ops.PackedTcWeights) and self._packed._dgrad is not None
+                    and self._packed._hdgrad is not None and self._packed.same_storage(self.aggregator.local_field, self.shape_net, self.channel_net)):
+                # the optimizer stepped the same tensors in place: re-pack into the same buffers (no allocation, same job table)
+                self._packed.refresh()
+                self._packed_key = key
+                return self._packed
             if self.mlp_impl == "tc":  # training: the transposed operands of the backward kernels ride in the same pack launch
                 self._packed = ops.PackedTcWeights(self.aggregator.local_field, self.shape_net, self.channel_net, self.aggregator.in_dim,
                                                    for_training=for_training)

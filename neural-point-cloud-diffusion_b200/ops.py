@@ -427,11 +427,10 @@ class PackedTcWeights:
         self.layers = layers
         ws = [l.weight.detach().float().contiguous() for l in layers]
         self.ws = ws
-        # one device->host transfer for everything the host needs: per-layer max|w| (scales), biases, narrow output layers
-        small = torch.cat([torch.stack(torch._foreach_norm(ws, float("inf")))]
-                          + [l.bias.detach().float().reshape(-1) for l in layers]
-                          + [sn[1].weight.detach().float().reshape(-1), sn[1].bias.detach().float().reshape(-1),
-                             cn[4].weight.detach().float().reshape(-1), cn[4].bias.detach().float().reshape(-1)]).cpu().numpy()
+        self._narrow = (sn[1], cn[4])
+        self._all_jobs = []    # (job, scale reference): refresh() re-runs them on the same buffers
+        self._layer_refs = []  # (npcd_tc_layer of a weight table, layer index): refresh() updates their inverse scales
+        small = np.ascontiguousarray(self._read_small(), dtype=np.float32)
         maxabs = small[:10]
         self.maxabs = maxabs
         self._off = 10
@@ -440,6 +439,7 @@ class PackedTcWeights:
         self.head_linears = [cn[3], cn[2], cn[1], cn[0], sn[0], lf[4]]  # order of use in npcd_heads_tc_bwd
         self._dgrad = None
         self._hdgrad = None
+        self._dgrad_refs = self._hdgrad_refs = None
         self._folded = None
         self.scales = [2.0 ** math.floor(math.log2(4.0 / float(m))) if m > 0 else 1.0 for m in maxabs]
         self._bias = [self._host(HIDDEN) for _ in range(10)]
@@ -453,6 +453,42 @@ class PackedTcWeights:
         self.struct = s
         self.error_flag = _error_flag(dev)
 
+    def _read_small(self):
+        """One device->host transfer for everything the host needs: per-layer max|w| (scales), biases, narrow output layers."""
+        sn1, cn4 = self._narrow
+        return torch.cat([torch.stack(torch._foreach_norm(self.ws, float("inf")))]
+                         + [l.bias.detach().float().reshape(-1) for l in self.layers]
+                         + [sn1.weight.detach().float().reshape(-1), sn1.bias.detach().float().reshape(-1),
+                            cn4.weight.detach().float().reshape(-1), cn4.bias.detach().float().reshape(-1)]).cpu().numpy()
+
+    def same_storage(self, local_field, shape_net, channel_net) -> bool:
+        lin = lambda seq: [m for m in seq if isinstance(m, torch.nn.Linear)]
+        lf, sn, cn = lin(local_field), lin(shape_net), lin(channel_net)
+        layers = [lf[0], lf[1], lf[2], lf[3], lf[4], sn[0], cn[0], cn[1], cn[2], cn[3]]
+        return (all(a is b for a, b in zip(layers, self.layers)) and self._narrow[0] is sn[1] and self._narrow[1] is cn[4]
+                and all(w.data_ptr() == l.weight.data_ptr() for w, l in zip(self.ws, layers)))
+
+    def refresh(self):
+        """Re-pack after an optimizer step that updated the parameters IN PLACE (same storage): the packed buffers, the job table and
+        the host arrays the weight tables point to are reused -- one max|w| reduction, one device->host transfer, one pack launch,
+        no allocation.  The inference-only views (folded heads, f16+e4m3x2 tables) are dropped and rebuilt on demand."""
+        np.copyto(self._small, self._read_small())  # biases / narrow layers: the tables hold pointers INTO this array
+        self.scales = [2.0 ** math.floor(math.log2(4.0 / float(m))) if m > 0 else 1.0 for m in self._small[:10]]
+
+        def scale_of(ref):
+            return min(self.scales[i] for i in ref) if isinstance(ref, tuple) else self.scales[ref]
+
+        for job, ref in self._all_jobs:
+            job.scale = float(scale_of(ref))
+        for lay, i in self._layer_refs:
+            lay.inv_scale = 1.0 / self.scales[i]
+        for pack, refs in ((self._dgrad, self._dgrad_refs), (self._hdgrad, self._hdgrad_refs)):
+            if pack is not None:
+                for j, ref in enumerate(refs):
+                    pack[1][j] = 1.0 / scale_of(ref)
+        self._folded = self._f8 = self._folded_f8 = None
+        self._run([j for j, _ in self._all_jobs])
+
     def _fill(self, s, fmt: int):
         """Fills the layer table of ``s`` with freshly allocated packed-weight buffers in operand format ``fmt`` (0: fp16 hi/lo,
         1: fp16 + e4m3) and returns the pack jobs that fill them."""
@@ -464,8 +500,11 @@ class PackedTcWeights:
             out = torch.empty(((k_pad + 63) // 64) * 2 * 32768, dtype=torch.uint8, device=self.dev)
             if k_pad % 64:
                 out.zero_()  # the tail of the last K-block is never written by the pack kernel
-            jobs.append(self._job(w, w.shape[1], HIDDEN, w.shape[1], k_pad, False, perm, self.scales[i], out, fmt))
+            jobs.append(self._job(w, w.shape[1], HIDDEN, w.shape[1], k_pad, False, perm, self.scales[i], out, fmt,
+                                  sref=i if fmt == 0 else None))
             dst.packed_w, dst.bias, dst.inv_scale, dst.k_pad = out.data_ptr(), self._bias[i], 1.0 / self.scales[i], k_pad
+            if fmt == 0:
+                self._layer_refs.append((dst, i))
 
         layer(s.pair[0], 0, PAIR_IN_COLS, self.perm0)
         for i in range(1, 4):
@@ -498,11 +537,13 @@ class PackedTcWeights:
         self.keep.append(a)
         return a.ctypes.data
 
-    def _job(self, w, ld, n_rows, k_in, k_pad, transpose, perm, scale, out, fmt: int = 0):
+    def _job(self, w, ld, n_rows, k_in, k_pad, transpose, perm, scale, out, fmt: int = 0, sref=None):
         self.keep += [w, out]
         j = _lib.PackJob()
         j.w, j.ld, j.n_rows, j.k_in, j.k_pad, j.transpose = w.data_ptr(), ld, n_rows, k_in, k_pad, int(transpose)
         j.perm, j.scale, j.out, j.format = (perm.data_ptr() if perm is not None else None), float(scale), out.data_ptr(), int(fmt)
+        if sref is not None:  # a job of the training set (forward tables + transposed backward operands): refresh() re-runs it
+            self._all_jobs.append((j, sref))
         return j
 
     def _run(self, jobs):
@@ -519,9 +560,10 @@ class PackedTcWeights:
         for l in range(4):
             w = self.ws[l]
             out = torch.empty(4 * 2 * 32768, dtype=torch.uint8, device=self.dev)
-            jobs.append(self._job(w, w.shape[1], 32 if l == 0 else HIDDEN, HIDDEN, HIDDEN, True, None, self.scales[l], out))
+            jobs.append(self._job(w, w.shape[1], 32 if l == 0 else HIDDEN, HIDDEN, HIDDEN, True, None, self.scales[l], out, sref=l))
             ptrs[l], invs[l] = out.data_ptr(), 1.0 / self.scales[l]
         self._dgrad = (ptrs, invs, None)
+        self._dgrad_refs = [0, 1, 2, 3]
         return jobs
 
     def _hdgrad_jobs(self):
@@ -534,9 +576,11 @@ class PackedTcWeights:
         jobs = []
         for j, i in enumerate(idx):
             out = torch.empty(4 * 2 * 32768, dtype=torch.uint8, device=self.dev)
-            jobs.append(self._job(self.ws[i], HIDDEN, HIDDEN, HIDDEN, HIDDEN, True, None, scales[j], out))
+            ref = (6, 5) if j in (3, 4) else i
+            jobs.append(self._job(self.ws[i], HIDDEN, HIDDEN, HIDDEN, HIDDEN, True, None, scales[j], out, sref=ref))
             ptrs[j], invs[j] = out.data_ptr(), 1.0 / scales[j]
         self._hdgrad = (ptrs, invs, None)
+        self._hdgrad_refs = [9, 8, 7, (6, 5), (6, 5), 4]
         return jobs
 
     def dgrad_pack(self):
