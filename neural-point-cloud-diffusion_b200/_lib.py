@@ -9,7 +9,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnpcd_b200.so")
+# NPCD_LIB_PATH: development aid (tools/gpu_ablate.sh) -- load a prebuilt experimental library instead of the in-tree one
+LIB_PATH = os.environ.get("NPCD_LIB_PATH") or os.path.join(_HERE, "libnpcd_b200.so")
 ABI_VERSION = 3
 
 _lock = threading.Lock()
@@ -159,7 +160,7 @@ def load():
         from . import build as _build
 
         try:
-            if os.path.isdir(_build.CSRC) and (_build.have_nvcc() or not os.path.isfile(LIB_PATH)):
+            if not os.environ.get("NPCD_LIB_PATH") and os.path.isdir(_build.CSRC) and (_build.have_nvcc() or not os.path.isfile(LIB_PATH)):
                 _build.build()
         except Exception as e:  # noqa: BLE001
             if not os.path.isfile(LIB_PATH):

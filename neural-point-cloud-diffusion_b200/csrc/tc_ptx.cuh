@@ -5,6 +5,23 @@
 
 #include "common.cuh"
 
+// ---- timing-only ablation switches (tools/build_variants.py, tools/gpu_ablate.sh); all off in the shipped build ----
+#ifndef NPCD_EXP_NSPLIT
+#define NPCD_EXP_NSPLIT 0    // experiment (results stay correct): every M128 N256 MMA issued as two N = 128 MMAs
+#endif
+#ifndef NPCD_EXP_NOREFILL
+#define NPCD_EXP_NOREFILL 0  // timing-only ablation: the weight producer signals the ring stages without copying anything
+#endif
+#ifndef NPCD_EXP_NOFENCE
+#define NPCD_EXP_NOFENCE 0   // timing-only ablation: no fence.proxy.async before the operand-ready arrives
+#endif
+#ifndef NPCD_EXP_NOTMEMLD
+#define NPCD_EXP_NOTMEMLD 0  // timing-only ablation: the epilogues do not read the accumulator
+#endif
+#ifndef NPCD_EXP_NOBIAS
+#define NPCD_EXP_NOBIAS 0    // timing-only ablation: no bias loads from the constant bank
+#endif
+
 namespace npcd {
 namespace tc {
 
@@ -101,7 +118,11 @@ __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() {
+#if !defined(NPCD_EXP_NOFENCE) || !NPCD_EXP_NOFENCE
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -174,6 +195,11 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) 
 }
 // asynchronous TMEM -> register load of 32 consecutive fp32 columns of this thread's lane; complete after tmem_wait(v)
 __device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&v)[32]) {
+#if defined(NPCD_EXP_NOTMEMLD) && NPCD_EXP_NOTMEMLD
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = taddr * (uint32_t)(i + 1);
+  return;
+#endif
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -291,6 +317,24 @@ __device__ __forceinline__ void split8(const float (&y)[8], uint4& hi, uint4& lo
 // one kind::f16 product and two kind::f8f6f4 products (the correction terms only need the 4 significant bits e4m3 has), all three
 // accumulating into the same fp32 TMEM accumulator.  Ranges: fp16 overflows at |y| >= 8190, lo8 / hi8 saturate (satfinite, the
 // correction degrades gracefully) at |y| > 448 / 896; absolute resolution of the corrections 2^-22 and below.
+#ifndef NPCD_EXP_NOCVT
+#define NPCD_EXP_NOCVT 0
+#endif
+#ifndef NPCD_EXP_NOF8MMA
+#define NPCD_EXP_NOF8MMA 0  // timing-only ablation: the K = 32 e4m3 MMAs are not issued
+#endif
+#ifndef NPCD_EXP_NOSTS8
+#define NPCD_EXP_NOSTS8 0   // timing-only ablation: the layer epilogues do not store the 8-bit tile
+#endif
+#ifndef NPCD_EXP_NOPOSENC
+#define NPCD_EXP_NOPOSENC 0 // timing-only ablation: the input warps skip the sin / cos evaluation
+#endif
+#ifndef NPCD_EXP_NOEPI
+#define NPCD_EXP_NOEPI 0
+#endif
+#ifndef NPCD_EXP_NOAGG
+#define NPCD_EXP_NOAGG 0    // timing-only ablation: the aggregation epilogue stages but does not sum / store
+#endif
 constexpr float kF8ActScale = 8.0f;          // 2^3: activations are stored times this
 constexpr float kF8AccScaleInv = 1.0f / 65536.0f;  // accumulator = 2^16 * (y . w_prescaled)
 
@@ -316,9 +360,15 @@ __device__ __forceinline__ void split8_f8(const float (&y)[8], uint4& hi, uint2&
     float r0, r1;
     unpack2(mul2(sub2(pack2(y[2 * j], y[2 * j + 1]), pack2(f.x, f.y)), k256), r0, r1);
     h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+#if NPCD_EXP_NOCVT  // timing-only ablation (results are garbage): the two e4m3 conversions replaced by byte shuffles
+    l[j] = __byte_perm(__float_as_uint(r0), __float_as_uint(r1), 0x0073);
+    g[j] = __byte_perm(h[j], 0u, 0x0031);
+    (void)sixteenth;
+#else
     l[j] = cvt_e4m3x2_f32(r0, r1);
     const __half2 hs = __hmul2(hh, sixteenth);
     g[j] = cvt_e4m3x2_f16x2(*reinterpret_cast<const uint32_t*>(&hs));
+#endif
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo8 = make_uint2(l[0] | (l[1] << 16), l[2] | (l[3] << 16));
