@@ -280,10 +280,31 @@ __device__ __forceinline__ void scan_smem(const SGrid& g, float x, float y, floa
   }
 }
 
-__device__ __forceinline__ bool any_within(const SGrid& g, float x, float y, float z, float T) {
-  bool hit = false;
-  scan_smem(g, x, y, z, T, [&](float, int) { hit = true; return true; });
-  return hit;
+// "Any point within r?" as ONE flattened loop over the 9 row ranges of the 27-cell neighbourhood, early exit on the first hit.
+// ncu on the drain pass of k_march_count_s with nine consecutive per-range loops: 45 % of the kernel's instructions ran at 3-4 active
+// lanes -- every one of the nine loops is as long as its slowest lane.  Flattened, a warp iteration costs its longest single lane.
+// (The ranges are looked up when the walk reaches them: no per-thread array, no extra shared memory.)
+__device__ __forceinline__ bool any_within_flat(const SGrid& g, float x, float y, float z, float T) {
+  const int cx = grid_coord(x), cy = grid_coord(y), cz = grid_coord(z);
+  const int x0 = max(cx - 1, 0), x1 = min(cx + 1, kGrid - 1) + 1;
+  int k = -1, i = 0, e = 0;
+#pragma unroll 1
+  while (true) {
+    while (i >= e) {  // next non-empty range
+      if (++k == 9) return false;
+      const int k3 = (k * 11) >> 5;  // k / 3 for k < 9
+      const int qz = cz + k3 - 1, qy = cy + (k - 3 * k3) - 1;
+      if (qz < 0 || qz >= kGrid || qy < 0 || qy >= kGrid) continue;
+      const int base = (qz * kGrid + qy) * kGrid;
+      i = (int)g.cs[base + x0];
+      e = (int)g.cs[base + x1];
+    }
+    const float4 p = g.pts[i];
+    ++i;
+    const float dx = __fsub_rn(x, p.x), dy = __fsub_rn(y, p.y), dz = __fsub_rn(z, p.z);
+    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    if (d2 <= T) return true;
+  }
 }
 
 __device__ __forceinline__ int fine_coord(float v) {
@@ -352,7 +373,7 @@ __global__ void __launch_bounds__(kChunk) k_march_count_s(const float* __restric
         const int r = item >> 7, i = item & 127;
         float x, y, z;
         sample_xyz(ray0 + r, i, x, y, z);
-        if (any_within(g, x, y, z, T)) atomicOr(&valid_s[r * 4 + (i >> 5)], 1u << (i & 31));
+        if (any_within_flat(g, x, y, z, T)) atomicOr(&valid_s[r * 4 + (i >> 5)], 1u << (i & 31));
       }
     }
     __syncwarp();
@@ -620,6 +641,498 @@ __global__ void __launch_bounds__(kChunk) k_knn_fill_s(const float* __restrict__
   }
 }
 
+
+// =====================================================================================================================================
+// Ray-coherent kernels (impl 3; n_points <= kSmemMaxPoints).  Same results bit for bit as the kernels above.
+//
+// ncu on the thread-per-sample kernels (profiles/r1_ncu_query_summary.md, r2_ncu_summary.md): 15-18 of 32 lanes active -- the exact
+// tests of the marcher's uncertain samples run at 3-4 active lanes (early exits), and every kept sample of the kNN kernel walks the
+// ~35 points of its own 27-cell neighbourhood although the samples of ONE ray share almost all of them.  Here a WARP owns a ray:
+//   1. the points that lie within r (+ margin) of the ray's LINE are gathered once into a per-warp candidate list (a CTA-wide
+//      pre-filter first keeps only the points near the plane that the CTA's rays -- two image rows of one view -- span);
+//   2. marcher: lane = depth sample, loop over the candidates (broadcast loads), only over the 32-sample words that the union of the
+//      candidates' reach intervals touches;
+//   3. kNN: lane = candidate, loop over the ray's kept samples: one distance per lane, ballot, and the <= 8 nearest in canonical
+//      (distance, index) order by ranking the accepted keys against each other (a warp-wide all-pairs compare of the ~6 accepted).
+// Every (sample, point) distance is computed by the same individually rounded operations as in the other kernels, and the candidate
+// list is a superset of the points within r of any sample of the ray, so validity words, counts, neighbour lists and positions are
+// identical; the pre-filters use plain (contracted) arithmetic with explicit margins.
+constexpr int kCandMax = 128;          // per-ray candidate list (float4 per entry, 2 KB per warp); longer lists fall back
+constexpr int kRWarps = kChunk / 32;   // 8 warps per CTA
+
+// bits [lo, hi] of the 32-bit word that holds depth samples [32 j, 32 j + 31]
+__device__ __forceinline__ uint32_t range_word(int lo, int hi, int j) {
+  const int a = max(lo - 32 * j, 0), b = min(hi - 32 * j, 31);
+  return a <= b ? ((0xffffffffu >> (31 - b)) & (0xffffffffu << a)) : 0u;
+}
+
+struct RayLine {
+  float ox, oy, oz, dx, dy, dz, inv_dd;
+};
+
+// Squared reach of the pre-filters: r^2 with 2 % + 1e-4 of slack (the exact test follows, so this only has to be conservative:
+// fp32 cancellation in |v|^2 - (v.d)^2/|d|^2 is ~1e-6 for |v| <= 4).
+__device__ __forceinline__ float reach2(float radius) { return radius * radius * 1.02f + 1e-4f; }
+
+// CTA-wide pre-filter.  The rays [ray_a, ray_b) all start at `o` (one view); n = unit normal of the plane through the first and the
+// last direction, w = max over the rays of |d.n| / |d|.  A point within r of a ray point x = o + L d has
+// |(p - o).n| <= L w + r <= (|p - o| + r) w + r.  Copies the points that pass into `out` (order irrelevant), returns the count.
+// `scratch` = 8 floats of shared memory.  Falls back to "all points" when the two directions are (nearly) parallel.
+__device__ __forceinline__ int slab_prefilter(const float4* __restrict__ pts_s, int P, const float* __restrict__ dirs, long long ray_a,
+                                              long long ray_b, float ox, float oy, float oz, float radius, float4* __restrict__ out,
+                                              float* scratch, uint16_t* __restrict__ out_idx = nullptr) {
+  int* cnt_s = reinterpret_cast<int*>(scratch + 4);
+  uint32_t* w_s = reinterpret_cast<uint32_t*>(scratch + 5);
+  if (threadIdx.x == 0) {
+    const float ax = __ldg(dirs + ray_a * 3), ay = __ldg(dirs + ray_a * 3 + 1), az = __ldg(dirs + ray_a * 3 + 2);
+    const float bx = __ldg(dirs + (ray_b - 1) * 3), by = __ldg(dirs + (ray_b - 1) * 3 + 1), bz = __ldg(dirs + (ray_b - 1) * 3 + 2);
+    const float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+    const float len = sqrtf(cx * cx + cy * cy + cz * cz);
+    const float la = sqrtf(ax * ax + ay * ay + az * az), lb = sqrtf(bx * bx + by * by + bz * bz);
+    const bool ok = len > 0.05f * la * lb;  // > ~3 degrees apart
+    scratch[0] = ok ? cx / len : 0.f;
+    scratch[1] = ok ? cy / len : 0.f;
+    scratch[2] = ok ? cz / len : 0.f;
+    scratch[3] = ok ? 1.f : 0.f;
+    *cnt_s = 0;
+    *w_s = 0u;
+  }
+  __syncthreads();
+  const float nx = scratch[0], ny = scratch[1], nz = scratch[2];
+  const bool ok = scratch[3] != 0.f;
+  if (!ok) {
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+      if (out) out[i] = pts_s[i];
+      if (out_idx) out_idx[i] = (uint16_t)i;
+    }
+    __syncthreads();
+    return P;
+  }
+  float w = 0.f;
+  for (long long r = ray_a + threadIdx.x; r < ray_b; r += blockDim.x) {
+    const float dx = __ldg(dirs + r * 3), dy = __ldg(dirs + r * 3 + 1), dz = __ldg(dirs + r * 3 + 2);
+    const float dl = sqrtf(dx * dx + dy * dy + dz * dz);
+    w = fmaxf(w, dl > 0.f ? fabsf(dx * nx + dy * ny + dz * nz) / dl : 1.f);
+  }
+  w = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(w)));  // non-negative floats order like their bit patterns
+  if ((threadIdx.x & 31) == 0) atomicMax(w_s, __float_as_uint(w));
+  __syncthreads();
+  w = __uint_as_float(*w_s) * 1.001f + 1e-6f;
+  const float r_eff = sqrtf(reach2(radius));
+  for (int i0 = 0; i0 < P; i0 += blockDim.x) {
+    const int i = i0 + threadIdx.x;
+    bool keep = false;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < P) {
+      p = pts_s[i];
+      const float vx = p.x - ox, vy = p.y - oy, vz = p.z - oz;
+      const float vlen = sqrtf(vx * vx + vy * vy + vz * vz);
+      keep = fabsf(p.x) < 1e8f && fabsf(vx * nx + vy * ny + vz * nz) <= r_eff + (vlen + r_eff) * w + 1e-5f;
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    int base = 0;
+    if ((threadIdx.x & 31) == 0 && m) base = atomicAdd(cnt_s, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) {
+      const int pos = base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+      if (out) out[pos] = p;
+      if (out_idx) out_idx[pos] = (uint16_t)i;
+    }
+  }
+  __syncthreads();
+  return *cnt_s;
+}
+
+// Per-warp gather: every point of list[0, n) within reach of the line goes to cand[] (at most kCandMax are stored; the return value
+// is the full count).  kIntervals: also ORs into maybe[4] the depth samples each candidate can reach (index range [i_lo, i_hi]).
+template <bool kIntervals>
+__device__ __forceinline__ int gather_candidates(const float4* __restrict__ list, int n, const RayLine& L, float R2, float4* __restrict__ cand,
+                                                 int lane, float t0, float sc, int pad_lo, int i_lo, int i_hi, uint32_t (&maybe)[4]) {
+  int ncand = 0;
+  const uint32_t lt = (1u << lane) - 1u;
+  for (int b = 0; b < n; b += 32) {
+    const int i = b + lane;
+    bool near = false;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    float s = 0.f, perp2 = 0.f;
+    if (i < n) {
+      p = list[i];
+      const float vx = p.x - L.ox, vy = p.y - L.oy, vz = p.z - L.oz;
+      s = vx * L.dx + vy * L.dy + vz * L.dz;
+      perp2 = (vx * vx + vy * vy + vz * vz) - s * s * L.inv_dd;
+      near = perp2 <= R2 && fabsf(p.x) < 1e8f;
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, near);
+    if (m == 0u) continue;
+    if (near) {
+      const int pos = ncand + __popc(m & lt);
+      if (pos < kCandMax) cand[pos] = p;
+    }
+    ncand += __popc(m);
+    if (kIntervals) {
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+      if (near) {
+        const float tc = s * L.inv_dd, h = sqrtf(fmaxf(R2 - perp2, 0.f) * L.inv_dd);
+        const float ulo = fminf(fmaxf((tc - h - t0) * sc, -1e6f), 1e6f), uhi = fminf(fmaxf((tc + h - t0) * sc, -1e6f), 1e6f);
+        const int lo = max((int)floorf(ulo) - 1 - pad_lo, i_lo), hi = min((int)ceilf(uhi) + 1, i_hi);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = range_word(lo, hi, j);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) maybe[j] |= __reduce_or_sync(0xffffffffu, w[j]);
+    }
+  }
+  __syncwarp();
+  return ncand;
+}
+
+__global__ void __launch_bounds__(kChunk) k_march_count_r(const float* __restrict__ cam, const float* __restrict__ dirs,
+                                                          const float* __restrict__ start, const float* __restrict__ end,
+                                                          const float* __restrict__ jitter, int rays_per_view, int views_per_obj,
+                                                          int chunks_per_obj, int P, const float4* __restrict__ sorted_pts,
+                                                          const float* __restrict__ aabb, float radius, float T, int max_shading,
+                                                          uint32_t* __restrict__ valid_bits, int* __restrict__ ray_count, int rays_per_cta) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];  // [object points P float4][pre-filtered points P float4][cand: 8 x kCandMax float4]
+  __shared__ float step_tab[kDepthRes];
+  __shared__ float scratch[8];
+  float4* pts_s = reinterpret_cast<float4*>(smem_raw);
+  float4* cta_s = pts_s + P;
+  float4* cand_all = cta_s + P;
+  const int obj = blockIdx.x / chunks_per_obj, chunk = blockIdx.x % chunks_per_obj;
+  const long long rays_per_obj = (long long)rays_per_view * views_per_obj;
+  const long long ray0 = obj * rays_per_obj + (long long)chunk * rays_per_cta;
+  const int n_local = (int)min((long long)rays_per_cta, rays_per_obj - (long long)chunk * rays_per_cta);
+  for (int i = threadIdx.x; i < P; i += blockDim.x) pts_s[i] = __ldg(sorted_pts + (size_t)obj * P + i);
+  for (int i = threadIdx.x; i < kDepthRes; i += blockDim.x) step_tab[i] = __fdiv_rn((float)i, (float)(kDepthRes - 1));
+  __syncthreads();
+  // CTA-wide pre-filter when all rays of the chunk belong to one view (the usual case: a chunk is a run of image rows)
+  const int view_a = (int)(ray0 / rays_per_view), view_b = (int)((ray0 + n_local - 1) / rays_per_view);
+  const float4* list = pts_s;
+  int n_list = P;
+  if (view_a == view_b && n_local >= 2) {
+    n_list = slab_prefilter(pts_s, P, dirs, ray0, ray0 + n_local, __ldg(cam + view_a * 3), __ldg(cam + view_a * 3 + 1),
+                            __ldg(cam + view_a * 3 + 2), radius, cta_s, scratch);
+    list = cta_s;
+  }
+  auto depth_of = [&](float t0, float t1, int i, const float* jit) {
+    const float span = __fsub_rn(t1, t0);
+    float t = __fadd_rn(t0, __fmul_rn(step_tab[i], span));
+    if (jit) t = __fadd_rn(t, __fmul_rn(jit[i], __fdiv_rn(span, (float)(kDepthRes - 1))));
+    return t;
+  };
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  float4* cand = cand_all + warp * kCandMax;
+  const float R2 = reach2(radius);
+  for (int g0 = warp * 32; g0 < n_local; g0 += n_warps * 32) {  // 32 rays per warp and round: lane-per-ray set-up, then warp-per-ray
+    const int r_mine = g0 + lane;
+    const bool has_ray = r_mine < n_local;
+    float ox = 0.f, oy = 0.f, oz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f, t0 = 0.f, t1 = 0.f;
+    int i_lo = 0, i_hi = -1;
+    if (has_ray) {
+      const long long ray = ray0 + r_mine;
+      const int view = (int)(ray / rays_per_view);
+      ox = __ldg(cam + view * 3), oy = __ldg(cam + view * 3 + 1), oz = __ldg(cam + view * 3 + 2);
+      dx = __ldg(dirs + ray * 3), dy = __ldg(dirs + ray * 3 + 1), dz = __ldg(dirs + ray * 3 + 2);
+      t0 = __ldg(start + ray), t1 = __ldg(end + ray);
+      i_hi = kDepthRes - 1;  // conservative sample range inside the object's box (see k_march_count)
+      if (aabb) {
+        const float* bx = aabb + (size_t)obj * 6;
+        float tmin = -INFINITY, tmax = INFINITY;
+        bool miss = false;
+        const float o3[3] = {ox, oy, oz}, d3[3] = {dx, dy, dz};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const float lo = __ldg(bx + a), hi = __ldg(bx + 3 + a);
+          if (fabsf(d3[a]) < 1e-12f) {
+            miss |= (o3[a] < lo || o3[a] > hi);
+          } else {
+            const float inv = 1.0f / d3[a];
+            const float ta = (lo - o3[a]) * inv, tb = (hi - o3[a]) * inv;
+            tmin = fmaxf(tmin, fminf(ta, tb));
+            tmax = fminf(tmax, fmaxf(ta, tb));
+          }
+        }
+        const float span = t1 - t0;
+        if (miss || tmin > tmax || !(span > 0.f)) {
+          if (miss || tmin > tmax) i_hi = -1;
+        } else {
+          const float sc = (float)(kDepthRes - 1) / span;
+          const float flo = (tmin - t0) * sc - 2.0f, fhi = (tmax - t0) * sc + 2.0f;
+          i_lo = flo <= 0.f ? 0 : (flo >= (float)kDepthRes ? kDepthRes : (int)flo);
+          i_hi = fhi >= (float)(kDepthRes - 1) ? kDepthRes - 1 : (fhi < 0.f ? -1 : (int)fhi + 1);
+          i_hi = min(i_hi, kDepthRes - 1);
+        }
+      }
+    }
+    uint32_t res[4] = {0u, 0u, 0u, 0u};  // validity words of this lane's ray
+    uint32_t todo = __ballot_sync(0xffffffffu, has_ray && i_hi >= i_lo);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      RayLine L;
+      L.ox = __shfl_sync(0xffffffffu, ox, src), L.oy = __shfl_sync(0xffffffffu, oy, src), L.oz = __shfl_sync(0xffffffffu, oz, src);
+      L.dx = __shfl_sync(0xffffffffu, dx, src), L.dy = __shfl_sync(0xffffffffu, dy, src), L.dz = __shfl_sync(0xffffffffu, dz, src);
+      const float rt0 = __shfl_sync(0xffffffffu, t0, src), rt1 = __shfl_sync(0xffffffffu, t1, src);
+      const int r_lo = __shfl_sync(0xffffffffu, i_lo, src), r_hi = __shfl_sync(0xffffffffu, i_hi, src);
+      const float* jit = jitter ? jitter + (ray0 + g0 + src) * kDepthRes : nullptr;
+      const float dd = L.dx * L.dx + L.dy * L.dy + L.dz * L.dz, span = rt1 - rt0;
+      const bool regular = dd > 1e-20f && span > 0.f;  // otherwise: every point is a candidate, every sample of the range is tested
+      L.inv_dd = regular ? 1.0f / dd : 0.f;
+      uint32_t maybe[4] = {0u, 0u, 0u, 0u};
+      int ncand = gather_candidates<true>(list, n_list, L, regular ? R2 : INFINITY, cand, lane, rt0,
+                                          regular ? (float)(kDepthRes - 1) / span : 0.f, jit ? 1 : 0, r_lo, r_hi, maybe);
+      const float4* cl = cand;
+      if (ncand > kCandMax || !regular) {  // overflow / degenerate ray: test against the whole (pre-filtered) list
+        cl = list;
+        ncand = n_list;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) maybe[j] = range_word(r_lo, r_hi, j);
+      }
+      uint32_t words[4] = {0u, 0u, 0u, 0u};
+      if (ncand > 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (maybe[j] == 0u) continue;  // warp-uniform
+          const int i = j * 32 + lane;
+          const float t = depth_of(rt0, rt1, i, jit);
+          const float x = axpy_rn(L.ox, t, L.dx), y = axpy_rn(L.oy, t, L.dy), z = axpy_rn(L.oz, t, L.dz);
+          bool hit = false;
+#pragma unroll 4
+          for (int c = 0; c < ncand; ++c) {
+            const float4 p = cl[c];  // same address in every lane: broadcast
+            const float ex = __fsub_rn(x, p.x), ey = __fsub_rn(y, p.y), ez = __fsub_rn(z, p.z);
+            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
+            hit |= d2 <= T;
+          }
+          words[j] = __ballot_sync(0xffffffffu, hit && ((maybe[j] >> lane) & 1u));
+        }
+      }
+      if (lane == src) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) res[j] = words[j];
+      }
+      __syncwarp();  // cand[] is rewritten by the next ray
+    }
+    if (has_ray) {
+      const long long ray = ray0 + r_mine;
+      *reinterpret_cast<uint4*>(valid_bits + ray * 4) = make_uint4(res[0], res[1], res[2], res[3]);
+      ray_count[ray] = min(__popc(res[0]) + __popc(res[1]) + __popc(res[2]) + __popc(res[3]), max_shading);
+    }
+  }
+}
+
+// kNN fill, ray-coherent version 2 (version 1 -- lane = candidate, per-sample ballot + all-pairs ranking -- was correct and 2x
+// SLOWER than the thread-per-sample kernel: ~390 issue slots per sample, a serial chain of two shared-memory round trips and three
+// warp syncs per sample).  Phase A, warp per ray: the ray's candidate list (indices into the pre-filtered point list) goes to a CTA
+// pool.  Phase B, thread per kept sample exactly like k_knn_fill_s, but the scan walks its RAY's list (~25 entries, the same for
+// the 1-3 rays a warp covers, so the lanes stay converged) instead of the 9 row ranges of its own 27-cell neighbourhood
+// (~35 points, 18 range loads and a different trip count in every lane).
+constexpr int kPool = 8192;     // candidate indices per CTA (u16); rays that do not fit fall back to the generic scan
+constexpr int kRayListMax = 128;
+
+// selection half of select_and_store_s: the <= 8 nearest of the `cnt` (<= kCand) accepted entries of this thread's columns
+__device__ __forceinline__ void select_from_columns(int cnt, const float* __restrict__ cand_d2, const uint16_t* __restrict__ cand_idx, int base,
+                                                    int* __restrict__ out) {
+#define NPCD_CE2(a, b)                                    \
+  {                                                       \
+    const unsigned long long lo_ = min(best[a], best[b]); \
+    best[b] = max(best[a], best[b]);                      \
+    best[a] = lo_;                                        \
+  }
+  unsigned long long best[kK];
+  auto key_of = [&](int en) {
+    return ((unsigned long long)__float_as_uint(__fsqrt_rn(cand_d2[en * kChunk])) << 32) | (unsigned)cand_idx[en * kChunk];
+  };
+#pragma unroll
+  for (int j = 0; j < kK; ++j) best[j] = j < cnt ? key_of(j) : ~0ull;
+  NPCD_CE2(0, 2) NPCD_CE2(1, 3) NPCD_CE2(4, 6) NPCD_CE2(5, 7)
+  NPCD_CE2(0, 4) NPCD_CE2(1, 5) NPCD_CE2(2, 6) NPCD_CE2(3, 7)
+  NPCD_CE2(0, 1) NPCD_CE2(2, 3) NPCD_CE2(4, 5) NPCD_CE2(6, 7)
+  NPCD_CE2(2, 4) NPCD_CE2(3, 5)
+  NPCD_CE2(1, 4) NPCD_CE2(3, 6)
+  NPCD_CE2(1, 2) NPCD_CE2(3, 4) NPCD_CE2(5, 6)
+#pragma unroll 1
+  for (int en = kK; en < cnt; ++en) {
+    unsigned long long cur = key_of(en);
+    if (cur < best[kK - 1]) {
+#pragma unroll
+      for (int j = 0; j < kK; ++j) {
+        const unsigned long long bj = best[j];
+        const bool sw = cur < bj;
+        best[j] = sw ? cur : bj;
+        cur = sw ? bj : cur;
+      }
+    }
+  }
+  int tmp[kK];
+#pragma unroll
+  for (int j = 0; j < kK; ++j) tmp[j] = best[j] == ~0ull ? -1 : base + (int)(best[j] & 0xffffffffu);
+  reinterpret_cast<int4*>(out)[0] = make_int4(tmp[0], tmp[1], tmp[2], tmp[3]);
+  reinterpret_cast<int4*>(out)[1] = make_int4(tmp[4], tmp[5], tmp[6], tmp[7]);
+#undef NPCD_CE2
+}
+
+__global__ void __launch_bounds__(kChunk) k_knn_fill_r(const float* __restrict__ cam, const float* __restrict__ dirs,
+                                                       const float* __restrict__ start, const float* __restrict__ end,
+                                                       const float* __restrict__ jitter, const int* __restrict__ ray_ids, long long n_sel,
+                                                       const long long* __restrict__ ray_offset, const uint32_t* __restrict__ valid_bits,
+                                                       int rays_per_view, int views_per_obj, int P, const int* __restrict__ cell_start,
+                                                       const float4* __restrict__ sorted_pts, float radius, float T, long long capacity,
+                                                       int* __restrict__ nbr_idx, float4* __restrict__ sample_pos,
+                                                       float* __restrict__ sample_t, int* __restrict__ sample_ray, int rays_per_cta) {
+  // [object points P float4][cand_d2 kCand x 256 f32][cand_idx kCand x 256 u16][pool kPool u16][per-warp gather buffer 8 x
+  // kRayListMax u16][pre-filtered point numbers P u16]
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ int off_s[kChunk + 1];
+  __shared__ uint16_t list_start[kChunk], list_count[kChunk];  // count 0xffff: no list (pool or gather buffer full) -> generic scan
+  __shared__ float scratch[8];
+  __shared__ int pool_used;
+  float4* pts_s = reinterpret_cast<float4*>(smem_raw);
+  float* cand_d2 = reinterpret_cast<float*>(pts_s + P);
+  uint16_t* cand_idx = reinterpret_cast<uint16_t*>(cand_d2 + kCand * kChunk);
+  uint16_t* pool = cand_idx + kCand * kChunk;
+  uint16_t* gbuf_all = pool + kPool;
+  uint16_t* cta_idx = gbuf_all + kRWarps * kRayListMax;  // numbers (into pts_s) of the points that pass the CTA-wide pre-filter
+  const long long sel0 = (long long)blockIdx.x * rays_per_cta;
+  const int n_local = (int)min((long long)rays_per_cta, n_sel - sel0);
+  const long long S = min(__ldg(ray_offset + n_sel), capacity);
+  const long long s0 = min(__ldg(ray_offset + sel0), S), s1 = min(__ldg(ray_offset + sel0 + n_local), S);
+  if (s1 <= s0) return;  // no kept sample in this chunk (uniform for the CTA)
+  const long long rays_per_obj = (long long)rays_per_view * views_per_obj;
+  const long long first_ray = ray_ids ? (long long)ray_ids[sel0] : sel0;
+  const int obj0 = (int)(first_ray / rays_per_obj);
+  for (int i = threadIdx.x; i < P; i += blockDim.x) pts_s[i] = __ldg(sorted_pts + (size_t)obj0 * P + i);
+  for (int i = threadIdx.x; i <= n_local; i += blockDim.x) off_s[i] = (int)(min(__ldg(ray_offset + sel0 + i), S) - s0);
+  if (threadIdx.x == 0) pool_used = 0;
+  __syncthreads();
+  int n_list = P;
+  if (!ray_ids && n_local >= 2 && sel0 / rays_per_view == (sel0 + n_local - 1) / rays_per_view) {
+    const int v = (int)(sel0 / rays_per_view);
+    n_list = slab_prefilter(pts_s, P, dirs, sel0, sel0 + n_local, __ldg(cam + v * 3), __ldg(cam + v * 3 + 1), __ldg(cam + v * 3 + 2), radius,
+                            nullptr, scratch, cta_idx);
+  } else {
+    for (int i = threadIdx.x; i < P; i += blockDim.x) cta_idx[i] = (uint16_t)i;
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  // ---- phase A: candidate list of every ray that has kept samples (warp per ray) ----
+  {
+    uint16_t* gbuf = gbuf_all + warp * kRayListMax;
+    const float R2 = reach2(radius);
+    for (int r = warp; r < n_local; r += n_warps) {
+      if (off_s[r + 1] - off_s[r] <= 0) continue;  // warp-uniform
+      const long long sel = sel0 + r;
+      const long long ray = ray_ids ? (long long)__ldg(ray_ids + sel) : sel;
+      const int view = (int)(ray / rays_per_view);
+      int ncand = kRayListMax + 1;  // rays of another object (chunk straddles two objects): generic scan
+      if (view / views_per_obj == obj0) {
+        const float ox = __ldg(cam + view * 3), oy = __ldg(cam + view * 3 + 1), oz = __ldg(cam + view * 3 + 2);
+        const float dx = __ldg(dirs + ray * 3), dy = __ldg(dirs + ray * 3 + 1), dz = __ldg(dirs + ray * 3 + 2);
+        const float dd = dx * dx + dy * dy + dz * dz;
+        const float inv_dd = dd > 1e-20f ? 1.0f / dd : 0.f, reach = dd > 1e-20f ? R2 : INFINITY;
+        ncand = 0;
+        for (int b = 0; b < n_list; b += 32) {
+          const int i = b + lane;
+          bool near = false;
+          uint16_t pi = 0;
+          if (i < n_list) {
+            pi = cta_idx[i];
+            const float4 p = pts_s[pi];
+            const float vx = p.x - ox, vy = p.y - oy, vz = p.z - oz;
+            const float sp = vx * dx + vy * dy + vz * dz;
+            near = (vx * vx + vy * vy + vz * vz) - sp * sp * inv_dd <= reach && fabsf(p.x) < 1e8f;
+          }
+          const uint32_t m = __ballot_sync(0xffffffffu, near);
+          if (near) {
+            const int pos = ncand + __popc(m & lt);
+            if (pos < kRayListMax) gbuf[pos] = pi;
+          }
+          ncand += __popc(m);
+        }
+      }
+      int base = 0;
+      const bool fits = ncand <= kRayListMax;
+      if (lane == 0 && fits) base = atomicAdd(&pool_used, ncand);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      const bool ok = fits && base + ncand <= kPool;
+      __syncwarp();
+      if (ok)
+        for (int c = lane; c < ncand; c += 32) pool[base + c] = gbuf[c];
+      if (lane == 0) {
+        list_start[r] = (uint16_t)(ok ? base : 0);
+        list_count[r] = (uint16_t)(ok ? ncand : 0xffff);
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // ---- phase B: thread per kept sample ----
+  const int n_samples = (int)(s1 - s0);
+  for (int sl = threadIdx.x; sl < n_samples; sl += blockDim.x) {
+    int lo = 0, hi = n_local;  // upper_bound(off_s, sl) - 1
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (off_s[mid] <= sl) lo = mid; else hi = mid;
+    }
+    const long long sel = sel0 + lo;
+    const long long ray = ray_ids ? (long long)ray_ids[sel] : sel;
+    int rank = sl - off_s[lo];
+    int i = 0;
+    const uint4 vb = __ldg(reinterpret_cast<const uint4*>(valid_bits + ray * 4));
+    const uint32_t w4[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int pc = __popc(w4[j]);
+      if (rank >= 0 && rank < pc) { i = j * 32 + nth_set_bit(w4[j], rank); rank = -1; }
+      else if (rank >= 0) rank -= pc;
+    }
+    const int view = (int)(ray / rays_per_view);
+    const int obj = view / views_per_obj;
+    const float ox = __ldg(cam + view * 3), oy = __ldg(cam + view * 3 + 1), oz = __ldg(cam + view * 3 + 2);
+    const float dx = __ldg(dirs + ray * 3), dy = __ldg(dirs + ray * 3 + 1), dz = __ldg(dirs + ray * 3 + 2);
+    const float t = sample_depth(__ldg(start + ray), __ldg(end + ray), i, jitter ? jitter + ray * kDepthRes : nullptr);
+    const float x = axpy_rn(ox, t, dx), y = axpy_rn(oy, t, dy), z = axpy_rn(oz, t, dz);
+    const long long s = s0 + sl;
+    const int n_c = list_count[lo];
+    bool done = false;
+    if (n_c != 0xffff) {
+      const uint16_t* cl = pool + list_start[lo];
+      float* my_d2 = cand_d2 + threadIdx.x;
+      uint16_t* my_idx = cand_idx + threadIdx.x;
+      int cnt = 0;
+#pragma unroll 2
+      for (int c = 0; c < n_c; ++c) {
+        const float4 p = pts_s[cl[c]];
+        const float ex = __fsub_rn(x, p.x), ey = __fsub_rn(y, p.y), ez = __fsub_rn(z, p.z);
+        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
+        if (d2 <= T) {
+          if (cnt < kCand) {
+            my_d2[cnt * kChunk] = d2;
+            my_idx[cnt * kChunk] = (uint16_t)__float_as_int(p.w);
+          }
+          ++cnt;
+        }
+      }
+      if (cnt <= kCand) {
+        select_from_columns(cnt, my_d2, my_idx, obj * P, nbr_idx + s * kK);
+        done = true;
+      }
+    }
+    if (!done)  // ray without a list (other object, very long list, pool full) or > kCand points within r
+      select_and_store_foreign(cell_start + (size_t)obj * (kGridCells + 1), sorted_pts + (size_t)obj * P, x, y, z, radius, obj * P,
+                               nbr_idx + s * kK);
+    const float q0 = __fdiv_rn(__fsub_rn(x, ox), dx), q1 = __fdiv_rn(__fsub_rn(y, oy), dy), q2 = __fdiv_rn(__fsub_rn(z, oz), dz);
+    float sum = 0.f, n_ok = 0.f;
+    if (q0 == q0) { sum = __fadd_rn(sum, q0); n_ok += 1.f; }
+    if (q1 == q1) { sum = __fadd_rn(sum, q1); n_ok += 1.f; }
+    if (q2 == q2) { sum = __fadd_rn(sum, q2); n_ok += 1.f; }
+    sample_pos[s] = make_float4(x, y, z, __fdiv_rn(sum, n_ok));
+    if (sample_t) sample_t[s] = __fdiv_rn(sum, n_ok);
+    if (sample_ray) sample_ray[s] = (int)sel;
+  }
+}
+
 // rays per CTA: kChunk for big launches; small launches (training: a few thousand rays) are split finer so every SM gets work
 static int rays_per_cta_for(long long n) {
   long long r = (n + 148 * 8 - 1) / (148 * 8);
@@ -649,9 +1162,20 @@ extern "C" int npcd_march_count(const float* cam_centers, const float* dirs, con
   NPCD_CHECK_ARG(max_shading_pts > 0 && max_shading_pts <= kDepthRes, "max_shading_pts must be in [1,128]");
   NPCD_CHECK_ARG(radius > 0.f && radius <= 2.0f / kGrid, "radius must be in (0, 1/12] (grid cell edge)");
   if (n_rays == 0) return 0;
-  NPCD_CHECK_ARG(impl >= 0 && impl <= 2, "impl must be 0 (auto), 1 (global-memory kernels) or 2 (shared-memory kernels)");
+  NPCD_CHECK_ARG(impl >= 0 && impl <= 3, "impl must be 0 (auto), 1 (global-memory kernels), 2 (shared-memory kernels) or 3 (ray-coherent kernels)");
   const long long rays_per_obj = (long long)rays_per_view * views_per_obj;
-  if (impl == 2) NPCD_CHECK_ARG(n_points <= kSmemMaxPoints && n_rays % rays_per_obj == 0, "shared-memory kernels: n_points <= 2048, whole objects");
+  if (impl >= 2) NPCD_CHECK_ARG(n_points <= kSmemMaxPoints && n_rays % rays_per_obj == 0, "shared-memory kernels: n_points <= 2048, whole objects");
+  if (impl == 3) {  // ray-coherent kernel (warp per ray, per-ray candidate list)
+    const int rpc = rays_per_cta_for(n_rays);
+    const int chunks_per_obj = (int)((rays_per_obj + rpc - 1) / rpc);
+    const long long n_obj = n_rays / rays_per_obj;
+    const size_t smem = (size_t)n_points * 32 + (size_t)kRWarps * kCandMax * 16;
+    cudaFuncSetAttribute(k_march_count_r, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_march_count_r<<<(unsigned)(n_obj * chunks_per_obj), kChunk, smem, (cudaStream_t)stream>>>(
+        cam_centers, dirs, ray_start, ray_end, jitter, rays_per_view, views_per_obj, chunks_per_obj, n_points, (const float4*)sorted_pts,
+        aabb, radius, radius_threshold(radius), max_shading_pts, valid_bits, ray_count, rpc);
+    return check_launch("npcd_march_count");
+  }
   if (impl != 1 && n_points <= kSmemMaxPoints && n_rays % rays_per_obj == 0) {
     const int rpc = rays_per_cta_for(n_rays);
     const int chunks_per_obj = (int)((rays_per_obj + rpc - 1) / rpc);
@@ -682,9 +1206,19 @@ extern "C" int npcd_knn_fill(const float* cam_centers, const float* dirs, const 
   NPCD_CHECK_ARG(capacity == 0 || (nbr_idx && sample_pos), "null output with capacity > 0");
   NPCD_CHECK_ARG(n_sel >= 0 && capacity >= 0, "bad sizes");
   if (n_sel == 0 || capacity == 0) return 0;
-  NPCD_CHECK_ARG(impl >= 0 && impl <= 2, "impl must be 0 (auto), 1 (global-memory kernels) or 2 (shared-memory kernels)");
+  NPCD_CHECK_ARG(impl >= 0 && impl <= 3, "impl must be 0 (auto), 1 (global-memory kernels), 2 (shared-memory kernels) or 3 (ray-coherent kernels)");
   NPCD_CHECK_ARG(radius > 0.f && radius <= 2.0f / kGrid, "radius must be in (0, 1/12] (grid cell edge)");
-  if (impl == 2) NPCD_CHECK_ARG(n_points <= kSmemMaxPoints, "shared-memory kernels: n_points <= 2048");
+  if (impl >= 2) NPCD_CHECK_ARG(n_points <= kSmemMaxPoints, "shared-memory kernels: n_points <= 2048");
+  if (impl == 3) {
+    const size_t smem = (size_t)n_points * 18 + (size_t)kChunk * kCand * 6 + (size_t)kPool * 2 + (size_t)kRWarps * kRayListMax * 2;
+    cudaFuncSetAttribute(k_knn_fill_r, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int rpc = rays_per_cta_for(n_sel);
+    k_knn_fill_r<<<(unsigned)((n_sel + rpc - 1) / rpc), kChunk, smem, (cudaStream_t)stream>>>(
+        cam_centers, dirs, ray_start, ray_end, jitter, ray_ids, n_sel, ray_offset, valid_bits, rays_per_view, views_per_obj, n_points,
+        cell_start, (const float4*)sorted_pts, radius, radius_threshold(radius), capacity, nbr_idx, (float4*)sample_pos, sample_t,
+        sample_ray, rpc);
+    return check_launch("npcd_knn_fill");
+  }
   if (impl != 1 && n_points <= kSmemMaxPoints) {
     const size_t smem = (size_t)n_points * 16 + (size_t)kChunk * (kCand * 6 + 9 * 4);
     cudaFuncSetAttribute(k_knn_fill_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -166,15 +167,16 @@ def grid_build(kp_pos) -> Grid:
     return g
 
 
-# 0 = auto (shared-memory kernels when n_points <= 2048), 1 = generic global-memory kernels, 2 = shared-memory kernels; tests flip
-# this to cross-check the two implementations bit for bit
-QUERY_IMPL = 0
+# 0 = auto, 1 = generic global-memory kernels, 2 = shared-memory thread-per-sample kernels (n_points <= 2048), 3 = ray-coherent
+# warp-per-ray kernels (n_points <= 2048); tests flip this to cross-check the implementations bit for bit (NPCD_QUERY_IMPL: the same
+# from the environment, development aid)
+QUERY_IMPL = int(os.environ.get("NPCD_QUERY_IMPL", "0"))
 USE_FINE_MASKS = True
 
 
 def grid_masks(grid: Grid, radius: float):
     """Sub-cell (sure, maybe) masks of the marcher for ``radius`` (built once per grid and radius)."""
-    if not USE_FINE_MASKS or QUERY_IMPL == 1 or grid.n_points > 2048:
+    if not USE_FINE_MASKS or QUERY_IMPL in (1, 3) or grid.n_points > 2048:
         return None
     if grid.masks is None or grid.mask_radius != float(radius):
         cells, _ = grid_dims()

@@ -977,7 +977,7 @@ def test_query_kernel_variants_agree_bit_for_bit(kind, train, syn, cameras, torc
     jitter = torch.rand((N, R, 128), device="cuda", generator=torch.Generator(device="cuda").manual_seed(1)) if train else None
     results = {}
     try:
-        for tag, impl, masks in (("generic", 1, False), ("smem", 2, False), ("smem+masks", 2, True)):
+        for tag, impl, masks in (("generic", 1, False), ("smem", 2, False), ("smem+masks", 2, True), ("ray", 3, False)):
             ops.QUERY_IMPL, ops.USE_FINE_MASKS = impl, masks
             grid = ops.grid_build(_t(torch, coords))
             vb, cnt = ops.march_count(rays, grid, T, 0.08, 50, jitter)
@@ -994,7 +994,7 @@ def test_query_kernel_variants_agree_bit_for_bit(kind, train, syn, cameras, torc
     ref = results["generic"]
     assert int(ref[2][-1].item()) > 100_000 or train
     assert int(ref[1].max()) == (50 if kind == "box" else int(ref[1].max()))
-    for tag in ("smem", "smem+masks"):
+    for tag in ("smem", "smem+masks", "ray"):
         for name, a, b in zip(("valid_bits", "ray_count", "ray_offset", "nbr_idx", "sample_pos", "sample_ray"), ref, results[tag]):
             assert torch.equal(a, b), (tag, name)
 
