@@ -199,8 +199,11 @@ int npcd_tc_linear_probe(const void* image, const long long* n_rows_dev, long lo
  * A layer is then ONE kind::f16 product plus TWO kind::f8f6f4 products (twice the tensor rate) into the same fp32 accumulator:
  * relative error ~2^-16 per product instead of 2^-22, measured well inside the 1e-4 bar on RGB (tests/test_gpu_precision.py).
  * Same sizes and call shapes as the format-0 functions above.                                                                       */
-/* development aid: CTA 0 of the inference pair kernel records clock64() at its phase boundaries into buf [64][32] int64 (NULL = off) */
+/* development aid: CTA 0 of the inference pair kernel records clock64() at its phase boundaries into buf [64][32] int64 (NULL = off);
+ * _heads: the same for the inference heads kernel (events: 2 l / 2 l + 1 = epilogue of layer l waits / has its accumulator,
+ * 10 = tile done, 16 + 3 l .. 18 + 3 l = MMA issuer of layer l < 4: start / first operand there / last MMA issued) */
 int npcd_debug_set_timeline(void* buf);
+int npcd_debug_set_timeline_heads(void* buf);
 int npcd_tc_pack_weights_f8(const float* w, int k_in, const int* perm, int k_pad /* multiple of 32 */, float scale, void* out, void* stream);
 int npcd_tc_rows_to_image_f8(const float* rows, long long n, void* image, void* stream);
 int npcd_tc_image_to_rows_f8(const void* image, long long n, float* rows, void* stream);

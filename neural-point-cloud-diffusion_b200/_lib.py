@@ -110,6 +110,7 @@ SIGNATURES = {
     "npcd_tc_pack_weights": [P, I, P, I, F, P, P],
     "npcd_tc_pack_weights_batched": [P, I, P],
     "npcd_debug_set_timeline": [P],
+    "npcd_debug_set_timeline_heads": [P],
     "npcd_tc_pack_weights_f8": [P, I, P, I, F, P, P],
     "npcd_tc_rows_to_image_f8": [P, L, P, P],
     "npcd_tc_image_to_rows_f8": [P, L, P, P],

@@ -1176,7 +1176,9 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
       // 1 or 3 output weight vectors; the two threads of a row combine through shared memory.
       auto epilogue_dot = [&](int l, int nout, float (&res)[3]) {
         const uint32_t ab = lc & 1u;
+        if (et == 0) NPCD_TL(tl_it, 2 * l);
         wait_acc(ab);
+        if (et == 0) NPCD_TL(tl_it, 2 * l + 1);
         const float inv = P.layers[l].inv_scale;
         const uint32_t t_acc = t_row + ab * 256u;
         float acc3[3] = {0.f, 0.f, 0.f};
@@ -1285,6 +1287,8 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
           for (int o = 0; o < 3; ++o) rgb[o] = 1.0f / (1.0f + expf(-(res[o] + P.chan_out_b[o])));
           P.rgbs[s] = make_float4(rgb[0], rgb[1], rgb[2], sigma);
         }
+        if (et == 0) NPCD_TL(tl_it, 10);
+        ++tl_it;
       }
     }
   }
@@ -1617,12 +1621,13 @@ void fill_layer(tc::Params& P, int i, const npcd_tc_layer& src, int epi, bool f8
 }
 
 long long* g_timeline = nullptr;
+long long* g_timeline_heads = nullptr;
 
 template <int kMode, bool kF8 = false>
 int launch_tc(const tc::Params& P_in, long long tiles, int num_sms, cudaStream_t st, const char* what) {
   static thread_local tc::Params P;
   P = P_in;
-  P.timeline = kMode == tc::MODE_PAIR ? g_timeline : nullptr;
+  P.timeline = kMode == tc::MODE_PAIR ? g_timeline : (kMode == tc::MODE_HEADS ? g_timeline_heads : nullptr);
   cudaError_t e = cudaFuncSetAttribute(tc::k_field_tc<kMode, kF8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal);
   if (e != cudaSuccess) {
     set_error("%s: cannot opt in to %d bytes of shared memory: %s", what, tc::kSmemTotal, cudaGetErrorString(e));
@@ -1715,6 +1720,10 @@ int heads_stage(const npcd_mlp_tc_weights* W, uint8_t* img, float* rgbs, float* 
 // development aid: the inference pair kernel's CTA 0 records clock64() at its phase boundaries into buf [64 tiles][32] (null: off)
 extern "C" int npcd_debug_set_timeline(void* buf) {
   g_timeline = (long long*)buf;
+  return 0;
+}
+extern "C" int npcd_debug_set_timeline_heads(void* buf) {
+  g_timeline_heads = (long long*)buf;
   return 0;
 }
 
