@@ -895,11 +895,17 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
       const float inv = P.layers[l].inv_scale;
       const uint32_t t_acc = t_row + ab * 256u;
       uint32_t v[2][32];
-      tmem_ld32_async(t_acc + half * 32, v[0]);
-      tmem_wait(v[0]);
+      constexpr bool kSplitLd = kSplit0 && !NPCD_EXP_NOSPLITLD;
+      if (kSplitLd) {  // first chunk in two 16-column loads, the second one issued AFTER the first half is published (tmem_ld16_async)
+        tmem_ld16_async(t_acc + half * 32, &v[0][0]);
+        tmem_wait16(&v[0][0]);
+      } else {
+        tmem_ld32_async(t_acc + half * 32, v[0]);
+        tmem_wait(v[0]);
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        if (i < 3) tmem_ld32_async(t_acc + (2 * (i + 1) + half) * 32, v[(i + 1) & 1]);
+        if (i < 3 && !(kSplitLd && i == 0)) tmem_ld32_async(t_acc + (2 * (i + 1) + half) * 32, v[(i + 1) & 1]);
         stash_wait(i);
         uint32_t* mptr = nullptr;
         if (kTrainP) mptr = P.stash_mask[l] + ((size_t)tile_now * 128 + row) * 8 + (2 * i + half);
@@ -907,6 +913,11 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
         if (kSplit0 && i == 0) {
           epi_chunk_store<kF8, 0, 2>(P, l, inv, slope, v[0], half * 32, sA, rowbase, x7, feat_row, nullptr);
           publish(kBarARdy + 0);
+          if (kSplitLd) {
+            tmem_ld16_async(t_acc + half * 32 + 16, &v[0][16]);
+            tmem_ld32_async(t_acc + (2 + half) * 32, v[1]);
+            tmem_wait16(&v[0][16]);
+          }
           epi_chunk_store<kF8, 2, 4>(P, l, inv, slope, v[0], half * 32, sA, rowbase, x7, feat_row, nullptr);
           publish(kBarARdy2);
         } else {

@@ -9,6 +9,9 @@
 #ifndef NPCD_EXP_NSPLIT
 #define NPCD_EXP_NSPLIT 0    // experiment (results stay correct): every M128 N256 MMA issued as two N = 128 MMAs
 #endif
+#ifndef NPCD_EXP_NOSPLITLD
+#define NPCD_EXP_NOSPLITLD 0 // 1: the first accumulator chunk of a layer epilogue is loaded with one 32-column tcgen05.ld (round-2 start)
+#endif
 #ifndef NPCD_EXP_NOREFILL
 #define NPCD_EXP_NOREFILL 0  // timing-only ablation: the weight producer signals the ring stages without copying anything
 #endif
@@ -218,6 +221,27 @@ __device__ __forceinline__ void tmem_wait(uint32_t (&v)[32]) {
                  "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
                  "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
                  "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
+
+// 16-column variants (the layer epilogues of the inference kernels load the first chunk of an accumulator in two halves: ptxas
+// keeps every use of a tcgen05.ld destination behind the tcgen05.wait::ld that follows it, which is the only way to keep the second
+// half's arithmetic from being scheduled in front of the first half's operand-ready arrive -- a register-only asm fence is invisible
+// to ptxas)
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait16(uint32_t* v) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
                :
                : "memory");
 }
