@@ -42,12 +42,17 @@ def have_nvcc() -> bool:
 
 
 def _digest(paths) -> str:
+    """Content digest of the sources + build switches.  File NAMES (not absolute paths) and the flags without the include
+    directories go in, so the stamp of a library built in one checkout still matches after the tree is copied elsewhere (gpurun
+    ships the built .so to a scratch path: hashing absolute paths made every fresh box rebuild at first import -- and two ranks of a
+    torchrun job race on that rebuild)."""
     h = hashlib.sha256()
-    for p in sorted(paths):
-        h.update(p.encode())
+    for p in sorted(paths, key=os.path.basename):
+        h.update(os.path.basename(p).encode())
         with open(p, "rb") as f:
             h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    flags = [f for f in NVCC_FLAGS if f not in (INCLUDE, CSRC)]
+    h.update(" ".join(flags).encode())
     return h.hexdigest()
 
 
@@ -57,8 +62,27 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
     stamp = os.path.join(OBJ_DIR, "stamp.txt")
     digest = _digest(sources + headers)
-    if not force and os.path.isfile(LIB) and os.path.isfile(stamp) and open(stamp).read() == digest:
+
+    def up_to_date() -> bool:
+        return os.path.isfile(LIB) and os.path.isfile(stamp) and open(stamp).read() == digest
+
+    if not force and up_to_date():
         return LIB
+    # one builder at a time (ranks of a multi-process job import the package simultaneously); whoever waited re-checks the stamp
+    import fcntl
+
+    lock = open(os.path.join(OBJ_DIR, "build.lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and up_to_date():
+            return LIB
+        return _build_locked(sources, stamp, digest, verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(sources, stamp, digest, verbose) -> str:
     nvcc = _nvcc()
     objs, procs = [], []
     for src in sources:
@@ -74,7 +98,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"])
+    tmp = LIB + f".tmp{os.getpid()}"  # link next to the target, then rename: a concurrent reader never sees a partial file
+    subprocess.check_call([nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"])
+    os.replace(tmp, LIB)
     with open(stamp, "w") as f:
         f.write(digest)
     return LIB

@@ -243,3 +243,24 @@ def test_lazy_row_adam_algorithm_equals_dense_adam_in_numpy():
         np.testing.assert_array_equal(a, b)
     stale = run(True, catch_up_before_read=False)
     assert np.abs(stale[0] - dense[0]).max() > 0
+
+
+def test_build_stamp_survives_a_copy_of_the_tree(lib, tmp_path):
+    """gpurun / the driver ship the built library to another path: the digest in build/stamp.txt must not depend on where the
+    checkout lives, or every fresh box rebuilds at first import (and the ranks of a torchrun job race on that rebuild)."""
+    import importlib.util
+    import shutil
+
+    pkg = os.path.join(ROOT, "neural-point-cloud-diffusion_b200")
+    dst = tmp_path / "repo"
+    shutil.copytree(os.path.join(pkg, "csrc"), dst / "neural-point-cloud-diffusion_b200" / "csrc")
+    shutil.copytree(os.path.join(ROOT, "include"), dst / "include")
+    shutil.copy(os.path.join(pkg, "build.py"), dst / "neural-point-cloud-diffusion_b200" / "build.py")
+    spec = importlib.util.spec_from_file_location("npcd_build_copy", str(dst / "neural-point-cloud-diffusion_b200" / "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    import glob
+
+    files = sorted(glob.glob(os.path.join(mod.CSRC, "*.cu"))) + sorted(glob.glob(os.path.join(mod.CSRC, "*.cuh"))) + \
+        sorted(glob.glob(os.path.join(mod.INCLUDE, "*.h")))
+    assert mod._digest(files) == open(os.path.join(pkg, "build", "stamp.txt")).read()
