@@ -63,8 +63,9 @@ int npcd_march_count(const float* cam_centers, const float* dirs, const float* r
                      const float* aabb /* optional, from npcd_grid_build: samples outside the box are skipped untested */,
                      const void* fine_masks /* optional, from npcd_grid_build_masks (same radius) */,
                      float radius, int max_shading_pts, unsigned* valid_bits, int* ray_count,
-                     int impl /* 0 auto; 1 generic global-memory kernels; 2 shared-memory thread-per-sample kernels (n_points <= 2048);
-                               3 ray-coherent kernels (warp per ray, per-ray candidate lists; n_points <= 2048; same results) */,
+                     int impl /* 0 auto (n_points <= 2048: march = 2, kNN fill = 3); 1 generic global-memory kernels; 2 shared-memory
+                               thread-per-sample kernels (n_points <= 2048); 3 ray-coherent kernels (march: warp per ray with a
+                               per-ray candidate list; fill: one candidate list per warp iteration; same results) */,
                      void* stream);
 int npcd_scan_workspace_bytes(long long n, size_t* bytes);
 int npcd_scan_counts(const int* ray_count, const int* ray_ids, long long n, long long* ray_offset, void* workspace,

@@ -167,9 +167,9 @@ def grid_build(kp_pos) -> Grid:
     return g
 
 
-# 0 = auto, 1 = generic global-memory kernels, 2 = shared-memory thread-per-sample kernels (n_points <= 2048), 3 = ray-coherent
-# warp-per-ray kernels (n_points <= 2048); tests flip this to cross-check the implementations bit for bit (NPCD_QUERY_IMPL: the same
-# from the environment, development aid)
+# 0 = auto (n_points <= 2048: marcher of 2, kNN fill of 3), 1 = generic global-memory kernels, 2 = shared-memory thread-per-sample
+# kernels (n_points <= 2048), 3 = ray-coherent kernels (n_points <= 2048); tests flip this to cross-check the implementations bit
+# for bit (NPCD_QUERY_IMPL: the same from the environment, development aid)
 QUERY_IMPL = int(os.environ.get("NPCD_QUERY_IMPL", "0"))
 USE_FINE_MASKS = True
 
