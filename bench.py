@@ -359,8 +359,8 @@ def bench_render(ctx, args):
         cm = stage.get("composite", 0.0)
         hp["composite_gbs"] = (20.0 * S + BYTES_PER_RAY * n_rays) / (cm * 1e-3) / 1e9 if cm > 0 else None
 
-    cfg = workload_config()
-    cfg.update({"mlp_impl": model.field.mlp_impl, "precision": model.field.precision if model.field.mlp_impl == "tc" else "f32"})
+    cfg = workload_config()  # identical in both arms (`--impl reference` prints the same dict); kernel choices go to `kernels`
+    kernels = {"mlp_impl": model.field.mlp_impl, "precision": model.field.precision if model.field.mlp_impl == "tc" else "f32"}
     line = {
         "metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -368,7 +368,7 @@ def bench_render(ctx, args):
         "views_per_sec": value / (RES * RES),
         "workload_stats": {"rays_per_step_per_gpu": n_rays, "shading_samples_per_step": S, "pairs_per_step": Np,
                            "per_rank": [{"rank": r, "S": int(v[0]), "Np": v[1], "ms_per_step": v[2]} for r, v in enumerate(per_rank)]},
-        "clocks": clocks, "gpu_launches": launches,
+        "kernels": kernels, "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "roofline": roofline,
     }

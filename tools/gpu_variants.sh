@@ -11,7 +11,7 @@ for defs in "$@"; do
   timeout 300 python tools/timeline_pair.py 2>&1 | tail -30
   for p in f16+e4m3x2 f16x3; do
     timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-secondary --precision $p 2>/dev/null > gpurun_out/$tag/bench_${i}_$p.json
-    python -c "import json,sys; d=json.loads(open('gpurun_out/$tag/bench_${i}_$p.json').read()); r=d['roofline']; print(d['config']['precision'], 'ms', round(d['ms_per_step'],2), 'Mrays/s', round(d['value']/1e6,2), 'pair', round(r['share_of_step']*d['ms_per_step'],1), 'heads', round(r['heads_share_of_step']*d['ms_per_step'],1), d['clocks']['sm_mhz'])"
+    python -c "import json,sys; d=json.loads(open('gpurun_out/$tag/bench_${i}_$p.json').read()); r=d['roofline']; print(d['kernels']['precision'], 'ms', round(d['ms_per_step'],2), 'Mrays/s', round(d['value']/1e6,2), 'pair', round(r['share_of_step']*d['ms_per_step'],1), 'heads', round(r['heads_share_of_step']*d['ms_per_step'],1), d['clocks']['sm_mhz'])"
   done
   i=$((i+1))
 done
