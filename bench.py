@@ -298,6 +298,30 @@ def bench_render(ctx, args):
     ctx.barrier()
     e2e_s = ctx.max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * n_rays * args.steps / e2e_s
+
+    # ---- informational: the opt-in operand scheme with ONE correction product (fields.MLP.precision = "f16+e4m3": weights
+    #      effectively rounded to fp16, 1.5 tensor passes per product).  NOT the headline: `value` above is the default scheme. ----
+    variants = None
+    if model.field.mlp_impl == "tc" and not args.precision and not args.no_secondary:
+        base_prec = model.field.precision
+        ref_out = step_device()
+        model.field.precision = "f16+e4m3"
+        alt_out = step_device()
+        diff = {k: float((ref_out[k] - alt_out[k]).abs().max().item()) for k in ("mask", "depth", "channels")}
+        del ref_out, alt_out
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+        ctx.barrier()
+        for a, b in ev2:
+            flush.zero_()
+            a.record()
+            step_device()
+            b.record()
+        ctx.barrier()
+        ms_alt = ctx.max_over_ranks(float(sum(a.elapsed_time(b) for a, b in ev2)))
+        model.field.precision = base_prec
+        variants = {"f16+e4m3": {"ms_per_step": ms_alt / 3, "value": world * n_rays * 3 / (ms_alt * 1e-3), "unit": "rays/s", "steps": 3,
+                                 "max_abs_diff_vs_default_scheme_rank0": diff, "dtype": "f32 activations x fp16-rounded weights",
+                                 "note": "opt-in (fields.MLP.precision); informational, not the headline value"}}
     h2d = sum(x.numel() * x.element_size() for x in (h_coords, h_feats, h_extr, h_intr))
     d2h = sum(x.numel() * x.element_size() for x in h_out.values())
 
@@ -374,6 +398,8 @@ def bench_render(ctx, args):
     }
     if verify is not None:
         line["verify"] = verify
+    if variants is not None:
+        line["precision_variants"] = variants
     return line
 
 

@@ -188,7 +188,9 @@ int npcd_field_tc_fwd(const int* nbr_idx, const float* sample_pos, const float* 
                       int stages /* bit0: dense packing + pair MLP + aggregation -> workspace, bit1: heads -> rgbs, bit2: heads with
                                     local_field.8 folded into W->shape / W->chan[0] by the caller (W' = W W_8, b' = W b_8 + b; W->agg unused),
                                     bit3: `weights` were packed in format 1 -- run the "f16 + e4m3 x 2" operand scheme (one fp16
-                                    product + two e4m3 correction products per layer instead of three fp16 products) */,
+                                    product + two e4m3 correction products per layer instead of three fp16 products),
+                                    bit4 (with bit3): only the activation-rounding correction product is issued ("f16 + e4m3": the
+                                    weights are then effectively rounded to fp16; 1.5 instead of 2 tensor passes per product) */,
                       int* error_flag /* device int, optional */, int num_sms, void* stream);
 /* fp32 rows [n,256] <-> the pre-split operand image the tensor-core kernels exchange: per 128-row tile 4 K-blocks x
  * (fp16 hi 16 KB, fp16 lo 16 KB) in the SWIZZLE_128B layout; ceil(n / 128) * 128 KB.                                           */

@@ -141,6 +141,7 @@ struct Params {
   uint8_t* hstash_x[6];      // operand images of F (local_field.8 output), C1, C2, C3 (channel_net hidden 1..3), C4, H (shape hidden)
   uint32_t* hstash_mask[5];  // sign bits of H, C1, C2, C3, C4
   long long* timeline;       // development aid (npcd_debug_set_timeline): clock64() of CTA 0's phase boundaries, [tile][32] events
+  int no_wcorr;              // f16 + e4m3 scheme with ONE correction product: the weight-rounding correction hi8 x Wlo8 is not issued
 };
 
 constexpr int kTimelineTiles = 64;
@@ -512,7 +513,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
                 mma16(d_tmem, a_hi + 4, b2 + 4, 1u);
               } else {
                 mma8(d_tmem, a_lo, b2, 1u);
-                mma8(d_tmem, a_lo + 4, b2 + 4, 1u);
+                if (!NPCD_EXP_NOWCORR && !P.no_wcorr) mma8(d_tmem, a_lo + 4, b2 + 4, 1u);
               }
             }
             __syncwarp();
@@ -532,7 +533,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
                 mma16(d_tmem, a_hi + 6, b2 + 6, 1u);
               } else {
                 mma8(d_tmem, a_lo + 2, b2 + 2, 1u);
-                mma8(d_tmem, a_lo + 6, b2 + 6, 1u);
+                if (!NPCD_EXP_NOWCORR && !P.no_wcorr) mma8(d_tmem, a_lo + 6, b2 + 6, 1u);
               }
               commit_stage(st2);
               if (l == n_layers - 1 && has_next && (!kPair || kb < 2)) commit_cta(kBarAFree + kb);
@@ -578,7 +579,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
                 if (2 * k8 < ks_n) mma8(d_tmem, a_lo + 2 * k8, b + 2 * k8, 1u);
 #pragma unroll
               for (int k8 = 0; k8 < 2; ++k8)
-                if (2 * k8 < ks_n) mma8(d_tmem, a_lo + 4 + 2 * k8, b + 4 + 2 * k8, 1u);
+                if (2 * k8 < ks_n && !NPCD_EXP_NOWCORR && !P.no_wcorr) mma8(d_tmem, a_lo + 4 + 2 * k8, b + 4 + 2 * k8, 1u);
             }
             commit_stage(st);
             // this K-block may take the next tile's first operand (arrive only where somebody waits: pair mode restages
@@ -1657,7 +1658,8 @@ namespace {
 template <int kMode, bool kF8 = false>
 int pair_stage(const int* nbr_idx, const float* sample_pos, const float* kp_pos, const float* kp_feat, const long long* n_samples_dev,
                long long capacity, const npcd_mlp_tc_weights* W, const TcWorkspace& ws, uint8_t* base,
-               const npcd_pair_stash_layout* layout, uint8_t* stash, int* error_flag, int num_sms, cudaStream_t st) {
+               const npcd_pair_stash_layout* layout, uint8_t* stash, int* error_flag, int num_sms, cudaStream_t st,
+               int no_wcorr = 0) {
   uint8_t* img = base + ws.img_off;
   int* pair_off = (int*)(base + ws.pair_off);
   int* tile_start = (int*)(base + ws.tile_off);
@@ -1687,6 +1689,7 @@ int pair_stage(const int* nbr_idx, const float* sample_pos, const float* kp_pos,
   P.nbr_idx = nbr_idx; P.sample_pos = (const float4*)sample_pos; P.kp_pos = kp_pos; P.kp_feat = kp_feat;
   P.pair_off = pair_off; P.tile_start = tile_start; P.n_tiles_dev = n_tiles_dev; P.img = img;
   P.n_samples_dev = n_samples_dev; P.capacity = capacity; P.error_flag = error_flag;
+  P.no_wcorr = no_wcorr;
   if (stash) {
     for (int l = 0; l < 4; ++l) {
       P.stash_x[l] = stash + layout->x[l];
@@ -1704,9 +1707,10 @@ namespace {
 template <int kMode, bool kF8 = false>
 int heads_stage(const npcd_mlp_tc_weights* W, uint8_t* img, float* rgbs, float* feat_out, const long long* n_samples_dev,
                 long long capacity, const npcd_pair_stash_layout* layout, uint8_t* stash, int* error_flag, int num_sms, cudaStream_t st,
-                bool folded = false) {
+                bool folded = false, int no_wcorr = 0) {
   static thread_local tc::Params P;
   memset(&P, 0, sizeof(P));
+  P.no_wcorr = no_wcorr;
   const int o = folded ? 1 : 0;  // folded: W->shape / W->chan[0] already contain local_field.8 (W' = W W_8, b' = W b_8 + b)
   if (!folded) fill_layer(P, 0, W->agg, tc::EPI_LINEAR, kF8);
   fill_layer(P, 1 - o, W->shape, tc::EPI_DOT1, kF8);
@@ -1767,9 +1771,11 @@ extern "C" int npcd_field_tc_fwd(const int* nbr_idx, const float* sample_pos, co
   int* tile_start = (int*)(base + ws.tile_off);
   int* n_tiles_dev = (int*)(base + ws.ntiles_off);
   const bool f8 = (stages & 8) != 0;  // W was packed with format 1 (f16 + e4m3 x 2 operand scheme)
+  const int no_wcorr = (stages & 16) ? 1 : 0;  // ... and only the activation-rounding correction is issued ("f16+e4m3")
+  NPCD_CHECK_ARG(!no_wcorr || f8, "stages bit 4 (single correction product) needs bit 3 (f16 + e4m3 operands)");
   if (stages & 1) {
     rc = f8 ? pair_stage<tc::MODE_PAIR, true>(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, W, ws, base, nullptr, nullptr,
-                                              error_flag, num_sms, st)
+                                              error_flag, num_sms, st, no_wcorr)
             : pair_stage<tc::MODE_PAIR>(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, W, ws, base, nullptr, nullptr,
                                         error_flag, num_sms, st);
     if (rc) return rc;
@@ -1777,7 +1783,7 @@ extern "C" int npcd_field_tc_fwd(const int* nbr_idx, const float* sample_pos, co
   NPCD_CHECK_ARG(!(stages & 4) || !feat_out, "the folded heads stage has no local_field.8 output to return");
   if (stages & 6)
     rc = f8 ? heads_stage<tc::MODE_HEADS, true>(W, img, rgbs, feat_out, n_samples_dev, capacity, nullptr, nullptr, error_flag, num_sms, st,
-                                                (stages & 4) != 0)
+                                                (stages & 4) != 0, no_wcorr)
             : heads_stage<tc::MODE_HEADS>(W, img, rgbs, feat_out, n_samples_dev, capacity, nullptr, nullptr, error_flag, num_sms, st,
                                           (stages & 4) != 0);
   return rc;

@@ -9,6 +9,9 @@
 #ifndef NPCD_EXP_NSPLIT
 #define NPCD_EXP_NSPLIT 0    // experiment (results stay correct): every M128 N256 MMA issued as two N = 128 MMAs
 #endif
+#ifndef NPCD_EXP_NOWCORR
+#define NPCD_EXP_NOWCORR 0   // precision experiment: the weight-rounding correction product hi8 x Wlo8 is not issued (24 MMAs per layer)
+#endif
 #ifndef NPCD_EXP_NOSPLITLD
 #define NPCD_EXP_NOSPLITLD 0 // 1: the first accumulator chunk of a layer epilogue is loaded with one 32-column tcgen05.ld (round-2 start)
 #endif

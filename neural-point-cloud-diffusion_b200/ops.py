@@ -20,9 +20,17 @@ from ._lib import call, ptr
 K_NEIGHBORS = 8
 DEPTH_RES = 128
 HIDDEN = 256
-# operand scheme of the tensor-core inference kernels: "f16x3" (three fp16 products per layer) or "f16+e4m3x2" (fp16 hi x hi plus
-# two e4m3 correction products at twice the tensor rate); fields.MLP.precision overrides it per model
+# operand scheme of the tensor-core inference kernels: "f16x3" (three fp16 products per layer), "f16+e4m3x2" (fp16 hi x hi plus
+# two e4m3 correction products at twice the tensor rate: the default) or "f16+e4m3" (opt-in: the same operands, only the
+# activation-rounding correction is issued -- the weights are then effectively rounded to fp16; DESIGN.md section 5 has the
+# measured errors); fields.MLP.precision overrides it per model
 DEFAULT_PRECISION = "f16+e4m3x2"
+F8_PRECISIONS = ("f16+e4m3x2", "f16+e4m3")  # schemes that use the format-1 (f16 + e4m3) operand images / weight tables
+
+
+def stage_bits(precision: str) -> int:
+    """`stages` bits 3 / 4 of npcd_field_tc_fwd for an operand scheme."""
+    return {"f16x3": 0, "f16+e4m3x2": 8, "f16+e4m3": 8 | 16}[precision]
 
 # number of kernels launched by this process through the C-ABI (bench.py reports it as gpu_launches)
 LAUNCHES = 0
@@ -523,7 +531,7 @@ class PackedTcWeights:
         first use), optionally with `local_field.8` folded into the heads."""
         if precision == "f16x3":
             return self.folded_struct() if folded else self.struct
-        if precision != "f16+e4m3x2":
+        if precision not in F8_PRECISIONS:
             raise ValueError(f"unknown precision {precision!r}")
         if self._f8 is None:
             f = _lib.TcWeights()
@@ -686,7 +694,7 @@ def field_tc_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity: 
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     kp_pos = kp_pos.detach().contiguous().float()
     kp_feat = kp_feat.detach().contiguous().float()
-    f8 = 8 if precision == "f16+e4m3x2" else 0  # `stages` bit 3: operand scheme of the packed weights
+    f8 = stage_bits(precision)  # `stages` bits 3 / 4: operand scheme of the packed weights, one or two correction products
     args = (ptr(nbr_idx), ptr(sample_pos), ptr(kp_pos), ptr(kp_feat), ptr(n_samples_dev), capacity,
             C.byref(weights.struct_for(precision, False)), ptr(ws), nbytes, ptr(rgbs), ptr(feat))
     _timed("pair_mlp", lambda: call("npcd_field_tc_fwd", *args, 1 | f8, ptr(weights.error_flag), sm_count(dev), _stream()))
@@ -710,21 +718,21 @@ def tc_rows_to_image(x, precision: str = "f16x3"):
     x = x.contiguous().float()
     n = x.shape[0]
     img = torch.zeros(((n + 127) // 128) * 131072, dtype=torch.uint8, device=x.device)
-    call("npcd_tc_rows_to_image" + ("_f8" if precision == "f16+e4m3x2" else ""), ptr(x), n, ptr(img), _stream())
+    call("npcd_tc_rows_to_image" + ("_f8" if precision in F8_PRECISIONS else ""), ptr(x), n, ptr(img), _stream())
     _count(1 if n else 0)
     return img
 
 
 def tc_image_to_rows(img, n: int, precision: str = "f16x3"):
     out = torch.empty((n, HIDDEN), device=img.device)
-    call("npcd_tc_image_to_rows" + ("_f8" if precision == "f16+e4m3x2" else ""), ptr(img), n, ptr(out), _stream())
+    call("npcd_tc_image_to_rows" + ("_f8" if precision in F8_PRECISIONS else ""), ptr(img), n, ptr(out), _stream())
     _count(1 if n else 0)
     return out
 
 
 def tc_linear_probe(x, linear: torch.nn.Linear, precision: str = "f16x3"):
     """out = x @ W^T + b through the tcgen05 engine (one packed 256x256 layer); self-test of descriptors / swizzle / TMEM."""
-    sfx = "_f8" if precision == "f16+e4m3x2" else ""
+    sfx = "_f8" if precision in F8_PRECISIONS else ""
     _need_cuda(x)
     dev = x.device
     x = x.contiguous().float()

@@ -157,3 +157,64 @@ def test_f8_large_activations_degrade_gracefully(torch_cuda):
     got = ops.tc_linear_probe(x.cuda(), lin, precision=F8).cpu().double()
     assert torch.isfinite(got).all()
     assert ((got - want).abs() / mag).max().item() < 2.0 ** -11
+
+
+# ---- "f16 + e4m3" with ONE correction product (opt-in: weights effectively rounded to fp16, 1.5 tensor passes per product) ----
+F8X1 = "f16+e4m3"
+
+
+@pytest.mark.parametrize("name", ["view32", "box32"])
+def test_f8x1_field_vs_oracle(name, syn, model, weights, torch_cuda):
+    """Per-sample colour / density within 1e-5 of the oracle (the default scheme's bar), the 256-d feature within 1e-4 of its range
+    (the default scheme holds 2e-5 there: this is where the dropped weight-rounding correction shows)."""
+    torch = torch_cuda
+    g, coords, feats, extr, intr, res = load_case(name, syn)
+    ref = orc.render(coords, feats, extr, intr, res, weights, return_aux=True)["aux"]
+    model.field.precision = F8X1
+    with torch.no_grad():
+        out = model.renderer(_t(torch, coords), _t(torch, feats), _t(torch, extr), _t(torch, intr), res, False, return_aux=True)
+    rgbs = out["aux"]["rgbs"].cpu().numpy()
+    feat = out["aux"]["feat"].cpu().numpy()
+    err = (np.abs(feat - ref["feat"]).max() / max(1.0, np.abs(ref["feat"]).max()), np.abs(rgbs[:, :3] - ref["rgb"]).max(),
+           np.abs(rgbs[:, 3] - ref["sigma"]).max() / max(1.0, ref["sigma"].max()))
+    print(f"{name}: (feat, rgb, sigma) max err vs oracle  f16+e4m3 {err}")
+    assert err[0] < 1e-4 and err[1] < 1e-5 and err[2] < 1e-5, err
+
+
+@pytest.mark.parametrize("name", EVAL_CASES + ["view128"])
+def test_f8x1_render_vs_golden(name, syn, model, torch_cuda):
+    """Images against the golden vectors of the UNMODIFIED reference at north_star's bar (1e-4), as for the other schemes."""
+    torch = torch_cuda
+    g, coords, feats, extr, intr, res = load_case(name, syn)
+    model.field.precision = F8X1
+    with torch.no_grad():
+        out = model.render(_t(torch, coords), _t(torch, feats), _t(torch, extr), _t(torch, intr), resolution=res)
+    ch = out["channels"].cpu().numpy()
+    bad = np.abs(ch - g["channels"]).max(-1) > IMG_TOL
+    assert bad.sum() <= (8 if name == "view128" else 0), int(bad.sum())
+    ok = ~bad.reshape(-1)
+    for k in ("mask", "depth"):
+        np.testing.assert_allclose(out[k].cpu().numpy().reshape(-1)[ok], g[k].reshape(-1)[ok], atol=IMG_TOL, rtol=0, err_msg=k)
+    if ch.size:
+        assert abs(psnr(ch.reshape(-1)[np.repeat(ok, 3)], g["channels"].reshape(-1)[np.repeat(ok, 3)])) > 80.0
+
+
+def test_f8x1_matches_simt_full_size(syn, model, cameras, torch_cuda):
+    """8 full-size views against the fp32 SIMT kernels on the same kNN lists: images within 2e-5 (a fifth of the bar), PSNR > 100 dB."""
+    torch = torch_cuda
+    poses, intr = cameras
+    views = [0, 31, 62, 93, 124, 155, 186, 217]
+    coords, feats = syn.make_clouds([0])
+    args = (_t(torch, coords), _t(torch, feats), _t(torch, poses[views][None]), _t(torch, intr[views][None]), 128, False)
+    with torch.no_grad():
+        model.field.mlp_impl = "simt"
+        ref = model.renderer(*args)
+        model.field.mlp_impl = "tc"
+        model.field.precision = F8X1
+        out = model.renderer(*args)
+    for k in ("mask", "depth", "channels"):
+        e = (ref[k] - out[k]).abs().max().item()
+        print(f"{k}: max |simt - f16+e4m3| {e:.2e}")
+        assert e < 2e-5, (k, e)
+    mse = ((ref["channels"] - out["channels"]).double() ** 2).mean().item()
+    assert 10 * np.log10(1.0 / max(mse, 1e-30)) > 100.0
