@@ -24,7 +24,7 @@ HIDDEN = 256
 # two e4m3 correction products at twice the tensor rate: the default) or "f16+e4m3" (opt-in: the same operands, only the
 # activation-rounding correction is issued -- the weights are then effectively rounded to fp16; DESIGN.md section 5 has the
 # measured errors); fields.MLP.precision overrides it per model
-DEFAULT_PRECISION = "f16+e4m3x2"
+DEFAULT_PRECISION = os.environ.get("NPCD_PRECISION", "f16+e4m3x2")  # the environment variable only changes the default of new models
 F8_PRECISIONS = ("f16+e4m3x2", "f16+e4m3")  # schemes that use the format-1 (f16 + e4m3) operand images / weight tables
 
 
