@@ -243,6 +243,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
   constexpr bool kTrain = kTrainP || kTrainH;
   constexpr bool kHeads = kMode == MODE_HEADS || kMode == MODE_HEADS_TRAIN;
   constexpr bool k2 = two_sm<kMode>();
+  constexpr bool kDynAgg = kPro && !k2 && !NPCD_EXP_NOREORDER;  // next tile's layer-0 epilogue interleaved with the aggregation
   constexpr int kSt = k2 ? kStages2 : kStages;                       // weight-ring stages
   constexpr int kStageBytes = k2 ? kTileBytesW / 2 : kTileBytesW;    // 2-SM: this CTA's half (128 of the 256 output rows) of a tile
   constexpr int kWF = k2 ? kBar2WFull : kBarWFull, kWE = k2 ? kBar2WEmpty : kBarWEmpty;
@@ -304,13 +305,11 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
 
   // ---- aggregation epilogue, sum phase: task = (sample of the tile, 8 of the pass's 128 columns); shared by the epilogue threads
   //      and, in inference pair mode, the input warps (u = thread number among the n_threads that take tasks) ----
-  auto agg_sum_tasks = [&](int u, int n_threads, int pass, int buf) {
+  auto agg_one = [&](int task, int pass, int buf, int s_begin) {
     const float* stage = reinterpret_cast<const float*>(sA + 4 * kTileBytesA);
     const uint8_t* samp_row = misc + kOffSampRow + buf * 128;
     const uint8_t* samp_cnt = misc + kOffSampCnt + buf * 128;
-    const int* info = reinterpret_cast<const int*>(misc + kOffInfo) + buf * 4;
-    const int s_begin = info[0], n_samp = info[1];
-    for (int task = u; task < (NPCD_EXP_NOAGG ? 0 : n_samp * 16); task += n_threads) {
+    {
       const int sl = task >> 4, c8 = task & 15;
       const int r0 = samp_row[sl], cnt = samp_cnt[sl];
       float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -353,6 +352,11 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
         *reinterpret_cast<uint2*>(kbp + kTileBytesA + swz8_hi((int)(s & 127), (col & 63) >> 3)) = hi8;
       }
     }
+  };
+  auto agg_sum_tasks = [&](int u, int n_threads, int pass, int buf) {
+    const int* info = reinterpret_cast<const int*>(misc + kOffInfo) + buf * 4;
+    const int s_begin = info[0], n_samp = info[1];
+    for (int task = u; task < (NPCD_EXP_NOAGG ? 0 : n_samp * 16); task += n_threads) agg_one(task, pass, buf, s_begin);
   };
   // barrier of the aggregation passes: the 256 epilogue threads (+ the 128 input-warp threads in inference pair mode)
   auto agg_bar = [&]() {
@@ -811,7 +815,8 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
 #pragma unroll 1
       for (int pass = 0; pass < 2; ++pass) {
         agg_bar();  // the epilogue threads have staged the pass
-        agg_sum_tasks(kEpiThreads + pt, kEpiThreads + kProThreads, pass, (int)(it & 1u));
+        if (kDynAgg && pass == 1) agg_sum_tasks(pt, kProThreads, pass, (int)(it & 1u));  // alone: the epilogue warps are on the next tile
+        else agg_sum_tasks(kEpiThreads + pt, kEpiThreads + kProThreads, pass, (int)(it & 1u));
         agg_bar();
       }
     }
@@ -888,7 +893,11 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
 
     // ACT / LINEAR epilogue of layer l: four 32-column chunks (2 i + half), software-pipelined TMEM loads
     int tl_it = 0;  // tile counter of this CTA (timeline)
-    auto epilogue_store = [&](int l, float slope, float* feat_row) {
+    // mid (inference pair kernel, layer 0 of every tile but a CTA's first): the epilogue starts while the input warps still sum
+    // pass 1 of the PREVIOUS tile's aggregation out of K-blocks 2..3; K-blocks 0..1 are written first, then the closing barrier of
+    // that sum phase, then K-blocks 2..3 (see the tile loop below).  A run-time flag on purpose: a second instantiation of this
+    // lambda (+19 KB of code, cold whenever it was entered) started ~700 cycles later than the shared one.
+    auto epilogue_store = [&](bool mid, int l, float slope, float* feat_row) {
       const uint32_t ab = lc & 1u;
       if (et == 0) NPCD_TL(tl_it, 2 * l);
       wait_acc(ab);
@@ -908,6 +917,10 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
       for (int i = 0; i < 4; ++i) {
         if (i < 3 && !(kSplitLd && i == 0)) tmem_ld32_async(t_acc + (2 * (i + 1) + half) * 32, v[(i + 1) & 1]);
         stash_wait(i);
+        if (kDynAgg && i == 2 && mid) {
+          agg_bar();  // pass 1 of the previous tile's aggregation has been summed: its staging area (K-blocks 2..3) is free
+          if (et == 0) NPCD_TL(tl_it - 1, 15);
+        }
         uint32_t* mptr = nullptr;
         if (kTrainP) mptr = P.stash_mask[l] + ((size_t)tile_now * 128 + row) * 8 + (2 * i + half);
         if (kTrainH && l >= 2) mptr = P.hstash_mask[l - 1] + ((size_t)tile_now * 128 + row) * 8 + (2 * i + half);
@@ -931,6 +944,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
       }
       ++lc;
     };
+    constexpr bool kWhole = false;
 
     if (kPair) {
       // ------------------------------------------------------------------------------------------------- pair mode ----
@@ -1077,11 +1091,119 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
         if (kTrain) sd_pending |= 1u << kb;
       };
 
+      // ---- layer 3: bias + LeakyReLU, normalised inverse-distance weight, segmented sum over each sample's rows
+      //      (fields/aggregators/mlp.py:86-88,119-121), staged as fp32 in K-blocks 2..3 (free once layer 3's MMAs are done),
+      //      two passes of 128 columns; the sums leave as the pre-split operand image the heads kernel bulk-copies.
+      //      defer_last (inference pair kernel): returns once pass 1 is staged and the accumulator released; the caller runs the
+      //      last barrier / sum / barrier itself, with the first half of the next tile's layer-0 epilogue in between.
+      auto agg_epilogue = [&](int buf, int cur_tile, bool defer_last) {
+        const uint32_t ab = lc & 1u;
+        if (et == 0) NPCD_TL(tl_it, 6);
+        wait_acc(ab);
+        if (et == 0) NPCD_TL(tl_it, 7);
+        if (!kPro) epi_bar_sync();  // wts[] / row maps of this tile were written by other warps of this group (kPro: by the input
+                                    // warps a tile ago, ordered by their A0Rdy arrive -> MMA -> accumulator-ready chain)
+        const float inv = P.layers[3].inv_scale;
+        const uint32_t t_acc = t_row + ab * 256u;
+        const float* wts = wts_all + buf * 128;
+        const uint8_t* row_samp = row_samp_all + buf * 128;
+        const uint8_t* samp_row = samp_row_all + buf * 128;
+        const uint8_t* samp_cnt = samp_cnt_all + buf * 128;
+        const int n_rows = info_all[buf * 4 + 2];
+        float wn = 0.f;
+        if (row < n_rows) {
+          const int sl = row_samp[row];
+          const int r0 = samp_row[sl], cnt = samp_cnt[sl];
+          float wsum = 0.f;
+          for (int j = 0; j < cnt; ++j) wsum += wts[r0 + j];
+          wn = wts[row] / wsum;
+        }
+        if (kTrain && half == 0) P.stash_wn[(size_t)cur_tile * 128 + row] = wn;
+        stash_wait(2);  // the fp32 staging below overwrites K-blocks 2..3 (X_3)
+        stash_wait(3);
+        // staging: [128 rows][128 cols] fp32 in K-blocks 2..3.  16-byte chunk c4 of a row sits at position
+        // ((c4 >> 1) | ((c4 & 1) << 4)) ^ (row & 7): conflict-free for the row-per-lane stores AND for the sum phase, where
+        // 16 lanes read chunks 2 c8 and 2 c8 + 1 of one row.
+        float* stage = reinterpret_cast<float*>(sA + 4 * kTileBytesA);
+        const uint64_t inv2 = pack2(inv, inv), slope2 = pack2(0.01f, 0.01f), wn2 = pack2(wn, wn);
+        // four 32-column chunks q (pass = q >> 1): the TMEM load of chunk q + 1 is in flight while chunk q is processed
+        uint32_t v[2][32];
+        tmem_ld32_async(t_acc + 64 * half, v[0]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int pass = q >> 1;
+          const int cl = 64 * half + 32 * (q & 1);  // column within the pass
+          const int c0 = 128 * pass + cl;
+          tmem_wait(v[q & 1]);
+          if (q < 3) tmem_ld32_async(t_acc + 128 * ((q + 1) >> 1) + 64 * half + 32 * ((q + 1) & 1), v[(q + 1) & 1]);
+          uint32_t mbits = 0u;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 b = *reinterpret_cast<const float4*>(&P.bias[3][c0 + g * 4]);
+            const uint32_t* vv = v[q & 1];
+            float y0, y1, y2, y3;
+            act2(vv[g * 4 + 0], vv[g * 4 + 1], inv2, b.x, b.y, slope2, y0, y1);
+            act2(vv[g * 4 + 2], vv[g * 4 + 3], inv2, b.z, b.w, slope2, y2, y3);
+            if (kTrain)
+              mbits |= ((y0 > 0.f ? 1u : 0u) | (y1 > 0.f ? 2u : 0u) | (y2 > 0.f ? 4u : 0u) | (y3 > 0.f ? 8u : 0u)) << (g * 4);
+            float4 o;
+            unpack2(mul2(pack2(y0, y1), wn2), o.x, o.y);
+            unpack2(mul2(pack2(y2, y3), wn2), o.z, o.w);
+            const int c4 = (cl >> 2) + g;
+            const int pos = ((c4 >> 1) | ((c4 & 1) << 4)) ^ x7;
+            *reinterpret_cast<float4*>(stage + row * 128 + (pos << 2)) = o;
+          }
+          if (kTrain) P.stash_mask[3][((size_t)cur_tile * 128 + row) * 8 + (c0 >> 5)] = mbits;
+          if (q & 1) {
+            if (pass == 1) release_acc(ab);
+            if (et == 0) NPCD_TL(tl_it, 8 + 4 * pass);
+            if (!(pass == 1 && defer_last)) {
+              agg_bar();
+              if (et == 0) NPCD_TL(tl_it, 9 + 4 * pass);
+              agg_sum_tasks(et, kPro ? kEpiThreads + kProThreads : kEpiThreads, pass, buf);
+              if (et == 0) NPCD_TL(tl_it, 10 + 4 * pass);
+              agg_bar();  // the staging area is rewritten by the next pass / the next tile's layer-0 epilogue
+              if (et == 0) NPCD_TL(tl_it, 11 + 4 * pass);
+            }
+          }
+        }
+        ++tl_it;
+        ++lc;
+      };
+
+      int cur = kPro ? (int)blockIdx.x : -1;
+      if (kPro) tile_now = cur;
+      if (kDynAgg) {
+        // Inference pair kernel (1-SM).  The aggregation of tile t used to keep the epilogue warps busy for ~5 700 cycles during which
+        // the tensor pipe only had layer 0 of tile t + 1 (timeline: profiles/r2_timeline_pair.md, "the largest single gap").  Now,
+        // as soon as pass 1 is STAGED (accumulator released), the epilogue warps start tile t + 1's layer-0 epilogue (K-blocks 0..1
+        // first; the staging area is K-blocks 2..3), so layer 1's MMAs start ~2 000 cycles earlier, while the input warps ALONE
+        // sum pass 1; the closing barrier of that sum phase sits in front of K-block 2 of the layer-0 epilogue.
+        // (one call site of epilogue_store: one epilogue per trip, the aggregation after every third)
+        bool mid = false;
+        int buf = 0;
+#pragma unroll 1
+        for (int l = 0; cur < n_tiles;) {
+          epilogue_store(mid, l, 0.01f, nullptr);
+          mid = false;
+          if (++l < 3) continue;
+          agg_epilogue(buf, cur, true);
+          agg_bar();  // pass 1 is staged: the input warps sum it
+          if (et == 0) NPCD_TL(tl_it - 1, 13);
+          cur += (int)gridDim.x;
+          if (cur >= n_tiles) {
+            agg_bar();  // (closing barrier of the sum phase; with a next tile it sits inside that tile's layer-0 epilogue)
+            break;
+          }
+          tile_now = cur;
+          buf ^= 1;
+          l = 0;
+          mid = true;
+        }
+      } else
       // Iteration -1 primes the pipeline (stages the first tile's input); iteration `it` runs the four layer epilogues of tile
       // `cur` and, between them, stages the input of the tile after it.  One call site per helper keeps the code I-cache sized.
       // (kPro, inference: the input warps 11..14 stage the layer-0 input; no priming iteration, no prologue work here.)
-      int cur = kPro ? (int)blockIdx.x : -1;
-      if (kPro) tile_now = cur;
       for (int it = kPro ? 0 : -1;; ++it) {
         const bool prime = it < 0;
         if (kPro && (k2 ? it >= n_pass : cur >= n_tiles)) break;  // (2-SM: phantom tiles keep the pair in lockstep)
@@ -1091,7 +1213,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
         const int buf = it & 1;
 #pragma unroll 1
         for (int l = 0; l < 3; ++l) {
-          if (!prime) epilogue_store(l, 0.01f, nullptr);
+          if (!prime) epilogue_store(kWhole, l, 0.01f, nullptr);
           if (!kPro && l == 0 && has_target) prologue_compute(target, buf ^ 1);
         }
         if (!kPro && has_target) {  // layer 3's MMAs release K-blocks 0 and 1 as they pass them
@@ -1102,81 +1224,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
           }
         }
         if (prime) { cur = target; tile_now = cur; continue; }
-        // ---- layer 3: bias + LeakyReLU, normalised inverse-distance weight, segmented sum over each sample's rows
-        //      (fields/aggregators/mlp.py:86-88,119-121), staged as fp32 in K-blocks 2..3 (free once layer 3's MMAs are done),
-        //      two passes of 128 columns; the sums leave as the pre-split operand image the heads kernel bulk-copies.
-        {
-          const uint32_t ab = lc & 1u;
-          if (et == 0) NPCD_TL(tl_it, 6);
-          wait_acc(ab);
-          if (et == 0) NPCD_TL(tl_it, 7);
-          if (!kPro) epi_bar_sync();  // wts[] / row maps of this tile were written by other warps of this group (kPro: by the input
-                                      // warps a tile ago, ordered by their A0Rdy arrive -> MMA -> accumulator-ready chain)
-          const float inv = P.layers[3].inv_scale;
-          const uint32_t t_acc = t_row + ab * 256u;
-          const float* wts = wts_all + buf * 128;
-          const uint8_t* row_samp = row_samp_all + buf * 128;
-          const uint8_t* samp_row = samp_row_all + buf * 128;
-          const uint8_t* samp_cnt = samp_cnt_all + buf * 128;
-          const int s_begin = info_all[buf * 4 + 0], n_samp = info_all[buf * 4 + 1], n_rows = info_all[buf * 4 + 2];
-          float wn = 0.f;
-          if (row < n_rows) {
-            const int sl = row_samp[row];
-            const int r0 = samp_row[sl], cnt = samp_cnt[sl];
-            float wsum = 0.f;
-            for (int j = 0; j < cnt; ++j) wsum += wts[r0 + j];
-            wn = wts[row] / wsum;
-          }
-          if (kTrain && half == 0) P.stash_wn[(size_t)cur * 128 + row] = wn;
-          stash_wait(2);  // the fp32 staging below overwrites K-blocks 2..3 (X_3)
-          stash_wait(3);
-          // staging: [128 rows][128 cols] fp32 in K-blocks 2..3.  16-byte chunk c4 of a row sits at position
-          // ((c4 >> 1) | ((c4 & 1) << 4)) ^ (row & 7): conflict-free for the row-per-lane stores AND for the sum phase, where
-          // 16 lanes read chunks 2 c8 and 2 c8 + 1 of one row.
-          float* stage = reinterpret_cast<float*>(sA + 4 * kTileBytesA);
-          const uint64_t inv2 = pack2(inv, inv), slope2 = pack2(0.01f, 0.01f), wn2 = pack2(wn, wn);
-          // four 32-column chunks q (pass = q >> 1): the TMEM load of chunk q + 1 is in flight while chunk q is processed
-          uint32_t v[2][32];
-          tmem_ld32_async(t_acc + 64 * half, v[0]);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int pass = q >> 1;
-            const int cl = 64 * half + 32 * (q & 1);  // column within the pass
-            const int c0 = 128 * pass + cl;
-            tmem_wait(v[q & 1]);
-            if (q < 3) tmem_ld32_async(t_acc + 128 * ((q + 1) >> 1) + 64 * half + 32 * ((q + 1) & 1), v[(q + 1) & 1]);
-            uint32_t mbits = 0u;
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const float4 b = *reinterpret_cast<const float4*>(&P.bias[3][c0 + g * 4]);
-              const uint32_t* vv = v[q & 1];
-              float y0, y1, y2, y3;
-              act2(vv[g * 4 + 0], vv[g * 4 + 1], inv2, b.x, b.y, slope2, y0, y1);
-              act2(vv[g * 4 + 2], vv[g * 4 + 3], inv2, b.z, b.w, slope2, y2, y3);
-              if (kTrain)
-                mbits |= ((y0 > 0.f ? 1u : 0u) | (y1 > 0.f ? 2u : 0u) | (y2 > 0.f ? 4u : 0u) | (y3 > 0.f ? 8u : 0u)) << (g * 4);
-              float4 o;
-              unpack2(mul2(pack2(y0, y1), wn2), o.x, o.y);
-              unpack2(mul2(pack2(y2, y3), wn2), o.z, o.w);
-              const int c4 = (cl >> 2) + g;
-              const int pos = ((c4 >> 1) | ((c4 & 1) << 4)) ^ x7;
-              *reinterpret_cast<float4*>(stage + row * 128 + (pos << 2)) = o;
-            }
-            if (kTrain) P.stash_mask[3][((size_t)cur * 128 + row) * 8 + (c0 >> 5)] = mbits;
-            if (q & 1) {
-              if (pass == 1) release_acc(ab);
-              if (et == 0) NPCD_TL(tl_it, 8 + 4 * pass);
-              agg_bar();
-              if (et == 0) NPCD_TL(tl_it, 9 + 4 * pass);
-              agg_sum_tasks(et, kPro ? kEpiThreads + kProThreads : kEpiThreads, pass, buf);
-              if (et == 0) NPCD_TL(tl_it, 10 + 4 * pass);
-              agg_bar();  // the staging area is rewritten by the next pass / the next tile's layer-0 epilogue
-              if (et == 0) NPCD_TL(tl_it, 11 + 4 * pass);
-            }
-          }
-          ++tl_it;
-          ++lc;
-        }
+        agg_epilogue(buf, cur, false);
         if (!has_target && !k2) break;
         cur = target;
         tile_now = cur;
@@ -1290,7 +1338,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
             }
           } else {
             // ll = 0: local_field.8 (linear) -> feat;  ll = 2..4: channel_net.0,2,4 (layer 2 reads feat and overwrites it in place)
-            epilogue_store(l, ll == 0 ? 1.0f : 0.01f, ll == 0 ? feat_row : nullptr);
+            epilogue_store(kWhole, l, ll == 0 ? 1.0f : 0.01f, ll == 0 ? feat_row : nullptr);
           }
         }
         if (half == 0 && s < S) {

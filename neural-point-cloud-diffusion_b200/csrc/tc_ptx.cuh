@@ -362,6 +362,9 @@ __device__ __forceinline__ void split8(const float (&y)[8], uint4& hi, uint4& lo
 #ifndef NPCD_EXP_NOAGG
 #define NPCD_EXP_NOAGG 0    // timing-only ablation: the aggregation epilogue stages but does not sum / store
 #endif
+#ifndef NPCD_EXP_NOREORDER
+#define NPCD_EXP_NOREORDER 0  // 1: the inference pair kernel's epilogue warps finish the aggregation before the next tile's layer 0
+#endif
 constexpr float kF8ActScale = 8.0f;          // 2^3: activations are stored times this
 constexpr float kF8AccScaleInv = 1.0f / 65536.0f;  // accumulator = 2^16 * (y . w_prescaled)
 
