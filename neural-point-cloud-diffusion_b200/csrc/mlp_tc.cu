@@ -170,6 +170,8 @@ __device__ __forceinline__ void epi_chunk_store(const Params& P, int l, float in
   }
   const int c16_0 = (c0 & 63) >> 3;
   const uint64_t inv2 = pack2(inv, inv), slope2 = pack2(slope, slope);
+  static_assert(kG0 % 2 == 0 && kG1 % 2 == 0, "8-bit tile: groups are stored in pairs");
+  uint2 lo8_even = make_uint2(0u, 0u), hi8_even = make_uint2(0u, 0u);
 #pragma unroll
   for (int g = kG0; g < kG1; ++g) {
     const float4 b0 = NPCD_EXP_NOBIAS ? make_float4(0.1f, 0.2f, 0.3f, 0.4f) : *reinterpret_cast<const float4*>(&P.bias[l][c0 + g * 8]);
@@ -200,13 +202,19 @@ __device__ __forceinline__ void epi_chunk_store(const Params& P, int l, float in
       split8_f8(y, hi, lo8, hi8);
       *reinterpret_cast<uint4*>(p) = hi;
       const int c8 = c16_0 + g;  // 8-column group within the K-block
-      uint8_t* q = kb_base + kTileBytesA + ((f8_chunk(c8) ^ x7) << 4) + (c8 & 1) * 8;
-      uint8_t* r = kb_base + kTileBytesA + (((f8_chunk(c8) + 4) ^ x7) << 4) + (c8 & 1) * 8;
-      if (!NPCD_EXP_NOSTS8) {
-        *reinterpret_cast<uint2*>(q) = lo8;
-        *reinterpret_cast<uint2*>(r) = hi8;
+      // The lo8 / hi8 bytes of two neighbouring 8-column groups share a 16-byte chunk: one 16-byte store per 16 columns.  (ncu on
+      // the version with 8-byte stores: 4 wavefronts per STS.64 instead of 2 -- the 32 rows of a warp put their 8 bytes into the
+      // same half of every bank group -- 3.0e9 store bank conflicts per launch, 41 % of all shared-store wavefronts.)
+      uint8_t* q = kb_base + kTileBytesA + ((f8_chunk(c8) ^ x7) << 4);
+      uint8_t* r = kb_base + kTileBytesA + (((f8_chunk(c8) + 4) ^ x7) << 4);
+      if (!(g & 1)) {
+        lo8_even = lo8;
+        hi8_even = hi8;
+      } else if (!NPCD_EXP_NOSTS8) {
+        *reinterpret_cast<uint4*>(q) = make_uint4(lo8_even.x, lo8_even.y, lo8.x, lo8.y);
+        *reinterpret_cast<uint4*>(r) = make_uint4(hi8_even.x, hi8_even.y, hi8.x, hi8.y);
       } else if (lo8.x == 0x12345678u && hi8.y == 0x9abcdef0u) {  // keeps the conversions alive
-        *reinterpret_cast<uint2*>(q) = lo8;
+        *reinterpret_cast<uint4*>(q) = make_uint4(lo8_even.x, lo8_even.y, lo8.x, lo8.y);
       }
     }
   }
@@ -690,8 +698,13 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
       if (!kF8) {
         *reinterpret_cast<uint4*>(t + kTileBytesA + ((c ^ x7) << 4)) = c_lo[src];
       } else {
-        *reinterpret_cast<uint2*>(t + kTileBytesA + ((f8_chunk(c, kb == 0) ^ x7) << 4) + (c & 1) * 8) = make_uint2(c_lo[src].x, c_lo[src].y);
-        *reinterpret_cast<uint2*>(t + kTileBytesA + (((f8_chunk(c, kb == 0) + 4) ^ x7) << 4) + (c & 1) * 8) = make_uint2(c_lo[src].z, c_lo[src].w);
+        // (c, c + 1), c even, share the 16-byte chunks of their lo8 / hi8 bytes: one 16-byte store each when the odd one comes
+        if (c & 1) {
+          *reinterpret_cast<uint4*>(t + kTileBytesA + ((f8_chunk(c, kb == 0) ^ x7) << 4)) =
+              make_uint4(c_lo[src - 1].x, c_lo[src - 1].y, c_lo[src].x, c_lo[src].y);
+          *reinterpret_cast<uint4*>(t + kTileBytesA + (((f8_chunk(c, kb == 0) + 4) ^ x7) << 4)) =
+              make_uint4(c_lo[src - 1].z, c_lo[src - 1].w, c_lo[src].z, c_lo[src].w);
+        }
       }
     };
     auto publish_a0 = [&](int kb) {
