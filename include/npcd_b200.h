@@ -176,7 +176,8 @@ typedef struct {
   const int* perm;
   float scale;
   void* out;
-  int format; /* 0: fp16 hi + fp16 lo tiles ("f16x3" scheme); 1: fp16 + e4m3 tiles ("f16+e4m3x2" scheme, see npcd_tc_pack_weights_f8) */
+  int format; /* 0: fp16 hi + fp16 lo tiles ("f16x3" scheme); 1: fp16 + e4m3 tiles ("f16+e4m3x2" scheme, see npcd_tc_pack_weights_f8);
+                 2: as 1 with the 8-bit tile in K = 32 steps of [Whi8 x 16 | Wlo8 x 16] (pair layers 1..3, npcd_field_tc_fwd stages bit 5) */
 } npcd_tc_pack_job;
 int npcd_tc_pack_weights_batched(const npcd_tc_pack_job* jobs, int n_jobs, void* stream);
 /* workspace (device bytes) for `capacity` kept samples (< 2^27 per launch): the pre-split [S,256] aggregate image that links the
@@ -190,7 +191,10 @@ int npcd_field_tc_fwd(const int* nbr_idx, const float* sample_pos, const float* 
                                     bit3: `weights` were packed in format 1 -- run the "f16 + e4m3 x 2" operand scheme (one fp16
                                     product + two e4m3 correction products per layer instead of three fp16 products),
                                     bit4 (with bit3): only the activation-rounding correction product is issued ("f16 + e4m3": the
-                                    weights are then effectively rounded to fp16; 1.5 instead of 2 tensor passes per product) */,
+                                    weights are then effectively rounded to fp16; 1.5 instead of 2 tensor passes per product),
+                                    bit5 (with bit3, without bit4; pair stage only): weights->pair[1..3] were packed in format 2 --
+                                    the A operand of those layers lives in tensor memory (epilogues convert the accumulator in
+                                    place), shared memory only feeds the weights */,
                       int* error_flag /* device int, optional */, int num_sms, void* stream);
 /* fp32 rows [n,256] <-> the pre-split operand image the tensor-core kernels exchange: per 128-row tile 4 K-blocks x
  * (fp16 hi 16 KB, fp16 lo 16 KB) in the SWIZZLE_128B layout; ceil(n / 128) * 128 KB.                                           */

@@ -221,6 +221,37 @@ __device__ __forceinline__ void epi_chunk_store(const Params& P, int l, float in
   if (mask_out) *mask_out = mbits;
 }
 
+// The same epilogue arithmetic for the tensor-memory operand form (kTS): every 16 values of the chunk (groups 2 p, 2 p + 1) go back
+// into the 16 accumulator columns they came from, t_chunk + 16 p: [fp16 x 16 (8 columns) | lo8 x 16 (4) | hi8 x 16 (4)].
+template <int kG0 = 0, int kG1 = 4>
+__device__ __forceinline__ void epi_chunk_ts(const Params& P, int l, float inv, float slope, const uint32_t (&v)[32], int c0,
+                                             uint32_t t_chunk) {
+  static_assert(kG0 % 2 == 0 && kG1 % 2 == 0, "pieces of 16 values");
+  const uint64_t inv2 = pack2(inv, inv), slope2 = pack2(slope, slope);
+#pragma unroll
+  for (int p = kG0 / 2; p < kG1 / 2; ++p) {
+    uint32_t w[16];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int g = 2 * p + h;
+      const float4 b0 = *reinterpret_cast<const float4*>(&P.bias[l][c0 + g * 8]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&P.bias[l][c0 + g * 8 + 4]);
+      float y[8];
+      act2(v[g * 8 + 0], v[g * 8 + 1], inv2, b0.x, b0.y, slope2, y[0], y[1]);
+      act2(v[g * 8 + 2], v[g * 8 + 3], inv2, b0.z, b0.w, slope2, y[2], y[3]);
+      act2(v[g * 8 + 4], v[g * 8 + 5], inv2, b1.x, b1.y, slope2, y[4], y[5]);
+      act2(v[g * 8 + 6], v[g * 8 + 7], inv2, b1.z, b1.w, slope2, y[6], y[7]);
+      uint4 hi;
+      uint2 lo8, hi8;
+      split8_f8(y, hi, lo8, hi8);
+      w[4 * h + 0] = hi.x; w[4 * h + 1] = hi.y; w[4 * h + 2] = hi.z; w[4 * h + 3] = hi.w;
+      w[8 + 2 * h] = lo8.x; w[8 + 2 * h + 1] = lo8.y;
+      w[12 + 2 * h] = hi8.x; w[12 + 2 * h + 1] = hi8.y;
+    }
+    tmem_st16(t_chunk + 16u * (uint32_t)p, w);
+  }
+}
+
 // Weight sharing across a 2-CTA cluster.  ncu on the single-CTA version: 878 GB per step of L2 -> SM reads, all of it the 0.90 MB of
 // packed weights re-streamed for every 128-row tile -- energy that buys no FLOPs on a board sitting on its power cap.  Both CTAs of a
 // cluster walk the same weight schedule, so CTA 0's producer issues ONE multicast bulk copy per ring stage that lands in both shared
@@ -237,9 +268,18 @@ constexpr bool kCluster = NPCD_TC_CLUSTER != 0;
 #endif
 
 // ------------------------------------------------------------------------------------------------------------- kernel ----
-template <int kMode, bool kF8 = false>
+// kTS (inference pair kernel, f16 + e4m3 x 2 scheme): the A operand of layers 1..3 lives in TENSOR MEMORY.  A layer epilogue
+// converts its accumulator IN PLACE -- the 16 fp32 columns a thread has just loaded take the fp16 image (8 columns), the lo8 bytes
+// (4 columns) and the hi8 bytes (4 columns) of those 16 values -- and the next layer's MMAs read that buffer as their A operand
+// while accumulating into the other one (the trick of attention kernels that keep P over S).  Per 16 input features: one K16
+// kind::f16 MMA on columns [0, 8) and ONE K32 kind::f8f6f4 MMA on columns [8, 16) = [lo8 | hi8] against weight rows [Whi8 | Wlo8]
+// (weight format 2) -- both correction products in one instruction.  Shared memory then only feeds B (8 KB instead of 12 KB per
+// M128 N256 step), the epilogues store nothing into shared memory, and K-blocks 0..1 are free for the next tile's layer-0 input as
+// soon as layer 0's MMAs are done.  Layer 0 itself still reads its gathered input from shared memory.
+template <int kMode, bool kF8 = false, bool kTS = false>
 __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
     k_field_tc(const __grid_constant__ Params P) {
+  static_assert(!kTS || (kMode == MODE_PAIR && kF8 && NPCD_TC_2SM == 0), "TS form: inference pair kernel, f8 scheme, 1-SM");
   constexpr bool kPro = kMode == MODE_PAIR;  // dedicated input warps (11..14)
   // inference: the epilogues publish K-block 0 of their output in two halves, so the next layer's MMAs start after 16 values per
   // thread instead of 32 (timeline of CTA 0: the first-block latency was ~1450 of the ~7100 cycles a layer takes)
@@ -515,6 +555,33 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
             }
             tc_fence_after();
             const uint64_t b = desc_w0 + (uint64_t)(st * (kStageBytes >> 4)), b2 = desc_w0 + (uint64_t)(st2 * (kStageBytes >> 4));
+            if (kTS) {
+              // A from tensor memory: feature group t = 2 h + p of the block (thread half h, 16-value piece p) sits in columns
+              // [32 h + 16 p, + 16) of the OTHER accumulator buffer: fp16 in the first 8, [lo8 | hi8] in the last 8
+              const uint32_t a_t = tmem_base + (ab ^ 1u) * 256u;
+              if (elect_one()) {
+                umma_f16_ts(d_tmem, a_t, b, kIdescMma, 0u);
+                umma_f16_ts(d_tmem, a_t + 32u, b + 4, kIdescMma, 1u);
+                umma_f8_ts(d_tmem, a_t + 8u, b2, kIdescMma, 1u);
+                umma_f8_ts(d_tmem, a_t + 40u, b2 + 4, kIdescMma, 1u);
+              }
+              __syncwarp();
+              timed_wait(bar(kBarARdy2), ph_ar2, tw_a);
+              ph_ar2 ^= 1u;
+              tc_fence_after();
+              if (elect_one()) {
+                umma_f16_ts(d_tmem, a_t + 16u, b + 2, kIdescMma, 1u);
+                umma_f16_ts(d_tmem, a_t + 48u, b + 6, kIdescMma, 1u);
+                commit_stage(st);
+                umma_f8_ts(d_tmem, a_t + 24u, b2 + 2, kIdescMma, 1u);
+                umma_f8_ts(d_tmem, a_t + 56u, b2 + 6, kIdescMma, 1u);
+                commit_stage(st2);
+              }
+              __syncwarp();
+              for (int q = 0; q < 2; ++q)
+                if (++st == kSt) { st = 0; ph_w ^= 1; }
+              continue;
+            }
             if (elect_one()) {
               mma16(d_tmem, a_hi, b, 0u);
               mma16(d_tmem, a_hi + 4, b + 4, 1u);
@@ -553,6 +620,32 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
             __syncwarp();
             for (int q = 0; q < 2; ++q)
               if (++st == kSt) { st = 0; ph_w ^= 1; }
+            continue;
+          }
+          if (kTS && l > 0) {  // K-blocks 1..3 of a tensor-memory operand: four K16 steps on the fp16 stage, four K32 steps on the 8-bit stage
+            const uint32_t a_t = tmem_base + (ab ^ 1u) * 256u + 64u * (uint32_t)kb;
+            timed_wait(bar(kWF + st), ph_w, tw_w);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t b = desc_w0 + (uint64_t)(st * (kStageBytes >> 4));
+#pragma unroll
+              for (int t = 0; t < 4; ++t) umma_f16_ts(d_tmem, a_t + 16u * t, b + 2 * t, kIdescMma, 1u);
+              commit_stage(st);
+            }
+            __syncwarp();
+            if (++st == kSt) { st = 0; ph_w ^= 1; }
+            timed_wait(bar(kWF + st), ph_w, tw_w);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t b = desc_w0 + (uint64_t)(st * (kStageBytes >> 4));
+#pragma unroll
+              for (int t = 0; t < 4; ++t) umma_f8_ts(d_tmem, a_t + 16u * t + 8u, b + 2 * t, kIdescMma, 1u);
+              commit_stage(st);
+              if (kb == nkb - 1) commit_cta(kBarAccRdy + ab);
+            }
+            if (lane == 0 && kb == nkb - 1 && l < 4) NPCD_TL(pass, 18 + 3 * l);
+            __syncwarp();
+            if (++st == kSt) { st = 0; ph_w ^= 1; }
             continue;
           }
           // stage "hi": A_hi*W_hi + A_lo*W_hi
@@ -596,7 +689,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
             commit_stage(st);
             // this K-block may take the next tile's first operand (arrive only where somebody waits: pair mode restages
             // K-blocks 0..1, and the last tile of a CTA has no successor)
-            if (l == n_layers - 1 && has_next && (!kPair || kb < 2)) commit_cta(kBarAFree + kb);
+            if (l == (kTS ? 0 : n_layers - 1) && has_next && (!kPair || kb < 2)) commit_cta(kBarAFree + kb);
             if (kb == nkb - 1) commit_cta(kBarAccRdy + ab);
           }
           if (lane == 0 && kb == nkb - 1 && l < 4) NPCD_TL(pass, 18 + 3 * l);  // last MMA of the layer issued
@@ -877,8 +970,9 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
 
     // publish one K-block of the A operand (all 8 epilogue warps arrive once per K-block)
     auto publish = [&](int barrier_index) {
+      if (kTS) tmem_wait_st();  // (the layer-0 input of a kTS kernel is published by the input warps, not here)
       tc_fence_before();
-      fence_proxy_async();
+      if (!kTS) fence_proxy_async();
       __syncwarp();
       if (lane == 0) arrive_issuer(barrier_index);
     };
@@ -938,17 +1032,20 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
         if (kTrainP) mptr = P.stash_mask[l] + ((size_t)tile_now * 128 + row) * 8 + (2 * i + half);
         if (kTrainH && l >= 2) mptr = P.hstash_mask[l - 1] + ((size_t)tile_now * 128 + row) * 8 + (2 * i + half);
         if (kSplit0 && i == 0) {
-          epi_chunk_store<kF8, 0, 2>(P, l, inv, slope, v[0], half * 32, sA, rowbase, x7, feat_row, nullptr);
+          if (kTS) epi_chunk_ts<0, 2>(P, l, inv, slope, v[0], half * 32, t_acc + half * 32);
+          else epi_chunk_store<kF8, 0, 2>(P, l, inv, slope, v[0], half * 32, sA, rowbase, x7, feat_row, nullptr);
           publish(kBarARdy + 0);
           if (kSplitLd) {
             tmem_ld16_async(t_acc + half * 32 + 16, &v[0][16]);
             tmem_ld32_async(t_acc + (2 + half) * 32, v[1]);
             tmem_wait16(&v[0][16]);
           }
-          epi_chunk_store<kF8, 2, 4>(P, l, inv, slope, v[0], half * 32, sA, rowbase, x7, feat_row, nullptr);
+          if (kTS) epi_chunk_ts<2, 4>(P, l, inv, slope, v[0], half * 32, t_acc + half * 32);
+          else epi_chunk_store<kF8, 2, 4>(P, l, inv, slope, v[0], half * 32, sA, rowbase, x7, feat_row, nullptr);
           publish(kBarARdy2);
         } else {
-          epi_chunk_store<kF8>(P, l, inv, slope, v[i & 1], (2 * i + half) * 32, sA, rowbase, x7, feat_row, mptr);
+          if (kTS) epi_chunk_ts<0, 4>(P, l, inv, slope, v[i & 1], (2 * i + half) * 32, t_acc + (2 * i + half) * 32);
+          else epi_chunk_store<kF8>(P, l, inv, slope, v[i & 1], (2 * i + half) * 32, sA, rowbase, x7, feat_row, mptr);
           if (i == 3) release_acc(ab);
           publish(kBarARdy + i);
         }
@@ -1377,7 +1474,8 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
 // Pack an fp32 [256, k_in] nn.Linear weight into per-K-block pre-swizzled fp16 hi/lo tiles (the exact shared-memory image the
 // MMA descriptors expect), multiplied by `scale` (a power of two).  perm[k'] = source column of packed column k' (or -1 = 0).
 // format 0: fp16 hi tile + fp16 lo tile; format 1 (f16 + e4m3 x 2 scheme, tc_ptx.cuh): fp16 tile of v * 2^13 + one 8-bit tile whose
-// row n is [Whi8 = e4m3(v * 2^5) of the 64 columns | Wlo8 = e4m3((v * 2^13 - W16) * 2^4) of the 64 columns]
+// row n is [Whi8 = e4m3(v * 2^5) of the 64 columns | Wlo8 = e4m3((v * 2^13 - W16) * 2^4) of the 64 columns]; format 2: the same values,
+// 8-bit tile rows = four K = 32 steps of [Whi8 of 16 columns | Wlo8 of the same 16 columns] (A operand in tensor memory, kTS)
 __device__ __forceinline__ void pack_weight_element(uint8_t* tile, int n, int kk, float v, int format, bool full_block) {
   const size_t off = (size_t)(n >> 3) * 1024 + (n & 7) * 128 + (((kk >> 3) ^ (n & 7)) << 4) + (kk & 7) * 2;
   if (format == 0) {
@@ -1392,6 +1490,13 @@ __device__ __forceinline__ void pack_weight_element(uint8_t* tile, int n, int kk
     const uint32_t w8 = cvt_e4m3x2_f32(v * 32.0f, (vs - __half2float(hi)) * 16.0f);  // byte 0 = Whi8, byte 1 = Wlo8
     const int c8 = kk >> 3;
     uint8_t* t8 = tile + kTileBytesW;
+    if (format == 2) {  // tensor-memory operand form: per 16 input features one K = 32 step, row bytes [Whi8 x 16 | Wlo8 x 16]
+      const int t = kk >> 4;
+      const size_t row = (size_t)(n >> 3) * 1024 + (n & 7) * 128;
+      t8[row + (((2 * t) ^ (n & 7)) << 4) + (kk & 15)] = (uint8_t)(w8 & 0xffu);
+      t8[row + (((2 * t + 1) ^ (n & 7)) << 4) + (kk & 15)] = (uint8_t)(w8 >> 8);
+      return;
+    }
     t8[swz8_lo(n, c8, full_block) + (kk & 7)] = (uint8_t)(w8 & 0xffu);
     t8[swz8_hi(n, c8, full_block) + (kk & 7)] = (uint8_t)(w8 >> 8);
   }
@@ -1610,7 +1715,7 @@ extern "C" int npcd_tc_pack_weights_batched(const npcd_tc_pack_job* jobs, int n_
     NPCD_CHECK_ARG(j.w && j.out, "null pointer");
     NPCD_CHECK_ARG(j.k_in > 0 && j.k_pad > 0 && j.k_pad % 16 == 0 && j.k_pad <= 256 && (j.perm || j.k_in <= j.k_pad), "bad sizes");
     NPCD_CHECK_ARG(j.n_rows > 0 && j.n_rows <= 256 && j.ld > 0 && !(j.perm && j.transpose), "bad job");
-    NPCD_CHECK_ARG(j.format == 0 || (j.format == 1 && j.k_pad % 32 == 0), "bad format");
+    NPCD_CHECK_ARG(j.format == 0 || (j.format == 1 && j.k_pad % 32 == 0) || (j.format == 2 && j.k_pad % 64 == 0), "bad format");
     J.j[i] = j;
   }
   tc::k_pack_weights_batched<<<dim3(256, n_jobs), 256, 0, (cudaStream_t)stream>>>(J);
@@ -1696,12 +1801,12 @@ void fill_layer(tc::Params& P, int i, const npcd_tc_layer& src, int epi, bool f8
 long long* g_timeline = nullptr;
 long long* g_timeline_heads = nullptr;
 
-template <int kMode, bool kF8 = false>
+template <int kMode, bool kF8 = false, bool kTS = false>
 int launch_tc(const tc::Params& P_in, long long tiles, int num_sms, cudaStream_t st, const char* what) {
   static thread_local tc::Params P;
   P = P_in;
   P.timeline = kMode == tc::MODE_PAIR ? g_timeline : (kMode == tc::MODE_HEADS ? g_timeline_heads : nullptr);
-  cudaError_t e = cudaFuncSetAttribute(tc::k_field_tc<kMode, kF8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal);
+  cudaError_t e = cudaFuncSetAttribute(tc::k_field_tc<kMode, kF8, kTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal);
   if (e != cudaSuccess) {
     set_error("%s: cannot opt in to %d bytes of shared memory: %s", what, tc::kSmemTotal, cudaGetErrorString(e));
     return 2;
@@ -1709,14 +1814,14 @@ int launch_tc(const tc::Params& P_in, long long tiles, int num_sms, cudaStream_t
   if (num_sms <= 0) num_sms = 148;
   unsigned grid = (unsigned)(tiles < num_sms ? (tiles > 0 ? tiles : 1) : num_sms);
   if (tc::kCluster) grid = (grid + 1u) & ~1u;  // whole 2-CTA clusters
-  tc::k_field_tc<kMode, kF8><<<grid, tc::threads_for<kMode>(), tc::kSmemTotal, st>>>(P);
+  tc::k_field_tc<kMode, kF8, kTS><<<grid, tc::threads_for<kMode>(), tc::kSmemTotal, st>>>(P);
   return check_launch(what);
 }
 }  // namespace
 
 namespace {
 // dense packing (pair_off = exclusive scan of the neighbour counts, greedy tile starts) + the pair kernel
-template <int kMode, bool kF8 = false>
+template <int kMode, bool kF8 = false, bool kTS = false>
 int pair_stage(const int* nbr_idx, const float* sample_pos, const float* kp_pos, const float* kp_feat, const long long* n_samples_dev,
                long long capacity, const npcd_mlp_tc_weights* W, const TcWorkspace& ws, uint8_t* base,
                const npcd_pair_stash_layout* layout, uint8_t* stash, int* error_flag, int num_sms, cudaStream_t st,
@@ -1760,7 +1865,7 @@ int pair_stage(const int* nbr_idx, const float* sample_pos, const float* kp_pos,
     P.stash_idx = (int*)(stash + layout->idx);
     P.stash_samp = (int*)(stash + layout->samp);
   }
-  return launch_tc<kMode, kF8>(P, ws.max_tiles, num_sms, st, "npcd_field_tc_fwd(pair)");
+  return launch_tc<kMode, kF8, kTS>(P, ws.max_tiles, num_sms, st, "npcd_field_tc_fwd(pair)");
 }
 }  // namespace
 
@@ -1834,8 +1939,13 @@ extern "C" int npcd_field_tc_fwd(const int* nbr_idx, const float* sample_pos, co
   const bool f8 = (stages & 8) != 0;  // W was packed with format 1 (f16 + e4m3 x 2 operand scheme)
   const int no_wcorr = (stages & 16) ? 1 : 0;  // ... and only the activation-rounding correction is issued ("f16+e4m3")
   NPCD_CHECK_ARG(!no_wcorr || f8, "stages bit 4 (single correction product) needs bit 3 (f16 + e4m3 operands)");
+  const bool ts = (stages & 32) != 0;  // W->pair[1..3] were packed with format 2: A operand of those layers in tensor memory
+  NPCD_CHECK_ARG(!ts || (f8 && !no_wcorr && NPCD_TC_2SM == 0),
+                 "stages bit 5 (tensor-memory operand form) needs bit 3, excludes bit 4 and the 2-SM build");
   if (stages & 1) {
-    rc = f8 ? pair_stage<tc::MODE_PAIR, true>(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, W, ws, base, nullptr, nullptr,
+    rc = ts ? pair_stage<tc::MODE_PAIR, true, NPCD_TC_2SM == 0>(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, W, ws, base,
+                                                                 nullptr, nullptr, error_flag, num_sms, st, 0)
+       : f8 ? pair_stage<tc::MODE_PAIR, true>(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, W, ws, base, nullptr, nullptr,
                                               error_flag, num_sms, st, no_wcorr)
             : pair_stage<tc::MODE_PAIR>(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, W, ws, base, nullptr, nullptr,
                                         error_flag, num_sms, st);

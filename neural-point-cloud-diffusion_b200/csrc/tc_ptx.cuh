@@ -158,6 +158,37 @@ __device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t adesc, uint64_
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- A operand from TENSOR MEMORY ("TS" form): lane = row, 32-bit column = 2 consecutive fp16 / 4 consecutive 8-bit K elements, a
+// K16 (f16) or K32 (f8f6f4) step = 8 consecutive columns; B still comes from shared memory.  The operand fetch of an M128 N256 step
+// drops from 12 KB to 8 KB of shared memory -- the measured ceiling of a shared-memory-fed 1-SM MMA is ~84 B/clk (159 cycles per
+// instruction, profiles/r2_ablation_pair.md), the TMEM path is not on that budget.
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// register -> TMEM store of 16 consecutive 32-bit columns of this thread's lane; complete after tmem_wait_st()
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---- cta_group::2: one instruction issued by the leader CTA of a pair runs on both SMs: M = 256 (rows 0-127 from the leader's
 // shared memory / TMEM, 128-255 from the peer's), every CTA supplies its own A rows and HALF of B (N / 2 rows of the K-major weight
 // tile), so an SM reads 8 KB instead of 12 KB of operands per M128 N256 K16-equivalent and holds half of every weight tile ----

@@ -28,9 +28,19 @@ DEFAULT_PRECISION = os.environ.get("NPCD_PRECISION", "f16+e4m3x2")  # the enviro
 F8_PRECISIONS = ("f16+e4m3x2", "f16+e4m3")  # schemes that use the format-1 (f16 + e4m3) operand images / weight tables
 
 
+# "f16+e4m3x2" inference: layers 1..3 of the pair MLP take their A operand from tensor memory (`stages` bit 5, weight format 2).
+# NPCD_TC_TS=0 keeps the shared-memory operand form of those layers (development aid / cross-check).
+TC_TS = os.environ.get("NPCD_TC_TS", "1") != "0"
+
+
 def stage_bits(precision: str) -> int:
     """`stages` bits 3 / 4 of npcd_field_tc_fwd for an operand scheme."""
     return {"f16x3": 0, "f16+e4m3x2": 8, "f16+e4m3": 8 | 16}[precision]
+
+
+def pair_stage_bits(precision: str) -> int:
+    """... plus bit 5 for the pair stage when its weights are the tensor-memory-form table."""
+    return stage_bits(precision) | (32 if precision == "f16+e4m3x2" and TC_TS else 0)
 
 # number of kernels launched by this process through the C-ABI (bench.py reports it as gpu_launches)
 LAUNCHES = 0
@@ -456,6 +466,7 @@ class PackedTcWeights:
         self._outs = (self._host(HIDDEN), self._host(1), self._host(3 * HIDDEN), self._host(3))
         self._f8 = None
         self._folded_f8 = None
+        self._f8_ts = None  # "f16+e4m3x2" table of the pair stage: layers 1..3 in format 2 (tensor-memory operand form)
         jobs = self._fill(s, 0)
         if for_training:
             jobs += self._dgrad_jobs() + self._hdgrad_jobs()
@@ -496,21 +507,24 @@ class PackedTcWeights:
             if pack is not None:
                 for j, ref in enumerate(refs):
                     pack[1][j] = 1.0 / scale_of(ref)
-        self._folded = self._f8 = self._folded_f8 = None
+        self._folded = self._f8 = self._folded_f8 = self._f8_ts = None
         self._run([j for j, _ in self._all_jobs])
 
-    def _fill(self, s, fmt: int):
+    def _fill(self, s, fmt: int, pair_fmt: int = None):
         """Fills the layer table of ``s`` with freshly allocated packed-weight buffers in operand format ``fmt`` (0: fp16 hi/lo,
-        1: fp16 + e4m3) and returns the pack jobs that fill them."""
+        1: fp16 + e4m3; ``pair_fmt`` = 2: layers 1..3 of the pair MLP in the tensor-memory operand form) and returns the pack jobs
+        that fill them."""
         jobs = []
+        pair_fmt = fmt if pair_fmt is None else pair_fmt
 
-        def layer(dst, i, k_pad, perm=None):
+        def layer(dst, i, k_pad, perm=None, fmt_l=None):
             w = self.ws[i]
             assert w.shape[0] == HIDDEN
+            fmt_l = fmt if fmt_l is None else fmt_l
             out = torch.empty(((k_pad + 63) // 64) * 2 * 32768, dtype=torch.uint8, device=self.dev)
             if k_pad % 64:
                 out.zero_()  # the tail of the last K-block is never written by the pack kernel
-            jobs.append(self._job(w, w.shape[1], HIDDEN, w.shape[1], k_pad, False, perm, self.scales[i], out, fmt,
+            jobs.append(self._job(w, w.shape[1], HIDDEN, w.shape[1], k_pad, False, perm, self.scales[i], out, fmt_l,
                                   sref=i if fmt == 0 else None))
             dst.packed_w, dst.bias, dst.inv_scale, dst.k_pad = out.data_ptr(), self._bias[i], 1.0 / self.scales[i], k_pad
             if fmt == 0:
@@ -518,7 +532,7 @@ class PackedTcWeights:
 
         layer(s.pair[0], 0, PAIR_IN_COLS, self.perm0)
         for i in range(1, 4):
-            layer(s.pair[i], i, 256)
+            layer(s.pair[i], i, 256, fmt_l=pair_fmt)
         layer(s.agg, 4, 256)
         layer(s.shape, 5, 256)
         for i in range(4):
@@ -538,7 +552,20 @@ class PackedTcWeights:
             f.feat_dim = self.struct.feat_dim
             self._run(self._fill(f, 1))
             self._f8 = f
-        return self.folded_struct(1) if folded else self._f8
+        if folded:
+            return self.folded_struct(1)
+        if precision == "f16+e4m3x2" and TC_TS:  # the pair stage's table: layers 1..3 in format 2, everything else shared with _f8
+            if self._f8_ts is None:
+                f = _lib.TcWeights()
+                C.memmove(C.byref(f), C.byref(self._f8), C.sizeof(_lib.TcWeights))
+                scratch = _lib.TcWeights()
+                jobs = self._fill(scratch, 1, pair_fmt=2)
+                self._run([j for j in jobs if int(j.format) == 2])
+                for i in range(1, 4):
+                    C.memmove(C.byref(f.pair[i]), C.byref(scratch.pair[i]), C.sizeof(scratch.pair[i]))
+                self._f8_ts = f
+            return self._f8_ts
+        return self._f8
 
     # ---- helpers --------------------------------------------------------------------------------------------------------
     def _host(self, n):
@@ -697,7 +724,8 @@ def field_tc_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity: 
     f8 = stage_bits(precision)  # `stages` bits 3 / 4: operand scheme of the packed weights, one or two correction products
     args = (ptr(nbr_idx), ptr(sample_pos), ptr(kp_pos), ptr(kp_feat), ptr(n_samples_dev), capacity,
             C.byref(weights.struct_for(precision, False)), ptr(ws), nbytes, ptr(rgbs), ptr(feat))
-    _timed("pair_mlp", lambda: call("npcd_field_tc_fwd", *args, 1 | f8, ptr(weights.error_flag), sm_count(dev), _stream()))
+    _timed("pair_mlp", lambda: call("npcd_field_tc_fwd", *args, 1 | pair_stage_bits(precision), ptr(weights.error_flag), sm_count(dev),
+                                    _stream()))
     if FOLD_HEADS and not want_feat:  # local_field.8 folded into shape_net.0 / channel_net.0: 5 GEMMs per sample instead of 6
         fargs = args[:6] + (C.byref(weights.struct_for(precision, True)),) + args[7:]
         _timed("heads", lambda: call("npcd_field_tc_fwd", *fargs, 4 | f8, ptr(weights.error_flag), sm_count(dev), _stream()))
