@@ -192,9 +192,9 @@ int npcd_field_tc_fwd(const int* nbr_idx, const float* sample_pos, const float* 
                                     product + two e4m3 correction products per layer instead of three fp16 products),
                                     bit4 (with bit3): only the activation-rounding correction product is issued ("f16 + e4m3": the
                                     weights are then effectively rounded to fp16; 1.5 instead of 2 tensor passes per product),
-                                    bit5 (with bit3, without bit4; pair stage only): weights->pair[1..3] were packed in format 2 --
-                                    the A operand of those layers lives in tensor memory (epilogues convert the accumulator in
-                                    place), shared memory only feeds the weights */,
+                                    bit5 (with bit3, without bit4; pair stage, and heads stage with bit2): weights->pair[1..3] resp.
+                                    weights->chan[1..3] were packed in format 2 -- the A operand of those layers lives in tensor
+                                    memory (epilogues convert the accumulator in place), shared memory only feeds the weights */,
                       int* error_flag /* device int, optional */, int num_sms, void* stream);
 /* fp32 rows [n,256] <-> the pre-split operand image the tensor-core kernels exchange: per 128-row tile 4 K-blocks x
  * (fp16 hi 16 KB, fp16 lo 16 KB) in the SWIZZLE_128B layout; ceil(n / 128) * 128 KB.                                           */

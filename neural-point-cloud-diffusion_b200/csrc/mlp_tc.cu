@@ -279,7 +279,12 @@ constexpr bool kCluster = NPCD_TC_CLUSTER != 0;
 template <int kMode, bool kF8 = false, bool kTS = false>
 __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
     k_field_tc(const __grid_constant__ Params P) {
-  static_assert(!kTS || (kMode == MODE_PAIR && kF8 && NPCD_TC_2SM == 0), "TS form: inference pair kernel, f8 scheme, 1-SM");
+  static_assert(!kTS || ((kMode == MODE_PAIR || kMode == MODE_HEADS) && kF8 && NPCD_TC_2SM == 0),
+                "TS form: inference kernels, f8 scheme, 1-SM");
+  // first layer whose A operand is the previous layer's epilogue output (and therefore, kTS, in tensor memory): layer 1 of the
+  // pair MLP; channel_net.2 of the FOLDED heads (layers: shape_net.0', channel_net.0' -- both read the tile image in shared
+  // memory --, channel_net.2, .4, .6)
+  constexpr int kTsFirst = kMode == MODE_PAIR ? 1 : 2;
   constexpr bool kPro = kMode == MODE_PAIR;  // dedicated input warps (11..14)
   // inference: the epilogues publish K-block 0 of their output in two halves, so the next layer's MMAs start after 16 values per
   // thread instead of 32 (timeline of CTA 0: the first-block latency was ~1450 of the ~7100 cycles a layer takes)
@@ -555,7 +560,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
             }
             tc_fence_after();
             const uint64_t b = desc_w0 + (uint64_t)(st * (kStageBytes >> 4)), b2 = desc_w0 + (uint64_t)(st2 * (kStageBytes >> 4));
-            if (kTS) {
+            if (kTS && l >= kTsFirst) {
               // A from tensor memory: feature group t = 2 h + p of the block (thread half h, 16-value piece p) sits in columns
               // [32 h + 16 p, + 16) of the OTHER accumulator buffer: fp16 in the first 8, [lo8 | hi8] in the last 8
               const uint32_t a_t = tmem_base + (ab ^ 1u) * 256u;
@@ -622,7 +627,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
               if (++st == kSt) { st = 0; ph_w ^= 1; }
             continue;
           }
-          if (kTS && l > 0) {  // K-blocks 1..3 of a tensor-memory operand: four K16 steps on the fp16 stage, four K32 steps on the 8-bit stage
+          if (kTS && l >= kTsFirst) {  // K-blocks 1..3 of a tensor-memory operand: four K16 steps on the fp16 stage, four K32 steps on the 8-bit stage
             const uint32_t a_t = tmem_base + (ab ^ 1u) * 256u + 64u * (uint32_t)kb;
             timed_wait(bar(kWF + st), ph_w, tw_w);
             tc_fence_after();
@@ -689,7 +694,8 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
             commit_stage(st);
             // this K-block may take the next tile's first operand (arrive only where somebody waits: pair mode restages
             // K-blocks 0..1, and the last tile of a CTA has no successor)
-            if (l == (kTS ? 0 : n_layers - 1) && has_next && (!kPair || kb < 2)) commit_cta(kBarAFree + kb);
+            // (kTS: the last layer that reads its A operand from shared memory releases the K-blocks for the next tile's input)
+            if (l == (kTS ? kTsFirst - 1 : n_layers - 1) && has_next && (!kPair || kb < 2)) commit_cta(kBarAFree + kb);
             if (kb == nkb - 1) commit_cta(kBarAccRdy + ab);
           }
           if (lane == 0 && kb == nkb - 1 && l < 4) NPCD_TL(pass, 18 + 3 * l);  // last MMA of the layer issued
@@ -1870,7 +1876,7 @@ int pair_stage(const int* nbr_idx, const float* sample_pos, const float* kp_pos,
 }  // namespace
 
 namespace {
-template <int kMode, bool kF8 = false>
+template <int kMode, bool kF8 = false, bool kTS = false>
 int heads_stage(const npcd_mlp_tc_weights* W, uint8_t* img, float* rgbs, float* feat_out, const long long* n_samples_dev,
                 long long capacity, const npcd_pair_stash_layout* layout, uint8_t* stash, int* error_flag, int num_sms, cudaStream_t st,
                 bool folded = false, int no_wcorr = 0) {
@@ -1894,7 +1900,7 @@ int heads_stage(const npcd_mlp_tc_weights* W, uint8_t* img, float* rgbs, float* 
     for (int i = 0; i < 6; ++i) P.hstash_x[i] = stash + layout->hx[i];
     for (int i = 0; i < 5; ++i) P.hstash_mask[i] = (uint32_t*)(stash + layout->hmask[i]);
   }
-  return launch_tc<kMode, kF8>(P, (capacity + 127) / 128, num_sms, st, "npcd_field_tc_fwd(heads)");
+  return launch_tc<kMode, kF8, kTS>(P, (capacity + 127) / 128, num_sms, st, "npcd_field_tc_fwd(heads)");
 }
 }  // namespace
 
@@ -1952,7 +1958,11 @@ extern "C" int npcd_field_tc_fwd(const int* nbr_idx, const float* sample_pos, co
     if (rc) return rc;
   }
   NPCD_CHECK_ARG(!(stages & 4) || !feat_out, "the folded heads stage has no local_field.8 output to return");
-  if (stages & 6)
+  NPCD_CHECK_ARG(!ts || !(stages & 2), "stages bit 5: the heads stage has a tensor-memory form only with local_field.8 folded (bit 2)");
+  if (ts && (stages & 4))  // W->chan[1..3] in format 2
+    rc = heads_stage<tc::MODE_HEADS, true, NPCD_TC_2SM == 0>(W, img, rgbs, feat_out, n_samples_dev, capacity, nullptr, nullptr, error_flag,
+                                                             num_sms, st, true, 0);
+  else if (stages & 6)
     rc = f8 ? heads_stage<tc::MODE_HEADS, true>(W, img, rgbs, feat_out, n_samples_dev, capacity, nullptr, nullptr, error_flag, num_sms, st,
                                                 (stages & 4) != 0, no_wcorr)
             : heads_stage<tc::MODE_HEADS>(W, img, rgbs, feat_out, n_samples_dev, capacity, nullptr, nullptr, error_flag, num_sms, st,

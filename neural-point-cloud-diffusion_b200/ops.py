@@ -466,7 +466,7 @@ class PackedTcWeights:
         self._outs = (self._host(HIDDEN), self._host(1), self._host(3 * HIDDEN), self._host(3))
         self._f8 = None
         self._folded_f8 = None
-        self._f8_ts = None  # "f16+e4m3x2" table of the pair stage: layers 1..3 in format 2 (tensor-memory operand form)
+        self._f8_ts = self._folded_f8_ts = None  # "f16+e4m3x2" tables of the pair / folded heads stage: layers 1..3 resp. channel_net.2/.4/.6 in format 2
         jobs = self._fill(s, 0)
         if for_training:
             jobs += self._dgrad_jobs() + self._hdgrad_jobs()
@@ -507,7 +507,7 @@ class PackedTcWeights:
             if pack is not None:
                 for j, ref in enumerate(refs):
                     pack[1][j] = 1.0 / scale_of(ref)
-        self._folded = self._f8 = self._folded_f8 = self._f8_ts = None
+        self._folded = self._f8 = self._folded_f8 = self._f8_ts = self._folded_f8_ts = None
         self._run([j for j, _ in self._all_jobs])
 
     def _fill(self, s, fmt: int, pair_fmt: int = None):
@@ -552,20 +552,32 @@ class PackedTcWeights:
             f.feat_dim = self.struct.feat_dim
             self._run(self._fill(f, 1))
             self._f8 = f
+        ts = precision == "f16+e4m3x2" and TC_TS
         if folded:
-            return self.folded_struct(1)
-        if precision == "f16+e4m3x2" and TC_TS:  # the pair stage's table: layers 1..3 in format 2, everything else shared with _f8
+            if not ts:
+                return self.folded_struct(1)
+            if self._folded_f8_ts is None:  # the heads stage's table: channel_net.2 / .4 / .6 in format 2
+                self._folded_f8_ts = self._with_format2(self.folded_struct(1), lambda f: f.chan, (7, 8, 9))
+            return self._folded_f8_ts
+        if ts:  # the pair stage's table: layers 1..3 in format 2, everything else shared with _f8
             if self._f8_ts is None:
-                f = _lib.TcWeights()
-                C.memmove(C.byref(f), C.byref(self._f8), C.sizeof(_lib.TcWeights))
-                scratch = _lib.TcWeights()
-                jobs = self._fill(scratch, 1, pair_fmt=2)
-                self._run([j for j in jobs if int(j.format) == 2])
-                for i in range(1, 4):
-                    C.memmove(C.byref(f.pair[i]), C.byref(scratch.pair[i]), C.sizeof(scratch.pair[i]))
-                self._f8_ts = f
+                self._f8_ts = self._with_format2(self._f8, lambda f: f.pair, (1, 2, 3))
             return self._f8_ts
         return self._f8
+
+    def _with_format2(self, base, table, layer_ids):
+        """Copy of the weight table ``base`` whose entries table(f)[1..3] (layers ``layer_ids`` of self.ws) point to format-2 packs
+        (8-bit tile in K = 32 steps of [Whi8 x 16 | Wlo8 x 16]: the tensor-memory operand form of `npcd_field_tc_fwd`, stages bit 5)."""
+        f = _lib.TcWeights()
+        C.memmove(C.byref(f), C.byref(base), C.sizeof(_lib.TcWeights))
+        jobs = []
+        for slot, i in zip((1, 2, 3), layer_ids):
+            w = self.ws[i]
+            out = torch.empty(4 * 2 * 32768, dtype=torch.uint8, device=self.dev)
+            jobs.append(self._job(w, HIDDEN, HIDDEN, HIDDEN, HIDDEN, False, None, self.scales[i], out, 2))
+            table(f)[slot].packed_w = out.data_ptr()
+        self._run(jobs)
+        return f
 
     # ---- helpers --------------------------------------------------------------------------------------------------------
     def _host(self, n):
@@ -728,7 +740,8 @@ def field_tc_fwd(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity: 
                                     _stream()))
     if FOLD_HEADS and not want_feat:  # local_field.8 folded into shape_net.0 / channel_net.0: 5 GEMMs per sample instead of 6
         fargs = args[:6] + (C.byref(weights.struct_for(precision, True)),) + args[7:]
-        _timed("heads", lambda: call("npcd_field_tc_fwd", *fargs, 4 | f8, ptr(weights.error_flag), sm_count(dev), _stream()))
+        _timed("heads", lambda: call("npcd_field_tc_fwd", *fargs, 4 | pair_stage_bits(precision), ptr(weights.error_flag), sm_count(dev),
+                                     _stream()))
     else:
         _timed("heads", lambda: call("npcd_field_tc_fwd", *args, 2 | f8, ptr(weights.error_flag), sm_count(dev), _stream()))
     _count(8)  # pair-offset scan (3 launches) + greedy tile starts (walk, scan, walk) + pair kernel + heads kernel
