@@ -61,6 +61,7 @@ enum Mode { MODE_PAIR = 0, MODE_HEADS = 1, MODE_PROBE = 2, MODE_PAIR_TRAIN = 3, 
 constexpr int kOffBars = 0;       // 24 mbarriers
 constexpr int kOffTmem = 192;
 constexpr int kOffInfo = 208;     // int[2][4]: s_begin, n_samp, n_rows
+constexpr int kOffEpiBusy = 240;  // int: the epilogue warps are inside a layer epilogue (the input warps yield issue slots, kYield)
 constexpr int kOffWts = 256;      // float[2][128] raw inverse-distance weights           (pair)
 constexpr int kOffRowSamp = 1280; // u8[2][128] row -> sample-in-tile                      (pair)
 constexpr int kOffSampRow = 1536; // u8[2][128] sample-in-tile -> first row                (pair)
@@ -279,8 +280,7 @@ constexpr bool kCluster = NPCD_TC_CLUSTER != 0;
 template <int kMode, bool kF8 = false, bool kTS = false>
 __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
     k_field_tc(const __grid_constant__ Params P) {
-  static_assert(!kTS || ((kMode == MODE_PAIR || kMode == MODE_HEADS) && kF8 && NPCD_TC_2SM == 0),
-                "TS form: inference kernels, f8 scheme, 1-SM");
+  static_assert(!kTS || ((kMode == MODE_PAIR || kMode == MODE_HEADS) && kF8), "TS form: inference kernels, f8 scheme");
   // first layer whose A operand is the previous layer's epilogue output (and therefore, kTS, in tensor memory): layer 1 of the
   // pair MLP; channel_net.2 of the FOLDED heads (layers: shape_net.0', channel_net.0' -- both read the tile image in shared
   // memory --, channel_net.2, .4, .6)
@@ -297,6 +297,10 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
   constexpr bool kHeads = kMode == MODE_HEADS || kMode == MODE_HEADS_TRAIN;
   constexpr bool k2 = two_sm<kMode>();
   constexpr bool kDynAgg = kPro && !k2 && !NPCD_EXP_NOREORDER;  // next tile's layer-0 epilogue interleaved with the aggregation
+  // The input warps (one per scheduler, next to two epilogue warps) pause their gather / positional-encoding arithmetic while a
+  // layer epilogue runs: timeline of the tensor-memory build -- the epilogue that overlapped it took 4 280 cycles instead of 3 050
+  // and the MMAs of the layer behind it waited for operands (5 560 instead of 4 890 cycles per layer).
+  constexpr bool kYield = kDynAgg && !NPCD_EXP_NOYIELD;
   constexpr int kSt = k2 ? kStages2 : kStages;                       // weight-ring stages
   constexpr int kStageBytes = k2 ? kTileBytesW / 2 : kTileBytesW;    // 2-SM: this CTA's half (128 of the 256 output rows) of a tile
   constexpr int kWF = k2 ? kBar2WFull : kBarWFull, kWE = k2 ? kBar2WEmpty : kBarWEmpty;
@@ -331,6 +335,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
     for (int i = 0; i < 2; ++i) { mbar_init(bar(kBarAccRdy + i), 1); mbar_init(bar(kBarAccFree + i), k2 ? 16 : 8); }
     for (int i = 0; i < 4; ++i) mbar_init(bar(kBarStash + i), 1);
     mbar_init(bar(kBarARdy2), k2 ? 16 : 8);
+    *reinterpret_cast<volatile int*>(misc + kOffEpiBusy) = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -505,6 +510,12 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
         }
         if (k2) umma_f8_2sm(d, a, b, kIdescMma, accumulate); else umma_f8(d, a, b, kIdescMma, accumulate);
       };
+      auto mma16ts = [&](uint32_t d, uint32_t a, uint64_t b, uint32_t accumulate) {  // A operand in tensor memory (kTS)
+        if (k2) umma_f16_ts_2sm(d, a, b, kIdescMma, accumulate); else umma_f16_ts(d, a, b, kIdescMma, accumulate);
+      };
+      auto mma8ts = [&](uint32_t d, uint32_t a, uint64_t b, uint32_t accumulate) {
+        if (k2) umma_f8_ts_2sm(d, a, b, kIdescMma, accumulate); else umma_f8_ts(d, a, b, kIdescMma, accumulate);
+      };
       auto commit_stage = [&](int stage) {  // the weight stage may be refilled once the MMAs issued so far have completed
         if (k2) umma_commit_2sm(bar(kWE + stage));
         else if (kCluster) umma_commit_mc(bar(kBarWEmpty + stage), 0x3);
@@ -565,21 +576,21 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
               // [32 h + 16 p, + 16) of the OTHER accumulator buffer: fp16 in the first 8, [lo8 | hi8] in the last 8
               const uint32_t a_t = tmem_base + (ab ^ 1u) * 256u;
               if (elect_one()) {
-                umma_f16_ts(d_tmem, a_t, b, kIdescMma, 0u);
-                umma_f16_ts(d_tmem, a_t + 32u, b + 4, kIdescMma, 1u);
-                umma_f8_ts(d_tmem, a_t + 8u, b2, kIdescMma, 1u);
-                umma_f8_ts(d_tmem, a_t + 40u, b2 + 4, kIdescMma, 1u);
+                mma16ts(d_tmem, a_t, b, 0u);
+                mma16ts(d_tmem, a_t + 32u, b + 4, 1u);
+                mma8ts(d_tmem, a_t + 8u, b2, 1u);
+                mma8ts(d_tmem, a_t + 40u, b2 + 4, 1u);
               }
               __syncwarp();
               timed_wait(bar(kBarARdy2), ph_ar2, tw_a);
               ph_ar2 ^= 1u;
               tc_fence_after();
               if (elect_one()) {
-                umma_f16_ts(d_tmem, a_t + 16u, b + 2, kIdescMma, 1u);
-                umma_f16_ts(d_tmem, a_t + 48u, b + 6, kIdescMma, 1u);
+                mma16ts(d_tmem, a_t + 16u, b + 2, 1u);
+                mma16ts(d_tmem, a_t + 48u, b + 6, 1u);
                 commit_stage(st);
-                umma_f8_ts(d_tmem, a_t + 24u, b2 + 2, kIdescMma, 1u);
-                umma_f8_ts(d_tmem, a_t + 56u, b2 + 6, kIdescMma, 1u);
+                mma8ts(d_tmem, a_t + 24u, b2 + 2, 1u);
+                mma8ts(d_tmem, a_t + 56u, b2 + 6, 1u);
                 commit_stage(st2);
               }
               __syncwarp();
@@ -630,21 +641,23 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
           if (kTS && l >= kTsFirst) {  // K-blocks 1..3 of a tensor-memory operand: four K16 steps on the fp16 stage, four K32 steps on the 8-bit stage
             const uint32_t a_t = tmem_base + (ab ^ 1u) * 256u + 64u * (uint32_t)kb;
             timed_wait(bar(kWF + st), ph_w, tw_w);
+            if (k2) timed_wait(bar(kBar2WPeer + st), ph_w, tw_w);
             tc_fence_after();
             if (elect_one()) {
               const uint64_t b = desc_w0 + (uint64_t)(st * (kStageBytes >> 4));
 #pragma unroll
-              for (int t = 0; t < 4; ++t) umma_f16_ts(d_tmem, a_t + 16u * t, b + 2 * t, kIdescMma, 1u);
+              for (int t = 0; t < 4; ++t) mma16ts(d_tmem, a_t + 16u * t, b + 2 * t, 1u);
               commit_stage(st);
             }
             __syncwarp();
             if (++st == kSt) { st = 0; ph_w ^= 1; }
             timed_wait(bar(kWF + st), ph_w, tw_w);
+            if (k2) timed_wait(bar(kBar2WPeer + st), ph_w, tw_w);
             tc_fence_after();
             if (elect_one()) {
               const uint64_t b = desc_w0 + (uint64_t)(st * (kStageBytes >> 4));
 #pragma unroll
-              for (int t = 0; t < 4; ++t) umma_f8_ts(d_tmem, a_t + 16u * t + 8u, b + 2 * t, kIdescMma, 1u);
+              for (int t = 0; t < 4; ++t) mma8ts(d_tmem, a_t + 16u * t + 8u, b + 2 * t, 1u);
               commit_stage(st);
               if (kb == nkb - 1) commit_cta(kBarAccRdy + ab);
             }
@@ -825,6 +838,14 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
         }
       }
     };
+    // yield to a running layer epilogue (kYield): called between the work units of prepare().  Cannot deadlock: the flag is only
+    // set inside epilogue_store, which never waits for the input warps while they are inside prepare() (the one barrier it shares
+    // with them, the closing barrier of the aggregation's last sum phase, is passed by the input warps BEFORE they enter prepare).
+    auto yield_to_epilogue = [&]() {
+      if (kYield) {
+        while (*reinterpret_cast<volatile int*>(misc + kOffEpiBusy)) __nanosleep(100);
+      }
+    };
     const float kPi = 3.14159274101257324f;
     // input of tile `tile` into K-blocks 0 / 1; wait_free: the K-blocks still hold the previous tile's X_3 until layer 3's MMAs pass
     auto prepare = [&](int tile, int buf, bool wait_free, uint32_t parity) {
@@ -864,16 +885,18 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
       const float nrm = sqrtf(d3[0] * d3[0] + d3[1] * d3[1] + d3[2] * d3[2]);
       wts_all[buf * 128 + row] = live ? 1.0f / (nrm + 1e-5f) : 0.f;
       // ---- K-block 0: [feat 0..31 | x: (sin, cos) of octaves 0..7 | d_x, (sin, cos)_x of octaves 8, 9, d_y, (sin, cos)_y of octaves 0..4]
+      float4 ft[8];  // the point's 32 features: loads in flight while this warp yields
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        ft[j] = live ? __ldg(reinterpret_cast<const float4*>(P.kp_feat + (size_t)idx * 32 + j * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      yield_to_epilogue();
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
-        float y[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (live) {
-          const float4 f0 = __ldg(reinterpret_cast<const float4*>(P.kp_feat + (size_t)idx * 32 + ch * 8));
-          const float4 f1 = __ldg(reinterpret_cast<const float4*>(P.kp_feat + (size_t)idx * 32 + ch * 8 + 4));
-          y[0] = f0.x; y[1] = f0.y; y[2] = f0.z; y[3] = f0.w; y[4] = f1.x; y[5] = f1.y; y[6] = f1.z; y[7] = f1.w;
-        }
+        const float y[8] = {ft[2 * ch].x, ft[2 * ch].y, ft[2 * ch].z, ft[2 * ch].w, ft[2 * ch + 1].x, ft[2 * ch + 1].y, ft[2 * ch + 1].z,
+                            ft[2 * ch + 1].w};
         split_c(y, ch);
       }
+      yield_to_epilogue();
       {
         float v[32];
         octaves(d3[0], kPi, 8, v);
@@ -896,6 +919,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
       for (int c = 0; c < 8; ++c) store_c(0, c, c);
       publish_a0(0);
       // ---- K-block 1: [(sin, cos)_y of octaves 5..9 | z: d, (sin, cos) x 10 | 0]
+      yield_to_epilogue();
       {
         float v[32];
         octaves(d3[1], kPi * 32.0f, 5, v);
@@ -1014,6 +1038,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
       const uint32_t ab = lc & 1u;
       if (et == 0) NPCD_TL(tl_it, 2 * l);
       wait_acc(ab);
+      if (kYield && et == 0) *reinterpret_cast<volatile int*>(misc + kOffEpiBusy) = 1;
       if (et == 0) NPCD_TL(tl_it, 2 * l + 1);
       const float inv = P.layers[l].inv_scale;
       const uint32_t t_acc = t_row + ab * 256u;
@@ -1058,6 +1083,7 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
         if (kTrain) sd_pending |= 1u << i;
         if (i < 3) tmem_wait(v[(i + 1) & 1]);
       }
+      if (kYield && et == 0) *reinterpret_cast<volatile int*>(misc + kOffEpiBusy) = 0;
       ++lc;
     };
     constexpr bool kWhole = false;
@@ -1946,10 +1972,9 @@ extern "C" int npcd_field_tc_fwd(const int* nbr_idx, const float* sample_pos, co
   const int no_wcorr = (stages & 16) ? 1 : 0;  // ... and only the activation-rounding correction is issued ("f16+e4m3")
   NPCD_CHECK_ARG(!no_wcorr || f8, "stages bit 4 (single correction product) needs bit 3 (f16 + e4m3 operands)");
   const bool ts = (stages & 32) != 0;  // W->pair[1..3] were packed with format 2: A operand of those layers in tensor memory
-  NPCD_CHECK_ARG(!ts || (f8 && !no_wcorr && NPCD_TC_2SM == 0),
-                 "stages bit 5 (tensor-memory operand form) needs bit 3, excludes bit 4 and the 2-SM build");
+  NPCD_CHECK_ARG(!ts || (f8 && !no_wcorr), "stages bit 5 (tensor-memory operand form) needs bit 3 and excludes bit 4");
   if (stages & 1) {
-    rc = ts ? pair_stage<tc::MODE_PAIR, true, NPCD_TC_2SM == 0>(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, W, ws, base,
+    rc = ts ? pair_stage<tc::MODE_PAIR, true, true>(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, W, ws, base,
                                                                  nullptr, nullptr, error_flag, num_sms, st, 0)
        : f8 ? pair_stage<tc::MODE_PAIR, true>(nbr_idx, sample_pos, kp_pos, kp_feat, n_samples_dev, capacity, W, ws, base, nullptr, nullptr,
                                               error_flag, num_sms, st, no_wcorr)
@@ -1960,7 +1985,7 @@ extern "C" int npcd_field_tc_fwd(const int* nbr_idx, const float* sample_pos, co
   NPCD_CHECK_ARG(!(stages & 4) || !feat_out, "the folded heads stage has no local_field.8 output to return");
   NPCD_CHECK_ARG(!ts || !(stages & 2), "stages bit 5: the heads stage has a tensor-memory form only with local_field.8 folded (bit 2)");
   if (ts && (stages & 4))  // W->chan[1..3] in format 2
-    rc = heads_stage<tc::MODE_HEADS, true, NPCD_TC_2SM == 0>(W, img, rgbs, feat_out, n_samples_dev, capacity, nullptr, nullptr, error_flag,
+    rc = heads_stage<tc::MODE_HEADS, true, true>(W, img, rgbs, feat_out, n_samples_dev, capacity, nullptr, nullptr, error_flag,
                                                              num_sms, st, true, 0);
   else if (stages & 6)
     rc = f8 ? heads_stage<tc::MODE_HEADS, true>(W, img, rgbs, feat_out, n_samples_dev, capacity, nullptr, nullptr, error_flag, num_sms, st,

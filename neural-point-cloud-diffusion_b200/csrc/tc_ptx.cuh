@@ -178,6 +178,23 @@ __device__ __forceinline__ void umma_f8_ts(uint32_t d_tmem, uint32_t a_tmem, uin
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the same under cta_group::2 (each CTA's rows come from its OWN tensor memory, at the same address)
+__device__ __forceinline__ void umma_f16_ts_2sm(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f8_ts_2sm(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // register -> TMEM store of 16 consecutive 32-bit columns of this thread's lane; complete after tmem_wait_st()
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(
@@ -392,6 +409,9 @@ __device__ __forceinline__ void split8(const float (&y)[8], uint4& hi, uint4& lo
 #endif
 #ifndef NPCD_EXP_NOAGG
 #define NPCD_EXP_NOAGG 0    // timing-only ablation: the aggregation epilogue stages but does not sum / store
+#endif
+#ifndef NPCD_EXP_NOYIELD
+#define NPCD_EXP_NOYIELD 0   // 1: the input warps do not pause while a layer epilogue runs
 #endif
 #ifndef NPCD_EXP_NOREORDER
 #define NPCD_EXP_NOREORDER 0  // 1: the inference pair kernel's epilogue warps finish the aggregation before the next tile's layer 0
