@@ -218,3 +218,32 @@ def test_f8x1_matches_simt_full_size(syn, model, cameras, torch_cuda):
         assert e < 2e-5, (k, e)
     mse = ((ref["channels"] - out["channels"]).double() ** 2).mean().item()
     assert 10 * np.log10(1.0 / max(mse, 1e-30)) > 100.0
+
+
+def test_tensor_memory_operand_form_matches_shared_memory_form(syn, model, cameras, torch_cuda, monkeypatch):
+    """The default inference kernels keep the A operand of pair layers 1..3 and of channel_net.2/.4/.6 in TENSOR MEMORY
+    (`stages` bit 5, weight format 2; `ops.TC_TS`).  Same operand values, same products, only the MMA grouping differs (one K16 f16 +
+    one K32 f8 step per 16 features instead of per-64-column blocks), so against the shared-memory operand form of the same scheme the
+    images agree to fp32-accumulation-order level -- and both sit inside the bar against the fp32 SIMT kernels."""
+    torch = torch_cuda
+    from npcd_b200 import ops
+
+    poses, intr = cameras
+    views = [0, 62, 124, 186]
+    coords, feats = syn.make_clouds([0])
+    args = (_t(torch, coords), _t(torch, feats), _t(torch, poses[views][None]), _t(torch, intr[views][None]), 128, False)
+    model.field.precision = F8
+    with torch.no_grad():
+        model.field.mlp_impl = "simt"
+        ref = model.renderer(*args)
+        model.field.mlp_impl = "tc"
+        monkeypatch.setattr(ops, "TC_TS", True)
+        ts = model.renderer(*args)
+        monkeypatch.setattr(ops, "TC_TS", False)
+        ss = model.renderer(*args)
+    for k in ("mask", "depth", "channels"):
+        e_form = (ts[k] - ss[k]).abs().max().item()
+        e_ts, e_ss = (ref[k] - ts[k]).abs().max().item(), (ref[k] - ss[k]).abs().max().item()
+        print(f"{k}: max |TS - SS| {e_form:.2e}   vs fp32 SIMT: TS {e_ts:.2e}, SS {e_ss:.2e}")
+        assert e_form < 5e-6, (k, e_form)
+        assert e_ts < 2e-5 and e_ss < 2e-5, (k, e_ts, e_ss)
