@@ -1384,19 +1384,31 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
         const float inv = P.layers[l].inv_scale;
         const uint32_t t_acc = t_row + ab * 256u;
         float acc3[3] = {0.f, 0.f, 0.f};
-        uint32_t v[2][32];
-        tmem_ld32_async(t_acc + half * 32, v[0]);
-        tmem_wait(v[0]);
+        // inference: all 128 accumulator columns of the thread go to registers first and the accumulator is released at once -- the
+        // next layer that accumulates into it (after the three-output epilogue: channel_net.0' of the NEXT tile) no longer waits for
+        // the ~6 000 cycles of dot-product arithmetic (352 threads: 184 registers per thread are there)
+        constexpr bool kEarly = kMode == MODE_HEADS && !NPCD_EXP_NOEARLYREL;
+        uint32_t v[kEarly ? 4 : 2][32];
+        if (kEarly) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) tmem_ld32_async(t_acc + (2 * i + half) * 32, v[i]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) tmem_wait(v[i]);
+          release_acc(ab);
+        } else {
+          tmem_ld32_async(t_acc + half * 32, v[0]);
+          tmem_wait(v[0]);
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (i < 3) tmem_ld32_async(t_acc + (2 * (i + 1) + half) * 32, v[(i + 1) & 1]);
+          if (!kEarly && i < 3) tmem_ld32_async(t_acc + (2 * (i + 1) + half) * 32, v[(i + 1) & 1]);
           const int c0 = (2 * i + half) * 32;
           uint32_t mbits = 0u;
           float hp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const float4 b = *reinterpret_cast<const float4*>(&P.bias[l][c0 + g * 4]);
-            const uint32_t* vv = v[i & 1];
+            const uint32_t* vv = v[kEarly ? i : (i & 1)];
             const float h0 = lrelu(fmaf(__uint_as_float(vv[g * 4 + 0]), inv, b.x)), h1 = lrelu(fmaf(__uint_as_float(vv[g * 4 + 1]), inv, b.y)),
                         h2 = lrelu(fmaf(__uint_as_float(vv[g * 4 + 2]), inv, b.z)), h3 = lrelu(fmaf(__uint_as_float(vv[g * 4 + 3]), inv, b.w));
             if (kTrainH) {  // the activated row is an operand of the narrow output layer's weight gradient: stash it as an image
@@ -1425,9 +1437,9 @@ __global__ void NPCD_TC_CLUSTER_DIMS __launch_bounds__(threads_for<kMode>(), 1)
             }
           }
           if (kTrainH) P.hstash_mask[nout == 1 ? 0 : 4][((size_t)tile_now * 128 + row) * 8 + (2 * i + half)] = mbits;
-          if (i < 3) tmem_wait(v[(i + 1) & 1]);
+          if (!kEarly && i < 3) tmem_wait(v[(i + 1) & 1]);
         }
-        release_acc(ab);
+        if (!kEarly) release_acc(ab);
         if (half == 1) { part[row * 4] = acc3[0]; part[row * 4 + 1] = acc3[1]; part[row * 4 + 2] = acc3[2]; }
         epi_bar_sync();
         if (half == 0) {

@@ -410,6 +410,9 @@ __device__ __forceinline__ void split8(const float (&y)[8], uint4& hi, uint4& lo
 #ifndef NPCD_EXP_NOAGG
 #define NPCD_EXP_NOAGG 0    // timing-only ablation: the aggregation epilogue stages but does not sum / store
 #endif
+#ifndef NPCD_EXP_NOEARLYREL
+#define NPCD_EXP_NOEARLYREL 0  // 1: the heads' dot-product epilogues release their accumulator after the arithmetic, not before
+#endif
 #ifndef NPCD_EXP_NOYIELD
 #define NPCD_EXP_NOYIELD 0   // 1: the input warps do not pause while a layer epilogue runs
 #endif
