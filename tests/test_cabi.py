@@ -264,3 +264,17 @@ def test_build_stamp_survives_a_copy_of_the_tree(lib, tmp_path):
     files = sorted(glob.glob(os.path.join(mod.CSRC, "*.cu"))) + sorted(glob.glob(os.path.join(mod.CSRC, "*.cuh"))) + \
         sorted(glob.glob(os.path.join(mod.INCLUDE, "*.h")))
     assert mod._digest(files) == open(os.path.join(pkg, "build", "stamp.txt")).read()
+
+
+def test_operand_scheme_stage_bits(monkeypatch):
+    """`stages` bits of npcd_field_tc_fwd per operand scheme (include/npcd_b200.h): bit 3 = f16 + e4m3 operands, bit 4 = one
+    correction product, bit 5 = tensor-memory operand form (only with the two-correction scheme; NPCD_TC_TS=0 switches it off)."""
+    import npcd_b200  # noqa: F401
+    from npcd_b200 import ops
+
+    assert ops.stage_bits("f16x3") == 0 and ops.stage_bits("f16+e4m3x2") == 8 and ops.stage_bits("f16+e4m3") == 24
+    monkeypatch.setattr(ops, "TC_TS", True)
+    assert ops.pair_stage_bits("f16+e4m3x2") == 8 | 32
+    assert ops.pair_stage_bits("f16+e4m3") == 24 and ops.pair_stage_bits("f16x3") == 0
+    monkeypatch.setattr(ops, "TC_TS", False)
+    assert ops.pair_stage_bits("f16+e4m3x2") == 8
