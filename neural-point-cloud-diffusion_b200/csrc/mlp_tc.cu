@@ -23,6 +23,10 @@
 //                 of the NEXT tile gathers the pair's point, computes the positional encoding and stores the layer-0 operand
 //                 as soon as layer 3's MMAs release K-blocks 0 / 1; the same warps then take a third of the segmented-sum
 //                 tasks of the aggregation epilogue.
+// Inference with the "f16 + e4m3 x 2" operand scheme (tc_ptx.cuh) runs the kTS instantiations: every layer whose A operand is the
+// previous layer's epilogue output reads it from TENSOR MEMORY (the epilogue converts its accumulator in place, see the comment at
+// k_field_tc); shared memory then holds the weight ring, the gathered layer-0 input / the heads' tile image, and the aggregation
+// staging.  The training modes and the "f16x3" / one-correction schemes keep every operand in shared memory as described above.
 // Pair mode packs (sample, neighbour) pairs DENSELY: a tile is a maximal run of whole samples whose pairs fit its 128 rows (greedy,
 // k_tile_walk below: ~125 used rows per tile), instead of 8 slots per sample (21 % padding at 6.3 neighbours per sample).
 // The next tile's gather + positional encoding is computed by the epilogue threads while the tensor pipe works on layers 1..2
